@@ -1,0 +1,289 @@
+"""ctypes wrapper around the CPU oracle (oracle/rz_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product package
+(rusterizer_b200/) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+
+COUNTER_FIELDS = (
+    "n_tris_in", "n_degenerate", "n_outside", "n_inside", "n_clipped_in",
+    "n_tris_setup", "n_bbox_px", "n_covered_px", "n_shaded_px", "n_samples_written",
+    "n_tex_oob", "n_clip_overflow",
+)
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in COUNTER_FIELDS]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n in COUNTER_FIELDS}
+
+
+def build(fast: bool = False, out_dir: os.PathLike | None = None) -> Path:
+    """Compile the oracle with gcc.  fast=True adds -O3 -march=native (timing build; must be
+    compiled on the machine that runs it)."""
+    out_dir = Path(out_dir) if out_dir else _HERE / "_build"
+    out_dir.mkdir(parents=True, exist_ok=True)
+    out = out_dir / ("liboracle_fast.so" if fast else "liboracle.so")
+    src = _HERE / "rz_oracle.c"
+    if out.exists() and out.stat().st_mtime >= src.stat().st_mtime:
+        return out
+    opt = ["-O3", "-march=native"] if fast else ["-O2"]
+    cmd = ["gcc", *opt, "-fPIC", "-shared", "-std=c11", "-ffp-contract=off", "-fno-fast-math",
+           "-o", str(out), str(src), "-lm"]
+    subprocess.run(cmd, check=True)
+    return out
+
+
+def _f32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _u32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+def _u8p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class OracleLib:
+    def __init__(self, path: os.PathLike | None = None, fast: bool = False):
+        self.path = Path(path) if path else build(fast=fast)
+        L = self.lib = C.CDLL(str(self.path))
+        fp, u32p, u8p = C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
+        u64p = C.POINTER(C.c_uint64)
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.c_uint32, C.c_uint32]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_bind_texture.argtypes = [C.c_void_p, C.c_uint32, u8p, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.orc_write_block.argtypes = [C.c_void_p, fp, fp, fp]
+        L.orc_render.argtypes = [C.c_void_p, fp, fp, C.c_uint32, u32p, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.orc_rasterize.argtypes = [C.c_void_p, fp, fp, C.c_uint64, C.c_uint32]
+        L.orc_vertex_stage.argtypes = [C.c_void_p, fp, C.c_uint32, fp]
+        L.orc_framebuffer.restype = u32p
+        L.orc_framebuffer.argtypes = [C.c_void_p]
+        L.orc_depth_samples.restype = fp
+        L.orc_depth_samples.argtypes = [C.c_void_p]
+        L.orc_color_samples.restype = u32p
+        L.orc_color_samples.argtypes = [C.c_void_p]
+        L.orc_owner_samples.restype = u32p
+        L.orc_owner_samples.argtypes = [C.c_void_p]
+        L.orc_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+        L.orc_reset_counters.argtypes = [C.c_void_p]
+        L.orc_mat4_mul.argtypes = [fp, fp, fp]
+        L.orc_mat4_vec.argtypes = [fp, fp, fp]
+        L.orc_triangle_2x_area.restype = C.c_float
+        L.orc_triangle_2x_area.argtypes = [fp]
+        L.orc_to_argb.restype = C.c_uint32
+        L.orc_to_argb.argtypes = [fp]
+        L.orc_box_filter_color.restype = C.c_uint32
+        L.orc_box_filter_color.argtypes = [u32p]
+        L.orc_try_clip.restype = C.c_int
+        L.orc_try_clip.argtypes = [fp, fp, fp, fp, C.c_int]
+        L.orc_perspective_divide.argtypes = [fp, fp]
+        L.orc_pixel_bbox.argtypes = [fp, u64p]
+        L.orc_viewport_setup.argtypes = [C.c_uint32, C.c_uint32, fp, fp, fp, fp, fp, fp]
+        L.orc_eval_pixel.argtypes = [fp, fp, fp, C.c_uint64, C.c_uint64, C.c_uint32, u32p, fp, fp, fp]
+        L.orc_eval_single.restype = C.c_int
+        L.orc_eval_single.argtypes = [fp, C.c_float, C.c_float, fp, fp]
+        L.orc_tex_sample.restype = C.c_uint64
+        L.orc_tex_sample.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, fp]
+        L.orc_tile_grid.argtypes = [C.c_uint32, C.c_uint32, u32p, u32p]
+        L.orc_tile_idx.restype = C.c_uint32
+        L.orc_tile_idx.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+        L.orc_tiles_marked.restype = C.c_uint32
+        L.orc_tiles_marked.argtypes = [C.c_void_p, C.c_int]
+
+    # ---- unit-level helpers (KATs) ----
+    def mat4_mul(self, a, b):
+        a, b = f32(a).reshape(16), f32(b).reshape(16)
+        r = np.empty(16, np.float32)
+        self.lib.orc_mat4_mul(_f32p(a), _f32p(b), _f32p(r))
+        return r.reshape(4, 4)
+
+    def mat4_vec(self, m, v):
+        m, v = f32(m).reshape(16), f32(v).reshape(4)
+        r = np.empty(4, np.float32)
+        self.lib.orc_mat4_vec(_f32p(m), _f32p(v), _f32p(r))
+        return r
+
+    def triangle_2x_area(self, xy):
+        xy = f32(xy).reshape(6)
+        return np.float32(self.lib.orc_triangle_2x_area(_f32p(xy)))
+
+    def to_argb(self, rgba):
+        rgba = f32(rgba).reshape(4)
+        return int(self.lib.orc_to_argb(_f32p(rgba)))
+
+    def box_filter_color(self, colors):
+        c = np.ascontiguousarray(colors, dtype=np.uint32).reshape(4)
+        return int(self.lib.orc_box_filter_color(_u32p(c)))
+
+    def try_clip(self, pos, attrs=None, cap=16):
+        """pos (3,4) clip-space; returns (kind, tris_pos (n,3,4), tris_attrs (n,3,6));
+        kind: 'outside' | 'inside' | 'clipped'."""
+        pos = f32(pos).reshape(12)
+        attrs = f32(np.zeros((3, 6)) if attrs is None else attrs).reshape(18)
+        op = np.zeros(cap * 12, np.float32)
+        oa = np.zeros(cap * 18, np.float32)
+        n = self.lib.orc_try_clip(_f32p(pos), _f32p(attrs), _f32p(op), _f32p(oa), cap)
+        if n < 0:
+            return "outside", op[:0].reshape(0, 3, 4), oa[:0].reshape(0, 3, 6)
+        if n == 0:
+            return "inside", op[:0].reshape(0, 3, 4), oa[:0].reshape(0, 3, 6)
+        return "clipped", op[: n * 12].reshape(n, 3, 4), oa[: n * 18].reshape(n, 3, 6)
+
+    def perspective_divide(self, clip):
+        clip = f32(clip).reshape(12)
+        out = np.empty(12, np.float32)
+        self.lib.orc_perspective_divide(_f32p(clip), _f32p(out))
+        return out.reshape(3, 4)
+
+    def pixel_bbox(self, xy):
+        xy = f32(xy).reshape(6)
+        out = np.zeros(4, np.uint64)
+        self.lib.orc_pixel_bbox(_f32p(xy), out.ctypes.data_as(C.POINTER(C.c_uint64)))
+        return tuple(int(v) for v in out)  # min_x, max_x, min_y, max_y
+
+    def viewport_setup(self, width, height, ndc):
+        ndc = f32(ndc).reshape(12)
+        pts, nrm = np.empty(6, np.float32), np.empty(6, np.float32)
+        z, w, inv = np.empty(3, np.float32), np.empty(3, np.float32), np.empty(1, np.float32)
+        self.lib.orc_viewport_setup(width, height, _f32p(ndc), _f32p(pts), _f32p(nrm), _f32p(z), _f32p(w), _f32p(inv))
+        return dict(points=pts.reshape(3, 2), normals=nrm.reshape(3, 2), depths=z, depths_camera_space=w,
+                    inv_2x_area=inv[0])
+
+    def eval_pixel(self, screen, w, attrs, x, y, interp_mask=0xFF):
+        screen, w, attrs = f32(screen).reshape(9), f32(w).reshape(3), f32(attrs).reshape(18)
+        mask = np.zeros(1, np.uint32)
+        ev, d, a = np.empty(12, np.float32), np.empty(4, np.float32), np.empty(6, np.float32)
+        self.lib.orc_eval_pixel(_f32p(screen), _f32p(w), _f32p(attrs), x, y, interp_mask, _u32p(mask), _f32p(ev),
+                                _f32p(d), _f32p(a))
+        return dict(mask=int(mask[0]), evals=ev.reshape(4, 3), depths=d, attr=a)
+
+    def eval_single(self, screen, x, y):
+        screen = f32(screen).reshape(9)
+        e, n = np.empty(3, np.float32), np.empty(6, np.float32)
+        ins = self.lib.orc_eval_single(_f32p(screen), C.c_float(x), C.c_float(y), _f32p(e), _f32p(n))
+        return bool(ins), e, n.reshape(3, 2)
+
+    def tex_sample(self, texels, u, v):
+        t = np.ascontiguousarray(texels, dtype=np.uint8)
+        h, w, tw = t.shape
+        out = np.empty(4, np.float32)
+        oob = self.lib.orc_tex_sample(_u8p(t), w, h, tw, C.c_float(u), C.c_float(v), _f32p(out))
+        return out, int(oob)
+
+    def tile_grid(self, width, height):
+        a, b = np.zeros(1, np.uint32), np.zeros(1, np.uint32)
+        self.lib.orc_tile_grid(width, height, _u32p(a), _u32p(b))
+        return int(a[0]), int(b[0])
+
+    def tile_idx(self, width, row, col):
+        return int(self.lib.orc_tile_idx(width, row, col))
+
+
+_LIBS: dict = {}
+
+
+def get_lib(fast: bool = False) -> OracleLib:
+    if fast not in _LIBS:
+        _LIBS[fast] = OracleLib(fast=fast)
+    return _LIBS[fast]
+
+
+class OracleRenderer:
+    """The reference's Renderer/Rasterizer surface (render.rs:47-127) on the CPU oracle."""
+
+    def __init__(self, width: int, height: int, lib: OracleLib | None = None):
+        self.L = lib or get_lib()
+        self.width, self.height = width, height
+        self.ctx = self.L.lib.orc_create(width, height)
+        if not self.ctx:
+            raise MemoryError("orc_create failed")
+
+    def close(self):
+        if self.ctx:
+            self.L.lib.orc_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def bind_texture(self, index: int, texels: np.ndarray):
+        t = np.ascontiguousarray(texels, dtype=np.uint8)
+        h, w, tw = t.shape
+        rc = self.L.lib.orc_bind_texture(self.ctx, index, _u8p(t), w, h, tw)
+        if rc != 0:
+            raise ValueError(f"orc_bind_texture failed: {rc}")
+
+    def write_block(self, world=None, view=None, projection=None):
+        arrs = [None if m is None else f32(m).reshape(16) for m in (world, view, projection)]
+        ptrs = [None if a is None else _f32p(a) for a in arrs]
+        self.L.lib.orc_write_block(self.ctx, *ptrs)
+
+    def render(self, pos, attrs, idx, vs_id=0, fs_id=0):
+        pos, attrs = f32(pos).reshape(-1, 3), f32(attrs).reshape(-1, 6)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1)
+        assert pos.shape[0] == attrs.shape[0]
+        rc = self.L.lib.orc_render(self.ctx, _f32p(pos), _f32p(attrs), pos.shape[0], _u32p(idx), idx.size, vs_id, fs_id)
+        if rc != 0:
+            raise RuntimeError(f"orc_render failed: {rc}")
+
+    def rasterize(self, clip_pos, attrs, fs_id=0):
+        clip_pos, attrs = f32(clip_pos).reshape(-1, 3, 4), f32(attrs).reshape(-1, 3, 6)
+        rc = self.L.lib.orc_rasterize(self.ctx, _f32p(clip_pos), _f32p(attrs), clip_pos.shape[0], fs_id)
+        if rc != 0:
+            raise RuntimeError(f"orc_rasterize failed: {rc}")
+
+    def vertex_stage(self, pos):
+        pos = f32(pos).reshape(-1, 3)
+        out = np.empty((pos.shape[0], 4), np.float32)
+        self.L.lib.orc_vertex_stage(self.ctx, _f32p(pos), pos.shape[0], _f32p(out))
+        return out
+
+    def _view(self, ptr, dtype, per_px):
+        n = self.width * self.height * per_px
+        return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype).reshape(self.height, self.width, per_px).copy()
+
+    def depth_samples(self):
+        return self._view(self.L.lib.orc_depth_samples(self.ctx), np.float32, 4)
+
+    def color_samples(self):
+        return self._view(self.L.lib.orc_color_samples(self.ctx), np.uint32, 4)
+
+    def owner_samples(self):
+        return self._view(self.L.lib.orc_owner_samples(self.ctx), np.uint32, 4)
+
+    def framebuffer(self):
+        p = self.L.lib.orc_framebuffer(self.ctx)
+        return np.ctypeslib.as_array(p, shape=(self.height * self.width,)).reshape(self.height, self.width).copy()
+
+    def counters(self):
+        c = Counters()
+        self.L.lib.orc_counters(self.ctx, C.byref(c))
+        return c.as_dict()
+
+    def reset_counters(self):
+        self.L.lib.orc_reset_counters(self.ctx)
+
+    def tiles_marked(self, prev=False):
+        return int(self.L.lib.orc_tiles_marked(self.ctx, 1 if prev else 0))
