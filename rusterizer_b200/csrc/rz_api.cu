@@ -1,0 +1,600 @@
+// rz_api.cu -- C ABI (include/rz.h) and host-side frame orchestration for the sm_100a kernels.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -prec-div=true -prec-sqrt=true
+//        -ftz=false -Xcompiler -ffp-contract=off ... (see __graft_entry__.build()).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rz.h"
+#include "rz_exact.cuh"
+#include "rz_geom.cuh"
+#include "rz_tile.cuh"
+#include "rz_types.cuh"
+
+using namespace rz;
+
+struct rz_mesh {
+    rz_ctx *ctx;
+    float *d_pos = nullptr;
+    float *d_attr = nullptr;
+    uint32_t *d_idx = nullptr;
+    uint32_t nv = 0;
+    uint64_t n_idx = 0;
+    size_t cap_pos = 0, cap_attr = 0, cap_idx = 0; // bytes (staging meshes are reused and grown)
+};
+
+struct DrawCmd {
+    const rz_mesh *mesh;
+    uint32_t fs;
+    float M[16];
+};
+
+struct Texture {
+    uint8_t *d_data = nullptr;
+    uint32_t w = 0, h = 0, tw = 0;
+    size_t len = 0;
+};
+
+struct rz_ctx {
+    int device = 0;
+    uint32_t W = 0, H = 0, tiles_x = 0, tiles_y = 0;
+    uint32_t row_begin = 0, row_end = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    float world[16], view[16], proj[16];
+    std::vector<Texture> textures;
+    std::vector<DrawCmd> draws;
+    std::vector<rz_mesh *> staging; // host-mesh draws of the current frame use staging[k]
+    size_t staging_used = 0;
+
+    // device buffers
+    unsigned char *d_state = nullptr; // FrameState + tile_count[]
+    unsigned long long *d_bins = nullptr;
+    RasterRec *d_recs = nullptr;
+    AttrRec *d_attrs = nullptr;
+    LargeItem *d_large = nullptr;
+    uint32_t *d_out = nullptr;
+    unsigned long long *d_cnt_backup = nullptr;
+    float *d_dbg_depth = nullptr;
+    uint32_t *d_dbg_color = nullptr, *d_dbg_owner = nullptr;
+    uint32_t rec_cap = 0, bin_cap = 0, large_cap = 0;
+    bool debug = false;
+
+    FrameState *h_state = nullptr; // pinned
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    rz_timings_t timings = {0, 0, 0, 0};
+    uint64_t launches = 0;
+    int num_sms = 148;
+    int sticky = RZ_OK;
+    std::string err;
+};
+
+static thread_local std::string g_err;
+
+static int fail(rz_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    g_err = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            if (ctx) (ctx)->sticky = RZ_E_CUDA;                                                         \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? RZ_E_NOMEM : RZ_E_CUDA, "%s: %s", #call, \
+                        cudaGetErrorString(e_));                                                        \
+        }                                                                                               \
+    } while (0)
+
+// Mat4 * Mat4 exactly as math/matrix.rs:56-79 (dot = sequential sum from 0.0, vector.rs:17-23).
+// This file is compiled with -Xcompiler -ffp-contract=off so the host never fuses either.
+static void mat4_mul(const float *A, const float *B, float *R) {
+    float out[16];
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            volatile float s = 0.0f;
+            for (int k = 0; k < 4; k++) {
+                volatile float p = A[i * 4 + k] * B[k * 4 + j];
+                s = s + p;
+            }
+            out[i * 4 + j] = s;
+        }
+    memcpy(R, out, sizeof out);
+}
+
+static size_t state_bytes(const rz_ctx *c) { return sizeof(FrameState) + sizeof(uint32_t) * (size_t)c->tiles_x * c->tiles_y; }
+
+static int free_frame_buffers(rz_ctx *c) {
+    cudaFree(c->d_bins); c->d_bins = nullptr;
+    cudaFree(c->d_recs); c->d_recs = nullptr;
+    cudaFree(c->d_attrs); c->d_attrs = nullptr;
+    cudaFree(c->d_large); c->d_large = nullptr;
+    return RZ_OK;
+}
+
+static int ensure_capacity(rz_ctx *c, uint32_t rec_cap, uint32_t bin_cap, uint32_t large_cap) {
+    const size_t tiles = (size_t)c->tiles_x * c->tiles_y;
+    if (bin_cap > c->bin_cap) {
+        cudaFree(c->d_bins); c->d_bins = nullptr;
+        CU(c, cudaMalloc(&c->d_bins, tiles * bin_cap * sizeof(unsigned long long)));
+        c->bin_cap = bin_cap;
+    }
+    if (rec_cap > c->rec_cap) {
+        cudaFree(c->d_recs); c->d_recs = nullptr;
+        cudaFree(c->d_attrs); c->d_attrs = nullptr;
+        CU(c, cudaMalloc(&c->d_recs, (size_t)rec_cap * sizeof(RasterRec)));
+        CU(c, cudaMalloc(&c->d_attrs, (size_t)rec_cap * sizeof(AttrRec)));
+        c->rec_cap = rec_cap;
+    }
+    if (large_cap > c->large_cap) {
+        cudaFree(c->d_large); c->d_large = nullptr;
+        CU(c, cudaMalloc(&c->d_large, (size_t)large_cap * sizeof(LargeItem)));
+        c->large_cap = large_cap;
+    }
+    return RZ_OK;
+}
+
+extern "C" {
+
+const char *rz_version(void) { return "rusterizer_b200 0.1 (sm_100a)"; }
+uint32_t rz_tile_width(void) { return TW; }
+uint32_t rz_tile_height(void) { return TH; }
+
+const char *rz_last_error(rz_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int rz_create(int device, uint32_t width, uint32_t height, rz_ctx **out) {
+    if (!out || width == 0 || height == 0 || width > 65535u || height > 65535u)
+        return fail(nullptr, RZ_E_INVALID, "rz_create: bad arguments (width/height must be 1..65535)");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, RZ_E_NO_DEVICE, "rz_create: no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(nullptr, RZ_E_NO_DEVICE, "rz_create: device %d out of range", device);
+    rz_ctx *c = new (std::nothrow) rz_ctx();
+    if (!c) return fail(nullptr, RZ_E_NOMEM, "rz_create: out of host memory");
+    c->device = device;
+    c->W = width; c->H = height;
+    c->tiles_x = (width + TW - 1) / TW;
+    c->tiles_y = (height + TH - 1) / TH;
+    c->row_begin = 0; c->row_end = height;
+    static const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}; // uniform.rs:18-27
+    memcpy(c->world, ident, 64); memcpy(c->view, ident, 64); memcpy(c->proj, ident, 64);
+#define CU_NEW(call)                                                                       \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            int rc_ = fail(nullptr, RZ_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_));  \
+            rz_destroy(c);                                                                 \
+            return rc_;                                                                    \
+        }                                                                                  \
+    } while (0)
+    CU_NEW(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_NEW(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    CU_NEW(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CU_NEW(cudaMalloc(&c->d_state, state_bytes(c)));
+    CU_NEW(cudaMemset(c->d_state, 0, state_bytes(c)));
+    CU_NEW(cudaMalloc(&c->d_out, (size_t)width * height * sizeof(uint32_t)));
+    CU_NEW(cudaMalloc(&c->d_cnt_backup, sizeof(unsigned long long) * 16));
+    CU_NEW(cudaHostAlloc(&c->h_state, sizeof(FrameState), cudaHostAllocDefault));
+    for (int i = 0; i < 4; i++) CU_NEW(cudaEventCreate(&c->ev[i]));
+    CU_NEW(cudaFuncSetAttribute(tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+    CU_NEW(cudaFuncSetAttribute(tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+#undef CU_NEW
+    *out = c;
+    return RZ_OK;
+}
+
+void rz_destroy(rz_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_frame_buffers(c);
+    cudaFree(c->d_state); cudaFree(c->d_out); cudaFree(c->d_cnt_backup);
+    cudaFree(c->d_dbg_depth); cudaFree(c->d_dbg_color); cudaFree(c->d_dbg_owner);
+    for (auto &t : c->textures) cudaFree(t.d_data);
+    for (auto *m : c->staging) rz_mesh_destroy(m);
+    if (c->h_state) cudaFreeHost(c->h_state);
+    for (int i = 0; i < 4; i++)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int rz_set_stream(rz_ctx *c, void *cuda_stream) {
+    if (!c) return RZ_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return RZ_OK;
+}
+
+int rz_bind_texture(rz_ctx *c, uint32_t index, const uint8_t *texels, uint32_t width, uint32_t height,
+                    uint32_t texel_width) {
+    if (!c || !texels || width == 0 || height == 0) return fail(c, RZ_E_INVALID, "rz_bind_texture: bad arguments");
+    if (texel_width != 3 && texel_width != 4)
+        return fail(c, RZ_E_INVALID, "rz_bind_texture: texel_width must be 3 or 4 (texture.rs:48)");
+    if (index != c->textures.size())
+        return fail(c, RZ_E_TEXTURE, "rz_bind_texture: index %u != number of bound textures %zu (uniform.rs:31)", index,
+                    c->textures.size());
+    CU(c, cudaSetDevice(c->device));
+    Texture t;
+    t.w = width; t.h = height; t.tw = texel_width;
+    t.len = (size_t)width * height * texel_width;
+    CU(c, cudaMalloc(&t.d_data, t.len));
+    CU(c, cudaMemcpyAsync(t.d_data, texels, t.len, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->textures.push_back(t);
+    return RZ_OK;
+}
+
+int rz_write_block(rz_ctx *c, const float *world, const float *view, const float *projection) {
+    if (!c) return RZ_E_INVALID;
+    if (world) memcpy(c->world, world, 64);
+    if (view) memcpy(c->view, view, 64);
+    if (projection) memcpy(c->proj, projection, 64);
+    return RZ_OK;
+}
+
+int rz_read_block(rz_ctx *c, float *world, float *view, float *projection) {
+    if (!c) return RZ_E_INVALID;
+    if (world) memcpy(world, c->world, 64);
+    if (view) memcpy(view, c->view, 64);
+    if (projection) memcpy(projection, c->proj, 64);
+    return RZ_OK;
+}
+
+static int mesh_upload(rz_ctx *c, rz_mesh *m, const float *pos, const float *attr, uint32_t nv, const uint32_t *idx,
+                       uint64_t n_idx) {
+    const size_t bp = (size_t)nv * 12, ba = (size_t)nv * 24, bi = (size_t)n_idx * 4;
+    if (bp > m->cap_pos) { cudaFree(m->d_pos); m->d_pos = nullptr; m->cap_pos = 0; CU(c, cudaMalloc(&m->d_pos, bp)); m->cap_pos = bp; }
+    if (ba > m->cap_attr) { cudaFree(m->d_attr); m->d_attr = nullptr; m->cap_attr = 0; CU(c, cudaMalloc(&m->d_attr, ba)); m->cap_attr = ba; }
+    if (bi > m->cap_idx) { cudaFree(m->d_idx); m->d_idx = nullptr; m->cap_idx = 0; CU(c, cudaMalloc(&m->d_idx, bi)); m->cap_idx = bi; }
+    if (bp) CU(c, cudaMemcpyAsync(m->d_pos, pos, bp, cudaMemcpyHostToDevice, c->stream));
+    if (ba) CU(c, cudaMemcpyAsync(m->d_attr, attr, ba, cudaMemcpyHostToDevice, c->stream));
+    if (bi) CU(c, cudaMemcpyAsync(m->d_idx, idx, bi, cudaMemcpyHostToDevice, c->stream));
+    m->nv = nv;
+    m->n_idx = n_idx;
+    return RZ_OK;
+}
+
+int rz_mesh_create(rz_ctx *c, const float *positions, const float *attributes, uint32_t nv, const uint32_t *indices,
+                   uint64_t n_idx, rz_mesh **out) {
+    if (!c || !out) return RZ_E_INVALID;
+    *out = nullptr;
+    if ((nv && (!positions || !attributes)) || (n_idx && !indices) || n_idx % 3 != 0 || n_idx / 3 > 0x1FFFFFFFull)
+        return fail(c, RZ_E_INVALID, "rz_mesh_create: bad arguments (n_idx must be a multiple of 3, < 2^29 triangles)");
+    CU(c, cudaSetDevice(c->device));
+    rz_mesh *m = new (std::nothrow) rz_mesh();
+    if (!m) return fail(c, RZ_E_NOMEM, "rz_mesh_create: out of host memory");
+    m->ctx = c;
+    int rc = mesh_upload(c, m, positions, attributes, nv, indices, n_idx);
+    if (rc == RZ_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(c, RZ_E_CUDA, "rz_mesh_create: sync failed");
+    if (rc != RZ_OK) {
+        rz_mesh_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return RZ_OK;
+}
+
+void rz_mesh_destroy(rz_mesh *m) {
+    if (!m) return;
+    if (m->ctx) cudaSetDevice(m->ctx->device);
+    cudaFree(m->d_pos); cudaFree(m->d_attr); cudaFree(m->d_idx);
+    delete m;
+}
+
+static int record_draw(rz_ctx *c, const rz_mesh *mesh, uint32_t vs_id, uint32_t fs_id) {
+    if (vs_id != RZ_VS_MVP) return fail(c, RZ_E_INVALID, "rz_render: unknown vertex shader id %u", vs_id);
+    if (fs_id > RZ_FS_DEBUG) return fail(c, RZ_E_INVALID, "rz_render: unknown fragment shader id %u", fs_id);
+    if (fs_id == RZ_FS_TEXTURE && c->textures.empty())
+        return fail(c, RZ_E_TEXTURE, "rz_render: FS Texture needs texture 0 bound (uniform.rs:36)");
+    DrawCmd d;
+    d.mesh = mesh;
+    d.fs = fs_id;
+    float pv[16];
+    mat4_mul(c->proj, c->view, pv);   // projection * view
+    mat4_mul(pv, c->world, d.M);      // (projection * view) * world   (main.rs:147-152, left-assoc)
+    c->draws.push_back(d);
+    return RZ_OK;
+}
+
+int rz_render(rz_ctx *c, const rz_mesh *mesh, uint32_t vs_id, uint32_t fs_id) {
+    if (!c || !mesh) return RZ_E_INVALID;
+    if (mesh->ctx != c) return fail(c, RZ_E_INVALID, "rz_render: mesh belongs to another ctx");
+    return record_draw(c, mesh, vs_id, fs_id);
+}
+
+int rz_render_host(rz_ctx *c, const float *positions, const float *attributes, uint32_t nv, const uint32_t *indices,
+                   uint64_t n_idx, uint32_t vs_id, uint32_t fs_id) {
+    if (!c) return RZ_E_INVALID;
+    if ((nv && (!positions || !attributes)) || (n_idx && !indices) || n_idx % 3 != 0 || n_idx / 3 > 0x1FFFFFFFull)
+        return fail(c, RZ_E_INVALID, "rz_render_host: bad arguments");
+    CU(c, cudaSetDevice(c->device));
+    if (c->staging_used == c->staging.size()) {
+        rz_mesh *m = new (std::nothrow) rz_mesh();
+        if (!m) return fail(c, RZ_E_NOMEM, "rz_render_host: out of host memory");
+        m->ctx = c;
+        c->staging.push_back(m);
+    }
+    rz_mesh *m = c->staging[c->staging_used];
+    int rc = mesh_upload(c, m, positions, attributes, nv, indices, n_idx);
+    if (rc != RZ_OK) return rc;
+    rc = record_draw(c, m, vs_id, fs_id);
+    if (rc == RZ_OK) c->staging_used++;
+    return rc;
+}
+
+static FrameParams make_params(rz_ctx *c, uint32_t *out_base) {
+    FrameParams P;
+    memset(&P, 0, sizeof P);
+    P.W = c->W; P.H = c->H;
+    P.tiles_x = c->tiles_x; P.tiles_y = c->tiles_y;
+    P.row_begin = c->row_begin; P.row_end = c->row_end;
+    P.ty_begin = c->row_begin / TH;
+    P.ty_end = (c->row_end + TH - 1) / TH;
+    P.rec_cap = c->rec_cap; P.bin_cap = c->bin_cap; P.large_cap = c->large_cap;
+    P.fs = reinterpret_cast<FrameState *>(c->d_state);
+    P.tile_count = reinterpret_cast<uint32_t *>(c->d_state + sizeof(FrameState));
+    P.bins = c->d_bins; P.recs = c->d_recs; P.attrs = c->d_attrs; P.large = c->d_large;
+    P.out = out_base;
+    if (c->debug) {
+        P.dbg_depth = c->d_dbg_depth; P.dbg_color = c->d_dbg_color; P.dbg_owner = c->d_dbg_owner;
+    }
+    if (!c->textures.empty()) {
+        const Texture &t = c->textures[0];
+        P.tex0.data = t.d_data; P.tex0.len = t.len; P.tex0.w = t.w; P.tex0.h = t.h; P.tex0.tw = t.tw; P.tex0.bound = 1;
+    }
+    return P;
+}
+
+// Enqueue one whole frame on the ctx stream.  timed: record stage events.
+static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
+    uint64_t total_tris = 0;
+    for (auto &d : c->draws) total_tris += d.mesh->n_idx / 3;
+    if (total_tris > 0x1FFFFFFFull) return fail(c, RZ_E_INVALID, "frame has more than 2^29 triangles");
+    {
+        uint32_t want_rec = std::max<uint64_t>(c->rec_cap, total_tris + 1024);
+        uint32_t want_bin = std::max<uint32_t>(c->bin_cap, 256u);
+        uint32_t want_large = std::max<uint32_t>(c->large_cap, 1u << 16);
+        int rc = ensure_capacity(c, want_rec, want_bin, want_large);
+        if (rc != RZ_OK) return rc;
+    }
+    FrameParams P = make_params(c, out_base);
+    cudaStream_t st = c->stream;
+    const size_t off = offsetof(FrameState, n_records);
+    CU(c, cudaMemsetAsync(c->d_state + off, 0, state_bytes(c) - off, st));
+    if (timed) CU(c, cudaEventRecord(c->ev[0], st));
+    uint32_t tri_base = 0;
+    for (auto &d : c->draws) {
+        const uint32_t nt = (uint32_t)(d.mesh->n_idx / 3);
+        if (nt == 0) continue;
+        DrawParams D;
+        D.pos = d.mesh->d_pos; D.attr = d.mesh->d_attr; D.idx = d.mesh->d_idx;
+        D.nv = d.mesh->nv; D.nt = nt; D.tri_base = tri_base; D.fs = d.fs;
+        memcpy(D.M, d.M, 64);
+        geom_kernel<<<(nt + NT - 1) / NT, NT, 0, st>>>(P, D);
+        c->launches++;
+        tri_base += nt;
+    }
+    if (timed) CU(c, cudaEventRecord(c->ev[1], st));
+    large_bin_kernel<<<c->num_sms * 2, NT, 0, st>>>(P);
+    c->launches++;
+    if (timed) CU(c, cudaEventRecord(c->ev[2], st));
+    const uint32_t n_tiles = P.tiles_x * (P.ty_end - P.ty_begin);
+    if (n_tiles) {
+        if (c->debug)
+            tile_kernel<true><<<n_tiles, NT, sizeof(TileSmem), st>>>(P);
+        else
+            tile_kernel<false><<<n_tiles, NT, sizeof(TileSmem), st>>>(P);
+        c->launches++;
+    }
+    if (timed) CU(c, cudaEventRecord(c->ev[3], st));
+    CU(c, cudaGetLastError());
+    return RZ_OK;
+}
+
+static void end_frame(rz_ctx *c) {
+    c->draws.clear();
+    c->staging_used = 0;
+}
+
+static int map_err_flags(rz_ctx *c, uint32_t flags) {
+    if (flags & ERR_INDEX) return fail(c, RZ_E_INDEX, "a mesh index is >= nv (the reference panics at render.rs:83-87)");
+    if (flags & (ERR_REC_OVF | ERR_BIN_OVF | ERR_LARGE_OVF))
+        return fail(c, RZ_E_CAPACITY, "an async frame outgrew its device buffers (flags 0x%x); re-issue via rz_framebuffer()", flags);
+    return RZ_OK;
+}
+
+int rz_framebuffer(rz_ctx *c, uint32_t *out_host, const uint32_t **out_device) {
+    if (!c) return RZ_E_INVALID;
+    if (c->sticky != RZ_OK) return c->sticky;
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    FrameState *dfs = reinterpret_cast<FrameState *>(c->d_state);
+    // surface errors of earlier async frames first
+    CU(c, cudaMemcpyAsync(c->h_state, dfs, sizeof(FrameState), cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    if (c->h_state->err) {
+        uint32_t flags = c->h_state->err;
+        CU(c, cudaMemsetAsync(&dfs->err, 0, sizeof(uint32_t), st));
+        end_frame(c);
+        return map_err_flags(c, flags);
+    }
+    CU(c, cudaMemcpyAsync(c->d_cnt_backup, dfs->counters, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToDevice, st));
+    int rc = RZ_OK;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        rc = enqueue_frame(c, c->d_out, true);
+        if (rc != RZ_OK) break;
+        CU(c, cudaMemcpyAsync(c->h_state, dfs, sizeof(FrameState), cudaMemcpyDeviceToHost, st));
+        CU(c, cudaStreamSynchronize(st));
+        const uint32_t flags = c->h_state->err;
+        if (!flags) break;
+        CU(c, cudaMemsetAsync(&dfs->err, 0, sizeof(uint32_t), st));
+        if (flags & ERR_INDEX) {
+            rc = map_err_flags(c, flags);
+            break;
+        }
+        // grow what overflowed (the cursors kept counting past the capacity) and replay the frame
+        CU(c, cudaMemcpyAsync(dfs->counters, c->d_cnt_backup, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToDevice, st));
+        uint32_t want_rec = c->rec_cap, want_bin = c->bin_cap, want_large = c->large_cap;
+        if (flags & ERR_REC_OVF) want_rec = std::max<uint64_t>((uint64_t)c->h_state->n_records * 5 / 4 + 1024, (uint64_t)c->rec_cap * 2);
+        if (flags & ERR_LARGE_OVF) want_large = std::max<uint64_t>((uint64_t)c->h_state->n_large * 5 / 4 + 1024, (uint64_t)c->large_cap * 2);
+        if (flags & ERR_BIN_OVF) {
+            std::vector<uint32_t> counts((size_t)c->tiles_x * c->tiles_y);
+            CU(c, cudaMemcpyAsync(counts.data(), c->d_state + sizeof(FrameState), counts.size() * 4, cudaMemcpyDeviceToHost, st));
+            CU(c, cudaStreamSynchronize(st));
+            uint32_t mx = 0;
+            for (uint32_t v : counts) mx = std::max(mx, v);
+            want_bin = std::max<uint64_t>((uint64_t)mx * 5 / 4 + 64, (uint64_t)c->bin_cap * 2);
+            const size_t bytes = (size_t)c->tiles_x * c->tiles_y * want_bin * 8;
+            if (bytes > ((size_t)64 << 30)) {
+                rc = fail(c, RZ_E_NOMEM, "a screen tile holds %u triangles; its bin would need %zu bytes", mx, bytes);
+                break;
+            }
+        }
+        rc = ensure_capacity(c, want_rec, want_bin, want_large);
+        if (rc != RZ_OK) break;
+        if (attempt == 7) rc = fail(c, RZ_E_CAPACITY, "frame still overflows after 8 growth attempts");
+    }
+    end_frame(c);
+    if (rc != RZ_OK) return rc;
+    float ms;
+    if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->timings.geometry_ms = ms;
+    if (cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]) == cudaSuccess) c->timings.bin_ms = ms;
+    if (cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->timings.tile_ms = ms;
+    if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]) == cudaSuccess) c->timings.total_ms = ms;
+    if (out_host) {
+        CU(c, cudaMemcpyAsync(out_host, c->d_out, (size_t)c->W * c->H * 4, cudaMemcpyDeviceToHost, st));
+        CU(c, cudaStreamSynchronize(st));
+    }
+    if (out_device) *out_device = c->d_out;
+    return RZ_OK;
+}
+
+int rz_framebuffer_async(rz_ctx *c, uint32_t *device_dst, const uint32_t **out_device) {
+    if (!c) return RZ_E_INVALID;
+    if (c->sticky != RZ_OK) return c->sticky;
+    CU(c, cudaSetDevice(c->device));
+    // an external destination holds only this ctx's rows [row_begin,row_end), starting at device_dst
+    uint32_t *base = device_dst ? device_dst - (size_t)c->row_begin * c->W : c->d_out;
+    int rc = enqueue_frame(c, base, false);
+    end_frame(c);
+    if (rc != RZ_OK) return rc;
+    if (out_device) *out_device = device_dst ? device_dst : c->d_out;
+    return RZ_OK;
+}
+
+int rz_sync(rz_ctx *c) {
+    if (!c) return RZ_E_INVALID;
+    if (c->sticky != RZ_OK) return c->sticky;
+    CU(c, cudaSetDevice(c->device));
+    FrameState *dfs = reinterpret_cast<FrameState *>(c->d_state);
+    CU(c, cudaMemcpyAsync(c->h_state, dfs, sizeof(FrameState), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (c->h_state->err) {
+        const uint32_t flags = c->h_state->err;
+        CU(c, cudaMemsetAsync(&dfs->err, 0, sizeof(uint32_t), c->stream));
+        return map_err_flags(c, flags);
+    }
+    return RZ_OK;
+}
+
+int rz_set_row_range(rz_ctx *c, uint32_t row_begin, uint32_t row_end) {
+    if (!c) return RZ_E_INVALID;
+    if (row_begin >= row_end || row_end > c->H || row_begin % TH != 0 || (row_end % TH != 0 && row_end != c->H))
+        return fail(c, RZ_E_INVALID, "rz_set_row_range: rows must be tile-aligned (%d) and inside the framebuffer", TH);
+    c->row_begin = row_begin;
+    c->row_end = row_end;
+    return RZ_OK;
+}
+
+int rz_counters(rz_ctx *c, rz_counters_t *out) {
+    if (!c || !out) return RZ_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(FrameState), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    const unsigned long long *k = c->h_state->counters;
+    out->n_tris_in = k[C_TRIS_IN]; out->n_degenerate = k[C_DEGENERATE]; out->n_outside = k[C_OUTSIDE];
+    out->n_inside = k[C_INSIDE]; out->n_clipped_in = k[C_CLIPPED_IN]; out->n_tris_setup = k[C_TRIS_SETUP];
+    out->n_bbox_px = k[C_BBOX_PX]; out->n_covered_px = k[C_COVERED_PX]; out->n_shaded_px = k[C_SHADED_PX];
+    out->n_samples_written = k[C_SAMPLES]; out->n_tex_oob = k[C_TEX_OOB]; out->n_clip_overflow = k[C_CLIP_OVF];
+    return RZ_OK;
+}
+
+int rz_reset_counters(rz_ctx *c) {
+    if (!c) return RZ_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemsetAsync(c->d_state, 0, sizeof(unsigned long long) * 16, c->stream));
+    return RZ_OK;
+}
+
+int rz_timings(rz_ctx *c, rz_timings_t *out) {
+    if (!c || !out) return RZ_E_INVALID;
+    *out = c->timings;
+    return RZ_OK;
+}
+
+uint64_t rz_launch_count(rz_ctx *c) { return c ? c->launches : 0; }
+
+int rz_debug_capture(rz_ctx *c, int enable) {
+    if (!c) return RZ_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    if (enable && !c->d_dbg_depth) {
+        const size_t n = (size_t)c->W * c->H * 4;
+        CU(c, cudaMalloc(&c->d_dbg_depth, n * 4));
+        CU(c, cudaMalloc(&c->d_dbg_color, n * 4));
+        CU(c, cudaMalloc(&c->d_dbg_owner, n * 4));
+    }
+    c->debug = enable != 0;
+    return RZ_OK;
+}
+
+int rz_debug_read(rz_ctx *c, float *depth, uint32_t *color, uint32_t *owner) {
+    if (!c) return RZ_E_INVALID;
+    if (!c->d_dbg_depth) return fail(c, RZ_E_INVALID, "rz_debug_read: capture was never enabled");
+    CU(c, cudaSetDevice(c->device));
+    const size_t bytes = (size_t)c->W * c->H * 16;
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (depth) CU(c, cudaMemcpy(depth, c->d_dbg_depth, bytes, cudaMemcpyDeviceToHost));
+    if (color) CU(c, cudaMemcpy(color, c->d_dbg_color, bytes, cudaMemcpyDeviceToHost));
+    if (owner) CU(c, cudaMemcpy(owner, c->d_dbg_owner, bytes, cudaMemcpyDeviceToHost));
+    return RZ_OK;
+}
+
+int rz_debug_vertex_stage(rz_ctx *c, const rz_mesh *mesh, float *out_clip) {
+    if (!c || !mesh || !out_clip) return RZ_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    if (mesh->nv == 0) return RZ_OK;
+    DrawParams D;
+    memset(&D, 0, sizeof D);
+    float pv[16];
+    mat4_mul(c->proj, c->view, pv);
+    mat4_mul(pv, c->world, D.M);
+    float4 *d_out = nullptr;
+    CU(c, cudaMalloc(&d_out, (size_t)mesh->nv * 16));
+    vertex_kernel<<<(mesh->nv + NT - 1) / NT, NT, 0, c->stream>>>(mesh->d_pos, mesh->nv, D, d_out);
+    c->launches++;
+    cudaError_t e = cudaMemcpyAsync(out_clip, d_out, (size_t)mesh->nv * 16, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(c, RZ_E_CUDA, "rz_debug_vertex_stage: %s", cudaGetErrorString(e));
+    return RZ_OK;
+}
+
+} // extern "C"

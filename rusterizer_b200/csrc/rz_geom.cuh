@@ -1,0 +1,321 @@
+// rz_geom.cuh -- stage 1+2: vertex transform, clip, triangle reconstruction, setup, binning.
+//
+// One thread per input triangle (Renderer::render + the front half of Rasterizer::rasterize,
+// render.rs:98-114, rasterizer/mod.rs:425-441).  Surviving triangles are compacted into the
+// record arrays with a warp-aggregated atomic (ballot + popc prefix), tagged with their
+// submission-order key, and binned into 16x16 screen tiles.  Small triangles are rasterised
+// exactly right here so that triangles covering no sample never reach a tile list; large ones
+// are queued for the cooperative binning kernel below.
+#pragma once
+#include "rz_exact.cuh"
+#include "rz_types.cuh"
+
+namespace rz {
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// Warp-aggregated "allocate one slot" (stream compaction by ballot/prefix): the converged lanes
+// elect a leader that bumps the global cursor once; every lane gets base + its rank.
+__device__ __forceinline__ uint32_t alloc_slot(uint32_t *cursor) {
+    unsigned m = __activemask();
+    int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(cursor, (uint32_t)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + __popc(m & lanemask_lt());
+}
+
+__device__ __forceinline__ void push_bin(const FrameParams &P, uint32_t tile, uint32_t key, uint32_t rec) {
+    uint32_t slot = atomicAdd(&P.tile_count[tile], 1u);
+    if (slot < P.bin_cap)
+        P.bins[(size_t)tile * P.bin_cap + slot] = ((unsigned long long)key << 32) | rec;
+    else
+        atomicOr(&P.fs->err, ERR_BIN_OVF);
+}
+
+struct GeomLocal {
+    uint32_t c[C_COUNT];
+    unsigned long long bbox;
+};
+
+// Rasterizer::perspective_divide + viewport_transform + RasterizerTriangle::new + bounding_box
+// (rasterizer/mod.rs:284-361) for one clip-space triangle, then cull / record / bin.
+// a0,a1,a2 point at the three VertexAttributes (6 floats each; global or local memory).
+__device__ __forceinline__ void emit_triangle(const FrameParams &P, uint32_t fs_id, const float *c0, const float *c1,
+                                              const float *c2, const float *a0, const float *a1, const float *a2,
+                                              uint32_t key, GeomLocal &lc) {
+    Setup s;
+    const float Wf = (float)P.W, Hf = (float)P.H;
+    const float *cv[3] = {c0, c1, c2};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float w = cv[i][3];
+        float nx = fdiv(cv[i][0], w), ny = fdiv(cv[i][1], w), nz = fdiv(cv[i][2], w);
+        s.px[i] = fdiv(fmul(Wf, fadd(nx, 1.0f)), 2.0f);
+        s.py[i] = fmul(Hf, fsub(1.0f, fdiv(fadd(ny, 1.0f), 2.0f)));
+        s.z[i] = fadd(fmul(fmul(fadd(nz, 1.0f), 0.5f), 1.0f), 0.0f); // (z+1)*0.5*(zmax-zmin)+zmin
+        s.w[i] = w;
+    }
+    setup_edges(s);
+    lc.c[C_TRIS_SETUP]++;
+
+    BBox b = pixel_bbox(s, P.W, P.H);
+    b.y0 = max(b.y0, P.row_begin); // screen-space shard owned by this ctx
+    b.y1 = min(b.y1, P.row_end);
+    if (b.x0 >= b.x1 || b.y0 >= b.y1) return;
+    const uint32_t bw = b.x1 - b.x0, bh = b.y1 - b.y0;
+    lc.bbox += (unsigned long long)bw * bh;
+
+    const bool small = bw <= GEOM_SMALL_DIM && bh <= GEOM_SMALL_DIM && bw * bh <= GEOM_SMALL_PX;
+    const uint32_t tx0 = b.x0 / TW, ty0 = b.y0 / TH;
+    uint32_t tmask = 0;
+    if (small) {
+        // exact coverage over the whole bbox: which of the <= 2x2 tiles see a covered sample?
+        for (uint32_t Y = b.y0; Y < b.y1; Y++)
+            for (uint32_t X = b.x0; X < b.x1; X++)
+                if (coverage_mask(s, (int)X, (int)Y)) tmask |= 1u << (((Y / TH - ty0) << 1) | (X / TW - tx0));
+        if (!tmask) return; // touches no sample: contributes nothing (the bbox pixels are already counted)
+    }
+
+    const uint32_t rec = alloc_slot(&P.fs->n_records);
+    if (rec >= P.rec_cap) {
+        atomicOr(&P.fs->err, ERR_REC_OVF);
+        return;
+    }
+    float4 *rr = reinterpret_cast<float4 *>(&P.recs[rec]);
+    rr[0] = make_float4(s.px[0], s.py[0], s.px[1], s.py[1]);
+    rr[1] = make_float4(s.px[2], s.py[2], s.z[0], s.z[1]);
+    rr[2] = make_float4(s.z[2], s.w[0], s.w[1], s.w[2]);
+    rr[3] = make_float4(__uint_as_float(key), __uint_as_float(fs_id), 0.0f, 0.0f);
+    float4 *ar = reinterpret_cast<float4 *>(&P.attrs[rec]);
+    ar[0] = make_float4(a0[0], a0[1], a0[2], a0[3]);
+    ar[1] = make_float4(a0[4], a0[5], a1[0], a1[1]);
+    ar[2] = make_float4(a1[2], a1[3], a1[4], a1[5]);
+    ar[3] = make_float4(a2[0], a2[1], a2[2], a2[3]);
+    ar[4] = make_float4(a2[4], a2[5], 0.0f, 0.0f);
+
+    if (small) {
+#pragma unroll
+        for (uint32_t q = 0; q < 4; q++)
+            if ((tmask >> q) & 1u) push_bin(P, (ty0 + (q >> 1)) * P.tiles_x + tx0 + (q & 1u), key, rec);
+    } else {
+        const uint32_t tyB = (b.y1 - 1) / TH + 1;
+        for (uint32_t ty = ty0; ty < tyB; ty += LARGE_SLAB_ROWS) {
+            uint32_t li = atomicAdd(&P.fs->n_large, 1u);
+            if (li < P.large_cap) {
+                LargeItem it;
+                it.rec = rec; it.key = key; it.ty0 = ty; it.ty1 = min(ty + (uint32_t)LARGE_SLAB_ROWS, tyB);
+                P.large[li] = it;
+            } else {
+                atomicOr(&P.fs->err, ERR_LARGE_OVF);
+            }
+        }
+    }
+}
+
+// clipping::distance_measure (rasterizer/clipping.rs:29-38); planes in CLIP_PLANES order (53-60)
+__device__ __forceinline__ float clip_distance(int plane, const float *p) {
+    float c = p[plane >> 1];
+    return (plane & 1) ? fsub(p[3], c) : fadd(p[3], c);
+}
+
+__global__ void __launch_bounds__(NT) geom_kernel(FrameParams P, DrawParams D) {
+    __shared__ unsigned long long s_cnt[C_COUNT];
+    if (threadIdx.x < C_COUNT) s_cnt[threadIdx.x] = 0ull;
+    __syncthreads();
+
+    GeomLocal lc;
+#pragma unroll
+    for (int k = 0; k < C_COUNT; k++) lc.c[k] = 0;
+    lc.bbox = 0ull;
+
+    const uint32_t t = blockIdx.x * NT + threadIdx.x;
+    if (t < D.nt) {
+        const uint32_t i0 = __ldg(&D.idx[3 * (size_t)t]), i1 = __ldg(&D.idx[3 * (size_t)t + 1]),
+                       i2 = __ldg(&D.idx[3 * (size_t)t + 2]);
+        if (i0 >= D.nv || i1 >= D.nv || i2 >= D.nv) {
+            atomicOr(&P.fs->err, ERR_INDEX); // the reference panics here (render.rs:83-87)
+        } else {
+            lc.c[C_TRIS_IN]++;
+            // vertex shader (main.rs:147-152): ((P*V)*W) * (x,y,z,1); the matrix product is hoisted
+            // to the host in the same operation order
+            const uint32_t vi[3] = {i0, i1, i2};
+            float c[3][4];
+#pragma unroll
+            for (int v = 0; v < 3; v++) {
+                const float *p = D.pos + 3 * (size_t)vi[v];
+                float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                    c[v][r] = dot4z(D.M[4 * r], D.M[4 * r + 1], D.M[4 * r + 2], D.M[4 * r + 3], x, y, z, 1.0f);
+            }
+            const uint32_t key0 = (D.tri_base + t) * 8u;
+
+            // clipping::try_clip (rasterizer/clipping.rs:62-195)
+            float a2x = cross2(fsub(c[1][0], c[0][0]), fsub(c[1][1], c[0][1]), fsub(c[2][0], c[0][0]),
+                               fsub(c[2][1], c[0][1]));
+            if (fabsf(a2x) < 0.000001f) {
+                lc.c[C_DEGENERATE]++;
+            } else {
+                bool all_in = true, any_out = false;
+#pragma unroll
+                for (int ax = 0; ax < 3; ax++) {
+                    bool in_lo = true, in_hi = true, out_lo = true, out_hi = true;
+#pragma unroll
+                    for (int v = 0; v < 3; v++) {
+                        float val = c[v][ax], w = c[v][3], nw = -w;
+                        in_lo &= val >= nw;
+                        in_hi &= val <= w;
+                        out_lo &= val < nw;
+                        out_hi &= val > w;
+                    }
+                    all_in &= in_lo & in_hi;
+                    any_out |= out_lo | out_hi;
+                }
+                if (any_out) {
+                    lc.c[C_OUTSIDE]++;
+                } else if (all_in) {
+                    lc.c[C_INSIDE]++;
+                    emit_triangle(P, D.fs, c[0], c[1], c[2], D.attr + 6 * (size_t)i0, D.attr + 6 * (size_t)i1,
+                                  D.attr + 6 * (size_t)i2, key0, lc);
+                } else {
+                    // Sutherland-Hodgman against LEFT,RIGHT,BOTTOM,TOP,NEAR,FAR (clipping.rs:118-171)
+                    float pv[2][MAX_POLY][4];
+                    float pa[2][MAX_POLY][6];
+                    int n_out = 3, cur = 0;
+                    for (int v = 0; v < 3; v++) {
+                        for (int k = 0; k < 4; k++) pv[0][v][k] = c[v][k];
+                        const float *a = D.attr + 6 * (size_t)vi[v];
+                        for (int k = 0; k < 6; k++) pa[0][v][k] = __ldg(a + k);
+                    }
+                    bool ovf = false;
+                    for (int plane = 0; plane < 6; plane++) {
+                        const int n_in = n_out, in = cur, out = cur ^ 1;
+                        n_out = 0;
+                        for (int i = 0; i < n_in; i++) {
+                            const int prev = (i + n_in - 1) % n_in;
+                            const float *pvv = pv[in][prev], *cvv = pv[in][i];
+                            const float pd = clip_distance(plane, pvv), cd = clip_distance(plane, cvv);
+                            const bool pin = pd >= 0.0f, cin = cd >= 0.0f;
+                            if (!pin && !cin) continue;
+                            if (n_out + 2 > MAX_POLY) {
+                                ovf = true;
+                                break;
+                            }
+                            if (pin != cin) { // crossing: intersection first (clipping.rs:43-51)
+                                const float alpha = fdiv(pd, fsub(pd, cd));
+                                const float om = fsub(1.0f, alpha);
+                                for (int k = 0; k < 4; k++)
+                                    pv[out][n_out][k] = fadd(fmul(pvv[k], om), fmul(cvv[k], alpha));
+                                for (int k = 0; k < 6; k++) // (cur - prev) * alpha + prev (clipping.rs:149,161)
+                                    pa[out][n_out][k] =
+                                        fadd(fmul(fsub(pa[in][i][k], pa[in][prev][k]), alpha), pa[in][prev][k]);
+                                n_out++;
+                            }
+                            if (cin) {
+                                for (int k = 0; k < 4; k++) pv[out][n_out][k] = cvv[k];
+                                for (int k = 0; k < 6; k++) pa[out][n_out][k] = pa[in][i][k];
+                                n_out++;
+                            }
+                        }
+                        cur = out;
+                    }
+                    if (ovf) lc.c[C_CLIP_OVF]++;
+                    if (n_out < 3) {
+                        lc.c[C_OUTSIDE]++; // late outside (clipping.rs:175-177)
+                    } else {
+                        lc.c[C_CLIPPED_IN]++;
+                        for (int i = 0; i + 2 < n_out; i++) // fan (0, i+1, i+2) (clipping.rs:185-190)
+                            emit_triangle(P, D.fs, pv[cur][0], pv[cur][i + 1], pv[cur][i + 2], pa[cur][0],
+                                          pa[cur][i + 1], pa[cur][i + 2], key0 + (uint32_t)min(i, 7), lc);
+                    }
+                }
+            }
+        }
+    }
+
+    // block-level counter reduction: warp reduce, one shared atomic per warp, one global per CTA
+#pragma unroll
+    for (int k = 0; k < C_COUNT; k++) {
+        if (k == C_BBOX_PX || k == C_COVERED_PX || k == C_SHADED_PX || k == C_SAMPLES || k == C_TEX_OOB) continue;
+        uint32_t v = __reduce_add_sync(0xffffffffu, lc.c[k]);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[k], (unsigned long long)v);
+    }
+    {
+        unsigned long long v = lc.bbox;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[C_BBOX_PX], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < C_COUNT && s_cnt[threadIdx.x]) atomicAdd(&P.fs->counters[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+// Vertex stage alone (render.rs:104-108) -- parity instrumentation for the clip-space positions.
+__global__ void __launch_bounds__(NT) vertex_kernel(const float *pos, uint32_t nv, DrawParams D, float4 *out) {
+    const uint32_t v = blockIdx.x * NT + threadIdx.x;
+    if (v >= nv) return;
+    float x = pos[3 * (size_t)v], y = pos[3 * (size_t)v + 1], z = pos[3 * (size_t)v + 2];
+    float r[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) r[k] = dot4z(D.M[4 * k], D.M[4 * k + 1], D.M[4 * k + 2], D.M[4 * k + 3], x, y, z, 1.0f);
+    out[v] = make_float4(r[0], r[1], r[2], r[3]);
+}
+
+__device__ __forceinline__ void load_setup(const RasterRec *recs, uint32_t rec, Setup &s, uint32_t &key, uint32_t &fs) {
+    const float4 *rr = reinterpret_cast<const float4 *>(&recs[rec]);
+    float4 r0 = __ldg(rr), r1 = __ldg(rr + 1), r2 = __ldg(rr + 2), r3 = __ldg(rr + 3);
+    s.px[0] = r0.x; s.py[0] = r0.y; s.px[1] = r0.z; s.py[1] = r0.w;
+    s.px[2] = r1.x; s.py[2] = r1.y; s.z[0] = r1.z; s.z[1] = r1.w;
+    s.z[2] = r2.x; s.w[0] = r2.y; s.w[1] = r2.z; s.w[2] = r2.w;
+    key = __float_as_uint(r3.x);
+    fs = __float_as_uint(r3.y);
+    setup_edges(s);
+}
+
+// Large-triangle binning: persistent CTAs steal (triangle, slab of tile rows) items; the 256
+// threads test the slab's tiles in parallel.  A tile is skipped only when, for some edge, the
+// most favourable sample position of tile-cap-bbox already fails that edge -- exact because the
+// f32 edge function is monotone in x and in y.
+__global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
+    __shared__ uint32_t s_item;
+    const uint32_t n = min(P.fs->n_large, P.large_cap);
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(&P.fs->large_next, 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        __syncthreads();
+        if (item >= n) break;
+        const LargeItem li = P.large[item];
+        Setup s;
+        uint32_t key, fs;
+        load_setup(P.recs, li.rec, s, key, fs);
+        BBox b = pixel_bbox(s, P.W, P.H);
+        b.y0 = max(b.y0, P.row_begin);
+        b.y1 = min(b.y1, P.row_end);
+        const uint32_t tx0 = b.x0 / TW, tx1 = (b.x1 - 1) / TW + 1, ntx = tx1 - tx0;
+        const uint32_t total = ntx * (li.ty1 - li.ty0);
+        for (uint32_t t = threadIdx.x; t < total; t += NT) {
+            const uint32_t tx = tx0 + t % ntx, ty = li.ty0 + t / ntx;
+            const uint32_t X0 = max(b.x0, tx * TW), X1 = min(b.x1, tx * TW + TW);
+            const uint32_t Y0 = max(b.y0, ty * TH), Y1 = min(b.y1, ty * TH + TH);
+            if (X0 >= X1 || Y0 >= Y1) continue;
+            const float sx_lo = fadd((float)X0, 0.125f), sx_hi = fadd((float)(X1 - 1), 0.875f);
+            const float sy_lo = fadd((float)Y0, 0.125f), sy_hi = fadd((float)(Y1 - 1), 0.875f);
+            bool keep = true;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float cx = s.nx[k] >= 0.0f ? sx_hi : sx_lo;
+                const float cy = s.ny[k] >= 0.0f ? sy_hi : sy_lo;
+                keep = keep && edge_pass(edge_eval(s, k, cx, cy), s.nx[k], s.ny[k]);
+            }
+            if (keep) push_bin(P, ty * P.tiles_x + tx, key, li.rec);
+        }
+    }
+}
+
+} // namespace rz

@@ -1,0 +1,109 @@
+// rz_types.cuh -- device-side data layout of one frame (see DESIGN.md "Data layout in HBM").
+#pragma once
+#include <stdint.h>
+
+namespace rz {
+
+constexpr int TW = 16;              // screen tile width  (pixels)
+constexpr int TH = 16;              // screen tile height (pixels)
+constexpr int TILE_PX = TW * TH;    // 256 = threads per tile CTA
+constexpr int NT = 256;             // threads per CTA in every kernel
+constexpr int CHUNK = 255;          // items per triangle-parallel chunk (item id fits u8, 0xFF = none)
+constexpr int SMALL_PX = 32;        // in-tile bbox area handled by one thread (4 x 32-bit coverage words)
+constexpr int POOL = 1536;          // per-chunk fragment records held in shared memory
+constexpr int SORT_CAP = 2048;      // tile lists up to this length are sorted in shared memory
+constexpr int GEOM_SMALL_PX = 64;   // bbox area up to which the geometry stage rasterises exactly
+constexpr int GEOM_SMALL_DIM = 16;  //   ... and max bbox extent (so it spans at most 2x2 tiles)
+constexpr int LARGE_SLAB_ROWS = 8;  // tile rows per large-triangle binning work item
+constexpr int MAX_POLY = 10;        // clipped polygon vertex budget (=> <= 8 fan triangles, 3 key bits)
+
+constexpr uint32_t CLEAR_COLOR = 0xFF191919u;    // rasterizer/buffers.rs:5
+constexpr float CLEAR_DEPTH = 3.40282347e+38f;   // f32::MAX, rasterizer/buffers.rs:6
+constexpr uint32_t NO_OWNER = 0xFFFFFFFFu;
+
+// error / overflow flags accumulated in FrameState::err
+enum : uint32_t {
+    ERR_REC_OVF = 1u,    // record array too small
+    ERR_BIN_OVF = 2u,    // a tile list outgrew its bin
+    ERR_LARGE_OVF = 4u,  // large-triangle queue too small
+    ERR_INDEX = 8u,      // mesh index >= nv
+};
+
+// counter slots in FrameState::counters (same order as rz_counters_t)
+enum {
+    C_TRIS_IN, C_DEGENERATE, C_OUTSIDE, C_INSIDE, C_CLIPPED_IN, C_TRIS_SETUP, C_BBOX_PX, C_COVERED_PX,
+    C_SHADED_PX, C_SAMPLES, C_TEX_OOB, C_CLIP_OVF, C_COUNT
+};
+
+// Device-side frame bookkeeping.  `counters` and `err` persist across frames (read by rz_counters /
+// rz_sync); everything from `n_records` on, and tile_count[] which follows in the same allocation,
+// is zeroed by one memset at the start of every frame.
+struct FrameState {
+    unsigned long long counters[16];
+    uint32_t err;         // sticky ERR_* flags
+    uint32_t pad0[3];
+    uint32_t n_records;   // emitted (post-clip, post-cull) triangles       <- per-frame part starts here
+    uint32_t n_large;     // large-triangle binning work items
+    uint32_t large_next;  // work-stealing cursor of the large binning kernel
+    uint32_t pad1;
+};
+
+// Raster record: everything the tile stage needs to re-create RasterizerTriangle
+// (rasterizer/mod.rs:178-184) except the attributes.  64 B = 4 x float4.
+struct __align__(16) RasterRec {
+    float p0x, p0y, p1x, p1y;
+    float p2x, p2y, z0, z1;
+    float z2, w0, w1, w2;
+    uint32_t key;   // submission order: 8 * (triangle number in frame) + fan index
+    uint32_t fs;    // fragment shader id of the draw
+    uint32_t pad0, pad1;
+};
+
+// Attribute record: VertexAttribute x3 (graphics_primitives.rs:10-13), 18 floats padded to 80 B.
+struct __align__(16) AttrRec {
+    float a[20];
+};
+
+// Large-triangle binning work item
+struct __align__(16) LargeItem {
+    uint32_t rec, key, ty0, ty1; // tile rows [ty0, ty1)
+};
+
+struct TexInfo {
+    const uint8_t *data;
+    unsigned long long len;
+    uint32_t w, h, tw, bound;
+};
+
+// Everything a kernel needs about the frame; passed by value.
+struct FrameParams {
+    uint32_t W, H;               // framebuffer size
+    uint32_t tiles_x, tiles_y;   // tile grid of the whole framebuffer
+    uint32_t ty_begin, ty_end;   // tile rows owned by this ctx (screen-space shard)
+    uint32_t row_begin, row_end; // same in pixel rows
+    uint32_t rec_cap, bin_cap, large_cap;
+    FrameState *fs;
+    uint32_t *tile_count;        // [tiles_x * tiles_y]
+    unsigned long long *bins;    // [tiles][bin_cap]  (key << 32 | rec)
+    RasterRec *recs;
+    AttrRec *attrs;
+    LargeItem *large;
+    uint32_t *out;               // resolved framebuffer u32[H][W]
+    float *dbg_depth;            // optional [H][W][4]
+    uint32_t *dbg_color;
+    uint32_t *dbg_owner;
+    TexInfo tex0;
+};
+
+// One draw call (Renderer::render, render.rs:98-114)
+struct DrawParams {
+    const float *pos;      // [nv][3]
+    const float *attr;     // [nv][6]
+    const uint32_t *idx;   // [3*nt]
+    uint32_t nv, nt;
+    uint32_t tri_base;     // triangle number of this draw's first triangle inside the frame
+    uint32_t fs;
+    float M[16];           // (projection * view) * world, row-major (main.rs:147-152)
+};
+
+} // namespace rz

@@ -1,0 +1,193 @@
+"""GPU parity tests proper (run on the B200 with `-m gpu`): the CUDA path, called through the
+C ABI, against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): coverage masks and depth-test outcomes bit-exact -> we compare the
+per-sample owner key, the per-sample depth BITS and the per-sample packed colour; resolved 8-bit
+colour within +-1 LSB -> we assert exact equality of the u32 image (tolerance 0, stricter than
+required).  Work counters must match the oracle's too.
+"""
+import numpy as np
+import pytest
+
+from helpers import compare, gpu_render, oracle_render
+from rusterizer_b200 import mathx, scenes
+from rusterizer_b200.mesh import Mesh
+
+pytestmark = pytest.mark.gpu
+
+
+def check(scene, **kw):
+    o = oracle_render(scene)
+    g = gpu_render(scene, debug=True, **kw)
+    msgs = compare(o, g)
+    assert not msgs, f"{scene.name}: " + "; ".join(msgs)
+    assert o["counters"]["n_tex_oob"] == 0 and o["counters"]["n_clip_overflow"] == 0
+    return o, g
+
+
+@pytest.mark.parametrize("elapsed", [0.0, 1.0, 2.5])
+@pytest.mark.parametrize("fs", [0, 1, 2])
+def test_default_scene(elapsed, fs):
+    """C1: the crate's default scene (cube + sphere, 2 draws) at fixed `elapsed`, all three FS."""
+    check(scenes.default_scene(elapsed, fs=fs))
+
+
+@pytest.mark.parametrize("elapsed", [0.0, 0.4, 3.0, 3.5, 5.9])
+def test_clip_test_scene(elapsed):
+    """C1 --clip-test: one triangle orbiting the window border (main.rs:106-125)."""
+    check(scenes.clip_test_scene(elapsed))
+
+
+def test_sphere_small_triangles():
+    """C2 scaled down: 80K ~pixel-sized triangles."""
+    check(scenes.sphere_scene(201, 201, width=640, height=360))
+
+
+def test_sphere_device_resident_mesh():
+    check(scenes.sphere_scene(101, 51, width=480, height=270), device_resident=True)
+
+
+def test_sphere_odd_resolution():
+    """Width not a multiple of 4 or of the tile size: scalar write-back path, ragged tiles."""
+    check(scenes.sphere_scene(101, 51, width=333, height=187))
+
+
+@pytest.mark.parametrize("b2f", [True, False])
+def test_overdraw_layers(b2f):
+    """4 stacked jittered grids, back-to-front / front-to-back: the in-order depth test and the
+    post-depth shading-position rule (rasterizer/mod.rs:70-83) under heavy overdraw."""
+    check(scenes.overdraw_scene(60, 30, width=480, height=270, back_to_front=b2f))
+
+
+def test_near_clip_field():
+    """C3 scaled down: every triangle straddles the near plane (Sutherland-Hodgman + fan)."""
+    o, _ = check(scenes.near_clip_scene(80, 40, width=640, height=360))
+    assert o["counters"]["n_clipped_in"] > 0.9 * o["counters"]["n_tris_in"]
+
+
+def test_fullscreen_quad_clipped_by_four_planes():
+    """C4(ii) scaled down: 2 huge triangles -> large-triangle binning + pixel-parallel tile path."""
+    check(scenes.fullscreen_quad_scene(512, 512))
+
+
+def test_mixed_large_and_small_in_one_frame():
+    """Large and small triangles interleaved in submission order inside the same tiles."""
+    s = scenes.sphere_scene(61, 31, width=400, height=240)
+    quad = scenes.fullscreen_quad_scene(400, 240).draws[0]
+    s.draws = [s.draws[0], quad, scenes.Draw(s.draws[0].mesh, mathx.rotate(1.0, 0.2, 0.0), 1), quad]
+    check(s)
+
+
+def test_coincident_triangles_keep_first():
+    """Equal depths: strict `<` keeps the EARLIER triangle (rasterizer/mod.rs:374)."""
+    s = scenes.sphere_scene(41, 21, width=320, height=200)
+    d = s.draws[0]
+    s.draws = [d, scenes.Draw(d.mesh, d.world, 1), scenes.Draw(d.mesh, d.world, 2)]
+    o, g = check(s)
+    nt = d.mesh.n_triangles
+    owned = o["owner"][o["owner"] != 0xFFFFFFFF] // 8
+    assert owned.max() < nt  # nothing from the 2nd / 3rd draw ever wins
+
+
+def test_random_soup():
+    """Seeded random triangle soup (arbitrary sizes, both windings, slivers, off-screen parts)."""
+    rng = np.random.RandomState(7)
+    nt = 3000
+    ctr = rng.uniform(-3, 3, (nt, 1, 3)).astype(np.float32)
+    ctr[..., 2] = rng.uniform(-3.5, 6, (nt, 1)).astype(np.float32)
+    size = (10 ** rng.uniform(-2.5, 0.3, (nt, 1, 1))).astype(np.float32)
+    verts = (ctr + rng.uniform(-1, 1, (nt, 3, 3)).astype(np.float32) * size).reshape(-1, 3)
+    attrs = rng.uniform(0, 1, (nt * 3, 6)).astype(np.float32)
+    mesh = Mesh(verts, np.arange(nt * 3, dtype=np.uint32), attrs)
+    for fs in (0, 1):
+        s = scenes.sphere_scene(width=512, height=288, mesh=mesh, fs=fs)
+        check(s)
+
+
+def test_empty_and_degenerate_inputs():
+    """Empty mesh, zero-area triangles, a frame with no draws."""
+    from rusterizer_b200.render import Renderer
+
+    r = Renderer(200, 120)
+    fb = r.framebuffer()
+    assert (fb == 0xFF191919).all()
+    empty = Mesh(np.zeros((0, 3)), np.zeros(0, np.uint32), np.zeros((0, 6)))
+    r.render(empty, 0, 1)
+    degenerate = Mesh([[0, 0, 0], [0, 1, 0], [0, 0, 0]], [0, 1, 2], np.zeros((3, 6)))
+    r.render(degenerate, 0, 1)
+    fb = r.framebuffer()
+    assert (fb == 0xFF191919).all()
+    assert r.counters()["n_degenerate"] == 1
+    r.close()
+
+
+def test_frames_are_independent_and_repeatable():
+    """framebuffer() clears: rendering the same scene twice gives the same image; an empty frame
+    after it gives the clear colour (resolve_and_clear, rasterizer/mod.rs:478-518)."""
+    from rusterizer_b200.render import Renderer
+
+    s = scenes.default_scene(1.0, width=320, height=180)
+    r = Renderer(s.width, s.height)
+    r.uniforms().bind_texture(0, s.texture)
+    scenes.render_scene(r, s)
+    a = r.framebuffer()
+    scenes.render_scene(r, s)
+    b = r.framebuffer()
+    c = r.framebuffer()
+    assert np.array_equal(a, b) and (c == 0xFF191919).all()
+    o = oracle_render(s)
+    assert np.array_equal(o["fb"], a)
+    r.close()
+
+
+def test_vertex_stage_bitwise():
+    """Stage 1 alone: clip-space positions bitwise equal to the oracle's vertex stage."""
+    from oracle.oracle import OracleRenderer
+    from rusterizer_b200.render import Renderer
+
+    s = scenes.sphere_scene(101, 51, width=320, height=180)
+    d = s.draws[0]
+    r = Renderer(s.width, s.height)
+    blk = r.uniforms().write_block()
+    blk.view, blk.projection, blk.world = s.view, s.projection, d.world
+    got = r.vertex_stage(r.upload(d.mesh))
+    o = OracleRenderer(s.width, s.height)
+    o.write_block(world=d.world, view=s.view, projection=s.projection)
+    want = o.vertex_stage(d.mesh.vertices)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    r.close()
+
+
+def test_error_behaviour():
+    """Same failure points as the reference's panics, as error codes."""
+    from rusterizer_b200.render import Renderer, RzError
+
+    r = Renderer(64, 64)
+    tex = scenes.Texture.checkerboard()
+    with pytest.raises(RzError) as e:  # uniform.rs:31 assert!(len == index)
+        r.uniforms().bind_texture(1, tex)
+    assert e.value.code == -4
+    tri = scenes.triangle()
+    with pytest.raises(RzError) as e:  # uniform.rs:36 get_texture(0) on an empty Vec
+        r.render(tri, 0, 0)
+    assert e.value.code == -4
+    with pytest.raises(RzError):
+        r.render(tri, 0, 7)
+    bad = Mesh(tri.vertices, [0, 1, 5], tri.attributes)  # render.rs:83-87 slice index panic
+    r.render(bad, 0, 1)
+    with pytest.raises(RzError) as e:
+        r.framebuffer()
+    assert e.value.code == -5
+    r.close()
+
+
+def test_capacity_growth_dense_tile():
+    """A whole 20K-triangle sphere inside a handful of tiles: tile bins overflow their initial
+    capacity; rz_framebuffer grows them and replays the frame; lists longer than the in-smem sort
+    capacity take the global-memory sort path."""
+    s = scenes.sphere_scene(101, 101, radius=0.15, width=256, height=256)
+    check(s)
+    s = scenes.overdraw_scene(8, 8, width=64, height=64)
+    layers = [scenes.Draw(d.mesh, d.world, d.fs) for d in s.draws] * 200  # 800 draws into 16 tiles
+    s.draws = layers
+    check(s)
