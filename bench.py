@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 raster path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode frames|tiles]
+
+One "step" = one whole frame of the hot path (geometry -> binning -> tile raster -> resolve) of the
+1M-triangle textured UV-sphere at 1920x1080, 4xMSAA, bilinear filtering (BASELINE.json configs[1]).
+At N>1 the ranks render independent frames of the orbiting-camera sweep of the same mesh
+(configs[4]); there is no data-path collective (DESIGN.md "Multi-GPU"), so scaling is "weak".
+`--mode tiles` instead splits ONE 8192x8192 frame into tile-row ranges per rank and gathers the
+strips with NCCL (configs[3]).
+
+Prints ONE JSON line on rank 0 (contract in the task statement):
+  value      Mtris/s with mesh, texture and uniforms already resident in HBM (CUDA events)
+  e2e        same metric through the host-buffer API: H2D of the mesh + D2H of the image every step
+  roofline   dominant kernel: algorithmic bytes / measured kernel time vs the measured HBM peak
+  cpu_baseline  the CPU oracle (C port of the reference algorithm) timed on this host, 1 core
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "Mtris/s at 1080p 4xMSAA (1M-triangle textured frame)"
+UNIT = "Mtris/s"
+HBM_FALLBACK_GBS = 6650.0
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scene(args):
+    from rusterizer_b200 import scenes
+
+    if args.mode == "tiles":
+        return scenes.sphere_scene(args.n_phi, args.n_theta, width=8192, height=8192)
+    return scenes.sphere_scene(args.n_phi, args.n_theta, width=args.width, height=args.height)
+
+
+def cpu_baseline(scene, budget_s=12.0, fast=True):
+    """Time the CPU oracle (the reference algorithm restated in C, single thread like the reference)
+    on whole frames of the same workload until ~budget_s of CPU time is spent."""
+    from oracle import oracle as orc
+
+    try:
+        lib = orc.OracleLib(orc.build(fast=fast, out_dir=Path(os.environ.get("TMPDIR", "/tmp")) / "rz_oracle_native"),
+                            fast=fast)
+        build = "gcc -O3 -march=native -ffp-contract=off"
+    except Exception:
+        lib = orc.get_lib(False)
+        build = "gcc -O2 -ffp-contract=off"
+    r = orc.OracleRenderer(scene.width, scene.height, lib)
+    r.bind_texture(0, scene.texture.texels)
+    r.write_block(view=scene.view, projection=scene.projection)
+
+    def frame():
+        for d in scene.draws:
+            r.write_block(world=d.world)
+            r.render(d.mesh.vertices, d.mesh.attributes, d.mesh.indices, 0, d.fs)
+        return r.framebuffer()
+
+    t = time.perf_counter()
+    frame()  # warm-up
+    first = time.perf_counter() - t
+    times = []
+    while sum(times) < budget_s and len(times) < 50:
+        t = time.perf_counter()
+        frame()
+        times.append(time.perf_counter() - t)
+        if first > budget_s:
+            break
+    best = min(times) if times else first
+    cnt = r.counters()
+    r.close()
+    frames = len(times) + 1
+    return {
+        "value": scene.n_triangles / best / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+        "sample": f"{frames} whole frames of the same workload ({scene.n_triangles} triangles, {scene.width}x{scene.height}), "
+                  f"best frame {best * 1e3:.1f} ms; oracle/rz_oracle.c built with {build}; host has {os.cpu_count()} cores, "
+                  "the reference is single-threaded",
+        "ms_per_frame": best * 1e3,
+        "gsamples_per_s": cnt["n_samples_written"] / frames / best / 1e9,
+    }
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  The crate is Rust and no Rust toolchain exists in
+    this image, so the arm times the oracle port of the same algorithm (1 thread: the reference has
+    no threading).  Each step is one whole frame of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scene = build_scene(args)
+    steps = max(1, min(args.steps, 10))
+    cb = cpu_baseline(scene, budget_s=min(60.0, 1.5 * steps))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_frame"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, scene),
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gsamples_per_s": cb["gsamples_per_s"],
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, scene):
+    return {
+        "workload": ("BASELINE configs[3]: one 8192x8192 frame of the 1M-triangle sphere split into tile-row ranges + NCCL gather"
+                     if args.mode == "tiles" else
+                     "BASELINE configs[1]: 1M-triangle textured UV-sphere (1001x501), 1920x1080, 4xMSAA, bilinear checkerboard texture"
+                     + ("; N>1: independent frames of the orbit sweep per GPU (configs[4])" if args.gpus > 1 else "")),
+        "triangles": scene.n_triangles, "vertices": scene.n_vertices, "width": scene.width, "height": scene.height,
+        "msaa": 4, "fs": "Texture", "parallelism": f"{args.mode}x{args.gpus}",
+        "l2": "flushed between timed frames (256 MiB memset outside the per-frame event pairs)",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="frames", choices=["frames", "tiles"])
+    ap.add_argument("--n-phi", type=int, default=1001)
+    ap.add_argument("--n-theta", type=int, default=501)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from rusterizer_b200 import scenes
+    from rusterizer_b200.camera import Camera
+    from rusterizer_b200.render import Renderer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_gpus = world
+
+    scene = build_scene(args)
+    mesh = scene.draws[0].mesh
+    W, H = scene.width, scene.height
+    K, Wm = args.steps, args.warmup
+
+    r = Renderer(W, H, device=local)
+    # a real (non-default) torch stream: torch.cuda.Event times exactly the stream our kernels run on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    r.set_stream(stream.cuda_stream)
+    r.uniforms().bind_texture(0, scene.texture)
+    dmesh = r.upload(mesh)
+    blk = r.uniforms().write_block()
+    blk.projection = scene.projection
+    blk.world = scene.draws[0].world
+
+    tiles_mode = args.mode == "tiles"
+    gather_buf = None
+    own_rows = H
+    if tiles_mode:
+        th = 16
+        rows_per = ((H // th + n_gpus - 1) // n_gpus) * th
+        r0, r1 = min(H, rank * rows_per), min(H, (rank + 1) * rows_per)
+        r.set_row_range(r0, r1)
+        own_rows = r1 - r0
+        strip = torch.empty((rows_per, W), dtype=torch.int32, device="cuda")
+        gather_buf = torch.empty((n_gpus * rows_per, W), dtype=torch.int32, device="cuda") if n_gpus > 1 else None
+        cams = [Camera()] * (K + Wm)
+    elif n_gpus > 1:
+        sweep = scenes.orbit_cameras(1024)
+        cams = [sweep[(s * n_gpus + rank) % 1024] for s in range(K + Wm)]
+    else:
+        cams = [Camera()] * (K + Wm)
+    views = [c.get_view_matrix() for c in cams]
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def frame_async(i):
+        blk.view = views[i]
+        r.render(dmesh, 0, 0)
+        if tiles_mode:
+            r.framebuffer_async(strip.data_ptr())
+            if gather_buf is not None:
+                dist.all_gather_into_tensor(gather_buf, strip)
+        else:
+            r.framebuffer_async()
+
+    # ---- warm-up: the synchronous path sizes the device buffers, then a few async frames ----
+    blk.view = views[0]
+    r.render(dmesh, 0, 0)
+    r.framebuffer_device()
+    for i in range(Wm):
+        frame_async(i)
+    r.sync()
+    r.reset_counters()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K frames, inputs resident in HBM, L2 flushed between frames ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    launches0 = r.launch_count()
+    t_wall0 = time.time()
+    for s in range(K):
+        flush.zero_()
+        ev0[s].record(stream)
+        frame_async(Wm + s)
+        ev1[s].record(stream)
+    r.sync()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    launches = r.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    total_ms = sum(step_ms)
+    cnt = r.counters()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    tot = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tot.item())
+    tris_per_step = scene.n_triangles if not tiles_mode else scene.n_triangles / n_gpus
+    frames_total = K * (1 if tiles_mode else n_gpus)
+    value = (scene.n_triangles * frames_total) / (total_ms_max / 1e3) / 1e6
+    samples = torch.tensor([cnt["n_samples_written"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(samples, op=dist.ReduceOp.SUM)
+    gsamples = float(samples.item()) / (total_ms_max / 1e3) / 1e9
+
+    # ---- per-kernel times (CUDA events on the same stream) over K profiled frames ----
+    stage = {"geometry_ms": [], "bin_ms": [], "tile_ms": [], "total_ms": []}
+    for s in range(min(K, 20)):
+        flush.zero_()
+        blk.view = views[Wm + s]
+        r.render(dmesh, 0, 0)
+        r.framebuffer_device()
+        t = r.timings()
+        for k in stage:
+            stage[k].append(t[k])
+    stage_avg = {k: sum(v) / len(v) for k, v in stage.items()}
+
+    # ---- e2e: host buffers in, host image out, every step (pinned memory) ----
+    pos_h = torch.from_numpy(mesh.vertices).pin_memory()
+    att_h = torch.from_numpy(mesh.attributes).pin_memory()
+    idx_h = torch.from_numpy(mesh.indices.view(np.int32)).pin_memory()
+    out_h = torch.empty((H, W), dtype=torch.int32).pin_memory()
+    e2e_steps = max(3, min(K, 20))
+
+    def frame_e2e(i):
+        blk.view = views[i % len(views)]
+        r.render_arrays(pos_h.data_ptr(), att_h.data_ptr(), mesh.n_vertices, idx_h.data_ptr(), mesh.indices.size, 0, 0)
+        r.framebuffer_into(out_h.data_ptr())  # synchronises; D2H of the resolved image
+
+    for i in range(3):
+        frame_e2e(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        frame_e2e(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2 = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2, op=dist.ReduceOp.MAX)
+    e2e_value = scene.n_triangles * e2e_steps * (1 if tiles_mode else n_gpus) / float(e2.item()) / 1e6
+    h2d = mesh.vertices.nbytes + mesh.attributes.nbytes + mesh.indices.nbytes + 192
+    d2h = W * H * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_kind = measured_peaks()
+    alg = {
+        "geometry": 36 * scene.n_vertices + 12 * scene.n_triangles + 192,  # mesh + indices + matrices
+        "tile": scene.texture.texels.nbytes + 4 * W * own_rows,  # texture + this rank's rows of the image
+    }
+    kt = {"geometry": stage_avg["geometry_ms"], "tile": stage_avg["tile_ms"]}
+    dom = max(kt, key=kt.get)
+    achieved = alg[dom] / (kt[dom] / 1e3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(dom)
+        except Exception:
+            traffic = None
+    frame_alg = scene.algorithmic_bytes()
+    ms_per_step = total_ms_max / K
+    roofline = {
+        "bound": "hbm", "kernel": f"{dom}_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+        "algorithmic_bytes_per_launch": alg[dom], "kernel_ms": kt[dom],
+        "kernel_ms_all": stage_avg, "kernel_share_of_frame": kt[dom] / max(stage_avg["total_ms"], 1e-9),
+        "frame_algorithmic_bytes": frame_alg, "frame_frac": frame_alg / (ms_per_step / 1e3) / 1e9 / peak,
+        "timing": "per-stage CUDA events on the launch stream over profiled frames run right after the timed region",
+    }
+    cb = None
+    if not args.no_cpu_baseline and not tiles_mode:
+        cb = cpu_baseline(scene, budget_s=args.cpu_budget)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if tiles_mode else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, scene),
+        "gsamples_per_s": gsamples, "ms_per_frame": ms_per_step,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": float(e2.item()) / e2e_steps * 1e3, "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cb,
+        "counters_per_frame": {k: v / K for k, v in cnt.items()},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -192,8 +192,8 @@ int rz_create(int device, uint32_t width, uint32_t height, rz_ctx **out) {
     CU_NEW(cudaMalloc(&c->d_cnt_backup, sizeof(unsigned long long) * 16));
     CU_NEW(cudaHostAlloc(&c->h_state, sizeof(FrameState), cudaHostAllocDefault));
     for (int i = 0; i < 4; i++) CU_NEW(cudaEventCreate(&c->ev[i]));
-    CU_NEW(cudaFuncSetAttribute(tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
-    CU_NEW(cudaFuncSetAttribute(tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+    CU_NEW(cudaFuncSetAttribute(tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemT<false>)));
+    CU_NEW(cudaFuncSetAttribute(tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemT<true>)));
 #undef CU_NEW
     *out = c;
     return RZ_OK;
@@ -399,9 +399,9 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     const uint32_t n_tiles = P.tiles_x * (P.ty_end - P.ty_begin);
     if (n_tiles) {
         if (c->debug)
-            tile_kernel<true><<<n_tiles, NT, sizeof(TileSmem), st>>>(P);
+            tile_kernel<true><<<n_tiles, NT, sizeof(TileSmemT<true>), st>>>(P);
         else
-            tile_kernel<false><<<n_tiles, NT, sizeof(TileSmem), st>>>(P);
+            tile_kernel<false><<<n_tiles, NT, sizeof(TileSmemT<false>), st>>>(P);
         c->launches++;
     }
     if (timed) CU(c, cudaEventRecord(c->ev[3], st));

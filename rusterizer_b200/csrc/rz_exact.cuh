@@ -67,6 +67,16 @@ __device__ __forceinline__ void setup_edges(Setup &s) {
     s.inv = fdiv(1.0f, cross2(v0x, v0y, v20x, v20y));
 }
 
+// Edge normals only (for shading, which needs neither inv_2x_area nor the depths).
+__device__ __forceinline__ void setup_normals(Setup &s) {
+    float v0x = fsub(s.px[1], s.px[0]), v0y = fsub(s.py[1], s.py[0]);
+    float v1x = fsub(s.px[2], s.px[1]), v1y = fsub(s.py[2], s.py[1]);
+    float v2x = fsub(s.px[0], s.px[2]), v2y = fsub(s.py[0], s.py[2]);
+    s.nx[0] = -v0y; s.ny[0] = v0x;
+    s.nx[1] = -v1y; s.ny[1] = v1x;
+    s.nx[2] = -v2y; s.ny[2] = v2x;
+}
+
 // EdgeFunctions::eval_single for one edge (rasterizer/mod.rs:125-132)
 __device__ __forceinline__ float edge_eval(const Setup &s, int k, float x, float y) {
     return dot2z(s.nx[k], s.ny[k], fsub(x, s.px[k]), fsub(y, s.py[k]));

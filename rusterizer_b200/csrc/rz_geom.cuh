@@ -55,8 +55,9 @@ __device__ __forceinline__ void emit_triangle(const FrameParams &P, uint32_t fs_
     for (int i = 0; i < 3; i++) {
         float w = cv[i][3];
         float nx = fdiv(cv[i][0], w), ny = fdiv(cv[i][1], w), nz = fdiv(cv[i][2], w);
-        s.px[i] = fdiv(fmul(Wf, fadd(nx, 1.0f)), 2.0f);
-        s.py[i] = fmul(Hf, fsub(1.0f, fdiv(fadd(ny, 1.0f), 2.0f)));
+        // `/ 2.0` is computed as `* 0.5`: scaling by a power of two rounds identically
+        s.px[i] = fmul(fmul(Wf, fadd(nx, 1.0f)), 0.5f);
+        s.py[i] = fmul(Hf, fsub(1.0f, fmul(fadd(ny, 1.0f), 0.5f)));
         s.z[i] = fadd(fmul(fmul(fadd(nz, 1.0f), 0.5f), 1.0f), 0.0f); // (z+1)*0.5*(zmax-zmin)+zmin
         s.w[i] = w;
     }
@@ -70,15 +71,37 @@ __device__ __forceinline__ void emit_triangle(const FrameParams &P, uint32_t fs_
     const uint32_t bw = b.x1 - b.x0, bh = b.y1 - b.y0;
     lc.bbox += (unsigned long long)bw * bh;
 
+    // ---- exact culls (results identical to walking the bbox) ----
+    // (1) Back-facing with a rigorous margin.  The three edge functions of any sample sum to the
+    // signed 2x area A; a covered sample has all three computed values >= 0.  With u = 2^-24 every
+    // computed edge value is within 4u*(|dy||sx-px| + |dx||sy-py|) of its exact value and the computed
+    // area within 8u*Bw*Bh of A, where Bw,Bh are the bbox extents and |s-p| <= B+1 inside the pixel
+    // bbox.  Hence coverage implies  area2 >= -u*(32*Bw*Bh + 12*(Bw+Bh)); we cull only below twice
+    // that bound (DESIGN.md "Exact culls").  NaN/inf compare false and fall through to the exact path.
+    const float area2 = cross2(fsub(s.px[1], s.px[0]), fsub(s.py[1], s.py[0]), fsub(s.px[2], s.px[0]),
+                               fsub(s.py[2], s.py[0]));
+    {
+        const float mnx = fminf(fminf(s.px[0], s.px[1]), s.px[2]), mxx = fmaxf(fmaxf(s.px[0], s.px[1]), s.px[2]);
+        const float mny = fminf(fminf(s.py[0], s.py[1]), s.py[2]), mxy = fmaxf(fmaxf(s.py[0], s.py[1]), s.py[2]);
+        const float Bw = mxx - mnx, Bh = mxy - mny;
+        const float tau = 1.1920929e-07f * (34.0f * Bw * Bh + 14.0f * (Bw + Bh)) + 1e-30f;
+        if (area2 < -tau) return;
+    }
     const bool small = bw <= GEOM_SMALL_DIM && bh <= GEOM_SMALL_DIM && bw * bh <= GEOM_SMALL_PX;
     const uint32_t tx0 = b.x0 / TW, ty0 = b.y0 / TH;
     uint32_t tmask = 0;
     if (small) {
-        // exact coverage over the whole bbox: which of the <= 2x2 tiles see a covered sample?
-        for (uint32_t Y = b.y0; Y < b.y1; Y++)
-            for (uint32_t X = b.x0; X < b.x1; X++)
-                if (coverage_mask(s, (int)X, (int)Y)) tmask |= 1u << (((Y / TH - ty0) << 1) | (X / TW - tx0));
-        if (!tmask) return; // touches no sample: contributes nothing (the bbox pixels are already counted)
+        const uint32_t tx1 = (b.x1 - 1) / TW, ty1 = (b.y1 - 1) / TH;
+        if (area2 < GEOM_THIN_AREA2) {
+            // (2) thin / tiny triangles usually touch no sample at all: rasterise them exactly right
+            // here so they never reach a tile list (pole slivers of a UV-sphere, distant meshes)
+            for (uint32_t Y = b.y0; Y < b.y1; Y++)
+                for (uint32_t X = b.x0; X < b.x1; X++)
+                    if (coverage_mask(s, (int)X, (int)Y)) tmask |= 1u << (((Y / TH - ty0) << 1) | (X / TW - tx0));
+            if (!tmask) return; // contributes nothing (its bbox pixels are already counted)
+        } else {
+            tmask = 1u | (tx1 > tx0 ? 2u : 0u) | (ty1 > ty0 ? 4u : 0u) | ((tx1 > tx0 && ty1 > ty0) ? 8u : 0u);
+        }
     }
 
     const uint32_t rec = alloc_slot(&P.fs->n_records);

@@ -4,19 +4,23 @@
 // (the reference's DepthBuffer / ColorBuffer, rasterizer/buffers.rs:83-157) lives in shared
 // memory from clear to resolve and only the box-filtered u32 image goes back to HBM.
 //
-// Submission order is honoured exactly:
-//   * the tile's list is sorted by order key (8 * triangle number + fan index);
-//   * runs of LARGE items (in-tile bbox > 32 px) are walked pixel-parallel: a thread owns a pixel
-//     for the whole run, so it applies the triangles in order by construction;
-//   * runs of SMALL items are processed triangle-parallel in chunks of <= 255 items:
-//       phase 1  thread = item : exact coverage over its bbox, sample depths -> smem records,
-//                                sets bit <item> in the bitmask of every pixel it covers;
-//       phase 2  thread = pixel: walks the set bits in ascending (= submission) order and replays
-//                                the reference's strict-< depth test, recording each fragment's
-//                                post-depth mask and the final per-sample owner;
-//       phase 3  thread = item : shades its fragments at the position the post-depth mask selects
-//                                (rasterizer/mod.rs:70-83) -- only those that still own a sample at
-//                                the end of the chunk can be seen, the others are skipped.
+// Submission order is honoured exactly, but without serialising on it.
+// Within a chunk of <= 255 SMALL items (in-tile bbox <= 32 px) every covered pixel of every item
+// becomes a FRAGMENT record {item, pixel, coverage, 4 sample depths} on a per-pixel list, and
+// each fragment F decides by itself, from the other fragments G of its pixel, what the ordered
+// replay of the reference would have done:
+//     post-depth mask  m(F)[s] = cov_F[s] & z_F[s] < z_old[s] & no G earlier than F with z_G[s] <= z_F[s]
+//     still visible    v(F)[s] = m(F)[s]  & no G later   than F with z_G[s] <  z_F[s]
+// ("earlier/later" by order key; strict-< depth test, rasterizer/mod.rs:374).  m(F) selects the
+// shading position (rasterizer/mod.rs:70-83) and feeds the counters; only fragments with v(F) != 0
+// are shaded, and they write colour + depth of exactly the samples in v(F).  Nothing in a chunk
+// depends on the order in which threads run, so a tile whose list fits one chunk is never sorted.
+//   phase A  thread = item     exact coverage over its bbox; sample depths -> fragment records
+//   phase B  thread = fragment m(F), v(F) from the pixel's list
+//   phase C  thread = fragment interpolate + fragment shader + pack; write samples
+// Tiles that need several chunks, or that contain LARGE items, sort their list by order key first;
+// runs of large items are walked pixel-parallel (a thread owns a pixel for the whole run, so it
+// applies the triangles in order by construction).
 #pragma once
 #include "rz_exact.cuh"
 #include "rz_geom.cuh"
@@ -26,7 +30,9 @@ namespace rz {
 
 // Texture::read_texel + Color::from_rgba (texture.rs:47-63, color.rs:22-29).  Reads past the
 // buffer (a panic in the reference) are clamped to the last byte and counted.
-__device__ __forceinline__ void read_texel(const TexInfo &t, uint32_t x, uint32_t y, float *rgba, uint32_t &oob) {
+// `lut[b]` holds (b as f32) / 255.0 computed with the same IEEE division, once per CTA.
+__device__ __forceinline__ void read_texel(const TexInfo &t, const float *lut, uint32_t x, uint32_t y, float *rgba,
+                                           uint32_t &oob) {
     const unsigned long long start =
         (unsigned long long)x * t.tw + (unsigned long long)y * t.tw * (unsigned long long)t.w;
     uint32_t b0, b1, b2, b3 = 255u;
@@ -46,22 +52,23 @@ __device__ __forceinline__ void read_texel(const TexInfo &t, uint32_t x, uint32_
         }
         b0 = bb[0]; b1 = bb[1]; b2 = bb[2]; b3 = bb[3];
     }
-    rgba[0] = fdiv((float)b0, 255.0f);
-    rgba[1] = fdiv((float)b1, 255.0f);
-    rgba[2] = fdiv((float)b2, 255.0f);
-    rgba[3] = fdiv((float)b3, 255.0f);
+    rgba[0] = lut[b0];
+    rgba[1] = lut[b1];
+    rgba[2] = lut[b2];
+    rgba[3] = lut[b3];
 }
 
 // Texture::sample (texture.rs:65-83) + Color::to_argb
-__device__ __forceinline__ uint32_t sample_texture_argb(const TexInfo &t, float u, float v, uint32_t &oob) {
+__device__ __forceinline__ uint32_t sample_texture_argb(const TexInfo &t, const float *lut, float u, float v,
+                                                        uint32_t &oob) {
     const float x = fmul(u, (float)(t.w - 1)), y = fmul(v, (float)(t.h - 1));
     const uint32_t x0 = sat_u32(floorf(x)), x1 = sat_u32(ceilf(x));
     const uint32_t y0 = sat_u32(floorf(y)), y1 = sat_u32(ceilf(y));
     float tl[4], tr[4], bl[4], br[4];
-    read_texel(t, x0, y0, tl, oob);
-    read_texel(t, x1, y0, tr, oob);
-    read_texel(t, x0, y1, bl, oob);
-    read_texel(t, x1, y1, br, oob);
+    read_texel(t, lut, x0, y0, tl, oob);
+    read_texel(t, lut, x1, y0, tr, oob);
+    read_texel(t, lut, x0, y1, bl, oob);
+    read_texel(t, lut, x1, y1, br, oob);
     const float xf = fsub(x, truncf(x)), yf = fsub(y, truncf(y)); // f32::fract
     const float omx = fsub(1.0f, xf), omy = fsub(1.0f, yf);
     float o[4];
@@ -77,8 +84,8 @@ __device__ __forceinline__ uint32_t sample_texture_argb(const TexInfo &t, float 
 // Fragment::interpolate (rasterizer/mod.rs:69-100) + the built-in fragment shaders
 // (main.rs:67-77) + Color::to_argb.  mpost is the POST-depth-test mask, depth0 the pre-test
 // sampled depth of sample 0 (0.0 when uncovered), as FragCoords.depths[0] (mod.rs:458-463).
-__device__ __forceinline__ uint32_t shade(const Setup &s, const AttrRec *ar, uint32_t fs, const TexInfo &tex, int X,
-                                          int Y, uint32_t mpost, float depth0, uint32_t &oob) {
+__device__ __forceinline__ uint32_t shade(const Setup &s, const AttrRec *ar, uint32_t fs, const TexInfo &tex,
+                                          const float *lut, int X, int Y, uint32_t mpost, float depth0, uint32_t &oob) {
     if (fs == 2u) return to_argb(depth0, depth0, depth0, 1.0f); // Color::grayscale(depths[0])
     float xs, ys;
     if (mpost == 0xFu) {
@@ -100,7 +107,7 @@ __device__ __forceinline__ uint32_t shade(const Setup &s, const AttrRec *ar, uin
     if (fs == 1u) return to_argb(RZ_INTERP(0), RZ_INTERP(1), RZ_INTERP(2), RZ_INTERP(3));
     const float tu = RZ_INTERP(4), tv = RZ_INTERP(5);
 #undef RZ_INTERP
-    return sample_texture_argb(tex, tu, tv, oob);
+    return sample_texture_argb(tex, lut, tu, tv, oob);
 }
 
 // Bitonic network in its "flip then halve" form: every compare-exchange puts the smaller key at
@@ -139,27 +146,57 @@ struct __align__(16) BigSetup {
 };
 static_assert(sizeof(BigSetup) == 96, "BigSetup must be 24 words");
 
-struct TileSmem {
-    float depth[TILE_PX * 4];
-    uint32_t color[TILE_PX * 4];
-    uint32_t okey[TILE_PX * 4];              // owner keys (parity instrumentation only)
-    unsigned long long sorted[SORT_CAP];
-    uint32_t pixmask[(CHUNK + 1) / 32][TILE_PX];
-    float4 pool[POOL];                       // fragment records: 4 sample depths; aliased by BigSetup[]
-    uint8_t mpost[POOL];
-    uint32_t owner[TILE_PX];                 // 4 x u8 item id per pixel; reused as resolve staging
-    uint32_t pxm[NT];                        // per item: which bbox pixels are covered
-    uint32_t meta[NT];                       // per item: base | lx0 << 12 | ly0 << 16 | bw << 20
-    uint32_t scan[NT / 32];
-    uint32_t first_big, first_small, cut;
-    unsigned long long cnt[4];
+constexpr uint32_t FR_NONE = 0xFFFFu;
+
+struct FragPool {
+    float4 z[POOL];        // the 4 sample depths (0.0 where uncovered, like Fragment.sampled_depths)
+    uint32_t meta[POOL];   // item | pixel << 8 | coverage << 16
+    uint16_t next[POOL];   // per-pixel list link
+    uint8_t fin[POOL];     // post-depth mask | still-visible mask << 4
 };
-static_assert(sizeof(BigSetup) * CHUNK <= sizeof(float4) * POOL, "BigSetup run must fit in the pool");
 
 template <bool DBG>
-__global__ void __launch_bounds__(NT) tile_kernel(FrameParams P) {
+struct TileSmemT {
+    float depth[TILE_PX * 4];
+    uint32_t color[TILE_PX * 4];
+    uint32_t okey[DBG ? TILE_PX * 4 : 4]; // owner keys (parity instrumentation only)
+    float lut[256];                       // (b as f32) / 255.0   (Color::from_rgba, color.rs:22-29)
+    float it_f[13][NT];                   // items of the current chunk: px,py x3 | z x3 | inv | w x3
+    uint32_t it_key[NT], it_rec[NT];
+    uint32_t it_box[NT];                  // lx0 | ly0 << 8 | bw << 16 | fs << 24
+    uint32_t pre[NT + 1];                 // exclusive prefix of the in-tile bbox areas (work units)
+    union {
+        FragPool fr;
+        unsigned long long sorted[SORT_CAP];
+        BigSetup big[CHUNK];
+    } u;
+    uint32_t head[TILE_PX];               // per-pixel fragment list heads; reused as resolve staging
+    uint32_t scan[NT / 32];
+    uint32_t first_big, first_small, nfrag, ovf;
+    unsigned long long cnt[4];
+};
+
+// Sort the tile's list by order key (in shared memory when it fits, else in place in HBM) and
+// leave the sorted entries in the global bin.
+template <typename SM>
+__device__ __forceinline__ void sort_tile_list(SM &S, unsigned long long *bin, int n) {
+    __syncthreads();
+    if (n <= SORT_CAP) {
+        for (int i = threadIdx.x; i < n; i += NT) S.u.sorted[i] = __ldcg(bin + i);
+        __syncthreads();
+        block_sort(S.u.sorted, n);
+        for (int i = threadIdx.x; i < n; i += NT) __stcg(bin + i, S.u.sorted[i]);
+    } else {
+        block_sort(bin, n);
+    }
+    __syncthreads();
+}
+
+template <bool DBG>
+__global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileSmem &S = *reinterpret_cast<TileSmem *>(smem_raw);
+    typedef TileSmemT<DBG> SM;
+    SM &S = *reinterpret_cast<SM *>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tx = blockIdx.x % P.tiles_x, ty = P.ty_begin + blockIdx.x / P.tiles_x;
@@ -168,6 +205,9 @@ __global__ void __launch_bounds__(NT) tile_kernel(FrameParams P) {
     const int lx = tid % TW, ly = tid / TW;
     const int X = tileX0 + lx, Y = tileY0 + ly;
 
+    const uint32_t n_total = P.tile_count[tile];
+    const int n = (int)min(n_total, P.bin_cap);
+
     // clear (the state resolve_and_clear leaves behind, rasterizer/mod.rs:497-506)
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -175,26 +215,17 @@ __global__ void __launch_bounds__(NT) tile_kernel(FrameParams P) {
         S.color[tid * 4 + k] = CLEAR_COLOR;
         if (DBG) S.okey[tid * 4 + k] = NO_OWNER;
     }
-#pragma unroll
-    for (int k = 0; k < (CHUNK + 1) / 32; k++) S.pixmask[k][tid] = 0u;
-    if (tid < 4) S.cnt[tid] = 0ull;
-
     uint32_t c_cov = 0, c_shaded = 0, c_samples = 0, c_oob = 0;
 
-    const uint32_t n_total = P.tile_count[tile];
-    const int n = (int)min(n_total, P.bin_cap);
     if (n > 0) {
+        S.head[tid] = FR_NONE;
+        S.lut[tid] = fdiv((float)tid, 255.0f);
+        if (tid < 4) S.cnt[tid] = 0ull;
         unsigned long long *bin = P.bins + (size_t)tile * P.bin_cap;
-        const unsigned long long *list;
-        if (n <= SORT_CAP) {
-            for (int i = tid; i < n; i += NT) S.sorted[i] = bin[i];
-            __syncthreads();
-            block_sort(S.sorted, n);
-            list = S.sorted;
-        } else {
-            __syncthreads();
-            block_sort(bin, n); // rare: in place in global memory
-            list = bin;
+        bool sorted = false;
+        if (n > CHUNK) {
+            sort_tile_list(S, bin, n);
+            sorted = true;
         }
         __syncthreads();
 
@@ -207,7 +238,7 @@ __global__ void __launch_bounds__(NT) tile_kernel(FrameParams P) {
             int bx0 = 0, by0 = 0, bw = 0, bh = 0; // in-tile bbox, tile-local origin
             bool big = false;
             if (valid) {
-                rec = (uint32_t)list[item];
+                rec = (uint32_t)__ldcg(bin + item);
                 load_setup(P.recs, rec, s, key, fs);
                 BBox b = pixel_bbox(s, P.W, P.H);
                 const int x0 = max((int)b.x0, tileX0), x1 = min((int)b.x1, tileX0 + TW);
@@ -220,18 +251,24 @@ __global__ void __launch_bounds__(NT) tile_kernel(FrameParams P) {
             if (tid == 0) {
                 S.first_big = CHUNK + 1;
                 S.first_small = CHUNK + 1;
-                S.cut = CHUNK + 1;
             }
             __syncthreads();
             if (valid && big) atomicMin(&S.first_big, (uint32_t)tid);
             if (valid && !big) atomicMin(&S.first_small, (uint32_t)tid);
             __syncthreads();
             const int nvalid = min(CHUNK, n - pos);
+            const int first_big = (int)S.first_big, first_small = (int)S.first_small;
 
-            if (S.first_big == 0) {
+            if (!sorted && first_big <= CHUNK) { // large items need the ordered walk
+                sort_tile_list(S, bin, n);
+                sorted = true;
+                continue;
+            }
+
+            if (first_big == 0) {
                 // ================= run of large items: pixel-parallel =================
-                const int run = min((int)S.first_small, nvalid);
-                BigSetup *B = reinterpret_cast<BigSetup *>(S.pool);
+                const int run = min(first_small, nvalid);
+                BigSetup *B = S.u.big;
                 if (tid < run) {
                     BigSetup &b = B[tid];
 #pragma unroll
@@ -275,7 +312,8 @@ __global__ void __launch_bounds__(NT) tile_kernel(FrameParams P) {
                     if (!mp) continue;
                     c_shaded++;
                     c_samples += __popc(mp);
-                    const uint32_t argb = shade(q, &P.attrs[B[it].rec], B[it].fs, P.tex0, X, Y, mp, zs[0], c_oob);
+                    const uint32_t argb =
+                        shade(q, &P.attrs[B[it].rec], B[it].fs, P.tex0, S.lut, X, Y, mp, zs[0], c_oob);
 #pragma unroll
                     for (int k = 0; k < 4; k++)
                         if ((mp >> k) & 1u) {
@@ -295,128 +333,175 @@ __global__ void __launch_bounds__(NT) tile_kernel(FrameParams P) {
                 continue;
             }
 
-            // ================= chunk of small items: triangle-parallel =================
-            int cnt = min((int)S.first_big, nvalid);
-            const bool mine = tid < cnt;
-            // ---- phase 1a: exact coverage of every bbox pixel (<= 32) ----
-            unsigned long long cov_lo = 0ull, cov_hi = 0ull;
-            uint32_t pxm = 0, ncov = 0;
-            if (mine) {
-                int j = 0;
-                for (int ry = 0; ry < bh; ry++)
-                    for (int rx = 0; rx < bw; rx++, j++) {
-                        const uint32_t m = coverage_mask(s, tileX0 + bx0 + rx, tileY0 + by0 + ry);
-                        if (m) {
-                            if (j < 16) cov_lo |= (unsigned long long)m << (4 * j);
-                            else cov_hi |= (unsigned long long)m << (4 * (j - 16));
-                            pxm |= 1u << j;
-                            ncov++;
-                        }
-                    }
+            // ================= chunk of small items =================
+            int cnt = sorted ? min(first_big, nvalid) : nvalid;
+            // ---- phase A0: item table + exclusive scan of the in-tile bbox areas ----
+            const uint32_t area = (tid < cnt) ? (uint32_t)(bw * bh) : 0u;
+            if (tid < cnt) {
+                S.it_f[0][tid] = s.px[0]; S.it_f[1][tid] = s.py[0]; S.it_f[2][tid] = s.px[1];
+                S.it_f[3][tid] = s.py[1]; S.it_f[4][tid] = s.px[2]; S.it_f[5][tid] = s.py[2];
+                S.it_f[6][tid] = s.z[0]; S.it_f[7][tid] = s.z[1]; S.it_f[8][tid] = s.z[2];
+                S.it_f[9][tid] = s.inv;
+                S.it_f[10][tid] = s.w[0]; S.it_f[11][tid] = s.w[1]; S.it_f[12][tid] = s.w[2];
+                S.it_key[tid] = key; S.it_rec[tid] = rec;
+                S.it_box[tid] = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bw << 16) | (fs << 24);
             }
-            // block exclusive scan of ncov -> record base
-            uint32_t incl = ncov;
+            uint32_t incl = area;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += v;
             }
             if (lane == 31) S.scan[warp] = incl;
+            if (tid == 0) {
+                S.nfrag = 0;
+                S.ovf = 0;
+            }
             __syncthreads();
             uint32_t wbase = 0;
 #pragma unroll
             for (int k = 0; k < NT / 32; k++)
                 if (k < warp) wbase += S.scan[k];
-            const uint32_t base = wbase + incl - ncov;
-            if (mine && base + ncov > POOL) atomicMin(&S.cut, (uint32_t)tid); // defer the rest to the next chunk
+            S.pre[tid] = wbase + incl - area; // exclusive prefix: first work unit of item <tid>
+            if (tid == NT - 1) S.pre[NT] = wbase + incl;
             __syncthreads();
-            cnt = min(cnt, (int)S.cut);
-            const bool act = tid < cnt;
-            // ---- phase 1b: sample depths -> records; publish per-pixel item bits ----
-            if (act) {
-                S.pxm[tid] = pxm;
-                S.meta[tid] = base | ((uint32_t)bx0 << 12) | ((uint32_t)by0 << 16) | ((uint32_t)bw << 20);
-                c_cov += ncov;
-                uint32_t bits = pxm, r = base;
-                while (bits) {
-                    const int j = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    const int ry = j / bw, rx = j - ry * bw;
-                    const uint32_t m = (uint32_t)((j < 16 ? cov_lo >> (4 * j) : cov_hi >> (4 * (j - 16))) & 0xFull);
-                    const int PX = tileX0 + bx0 + rx, PY = tileY0 + by0 + ry;
-                    float4 z;
-                    z.x = (m & 1u) ? sample_depth(s, PX, PY, 0) : 0.0f;
-                    z.y = (m & 2u) ? sample_depth(s, PX, PY, 1) : 0.0f;
-                    z.z = (m & 4u) ? sample_depth(s, PX, PY, 2) : 0.0f;
-                    z.w = (m & 8u) ? sample_depth(s, PX, PY, 3) : 0.0f;
-                    S.pool[r] = z;
-                    S.mpost[r] = (uint8_t)m; // pre-depth mask for phase 2, replaced by the post-depth mask
-                    const int p = (by0 + ry) * TW + bx0 + rx;
-                    atomicOr(&S.pixmask[tid >> 5][p], 1u << (tid & 31));
-                    r++;
-                }
-            }
-            __syncthreads();
-            // ---- phase 2: thread = pixel, ordered depth resolve ----
-            {
-                float d0 = S.depth[tid * 4], d1 = S.depth[tid * 4 + 1], d2 = S.depth[tid * 4 + 2],
-                      d3 = S.depth[tid * 4 + 3];
-                uint32_t own = 0xFFFFFFFFu;
-                const int nwords = (cnt + 31) >> 5;
-                for (int wd = 0; wd < nwords; wd++) {
-                    uint32_t bits = S.pixmask[wd][tid];
-                    if (!bits) continue;
-                    S.pixmask[wd][tid] = 0u;
-                    while (bits) {
-                        const int it = (wd << 5) + __ffs(bits) - 1;
-                        bits &= bits - 1;
-                        const uint32_t meta = S.meta[it];
-                        const int ibw = (int)(meta >> 20);
-                        const int j = (ly - (int)((meta >> 16) & 0xF)) * ibw + (lx - (int)((meta >> 12) & 0xF));
-                        const uint32_t r = (meta & 0xFFFu) + __popc(S.pxm[it] & ((1u << j) - 1u));
-                        const uint32_t m = S.mpost[r];
-                        const float4 z = S.pool[r];
-                        uint32_t mp = 0;
-                        if ((m & 1u) && z.x < d0) { mp |= 1u; d0 = z.x; own = (own & 0xFFFFFF00u) | (uint32_t)it; }
-                        if ((m & 2u) && z.y < d1) { mp |= 2u; d1 = z.y; own = (own & 0xFFFF00FFu) | ((uint32_t)it << 8); }
-                        if ((m & 4u) && z.z < d2) { mp |= 4u; d2 = z.z; own = (own & 0xFF00FFFFu) | ((uint32_t)it << 16); }
-                        if ((m & 8u) && z.w < d3) { mp |= 8u; d3 = z.w; own = (own & 0x00FFFFFFu) | ((uint32_t)it << 24); }
-                        S.mpost[r] = (uint8_t)mp;
+
+            bool need_sort = false;
+            for (;;) {
+                // ---- phase A: thread = (item, bbox pixel) work unit, spread evenly over the CTA ----
+                const int units = (int)S.pre[cnt];
+                uint32_t cov_try = 0;
+                for (int u0 = 0; u0 < units; u0 += NT) {
+                    const int u = u0 + tid;
+                    uint32_t m = 0, it = 0, p = 0;
+                    Setup q;
+                    int PX = 0, PY = 0;
+                    if (u < units) {
+                        int lo = 0, hi = cnt; // last item whose first unit is <= u
+                        while (hi - lo > 1) {
+                            const int mid = (lo + hi) >> 1;
+                            if ((int)S.pre[mid] <= u) lo = mid; else hi = mid;
+                        }
+                        it = (uint32_t)lo;
+                        const uint32_t box = S.it_box[it];
+                        const int ibw = (int)((box >> 16) & 0xFFu);
+                        const int j = u - (int)S.pre[it];
+                        const int ry = j / ibw, rx = j - ry * ibw;
+                        const int lpx = (int)(box & 0xFFu) + rx, lpy = (int)((box >> 8) & 0xFFu) + ry;
+                        p = (uint32_t)(lpy * TW + lpx);
+                        PX = tileX0 + lpx; PY = tileY0 + lpy;
+                        q.px[0] = S.it_f[0][it]; q.py[0] = S.it_f[1][it]; q.px[1] = S.it_f[2][it];
+                        q.py[1] = S.it_f[3][it]; q.px[2] = S.it_f[4][it]; q.py[2] = S.it_f[5][it];
+                        setup_normals(q);
+                        m = coverage_mask(q, PX, PY);
+                    }
+                    const uint32_t bal = __ballot_sync(0xffffffffu, m != 0u);
+                    if (bal) { // warp-aggregated fragment allocation (ballot + popc prefix)
+                        uint32_t slot = 0;
+                        if (lane == 0) slot = atomicAdd(&S.nfrag, (uint32_t)__popc(bal));
+                        slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(bal & lanemask_lt());
+                        if (m) {
+                            cov_try++;
+                            if (slot < POOL) {
+                                q.z[0] = S.it_f[6][it]; q.z[1] = S.it_f[7][it]; q.z[2] = S.it_f[8][it];
+                                q.inv = S.it_f[9][it];
+                                float4 z;
+                                z.x = (m & 1u) ? sample_depth(q, PX, PY, 0) : 0.0f;
+                                z.y = (m & 2u) ? sample_depth(q, PX, PY, 1) : 0.0f;
+                                z.z = (m & 4u) ? sample_depth(q, PX, PY, 2) : 0.0f;
+                                z.w = (m & 8u) ? sample_depth(q, PX, PY, 3) : 0.0f;
+                                S.u.fr.z[slot] = z;
+                                S.u.fr.meta[slot] = it | (p << 8) | (m << 16);
+                                S.u.fr.next[slot] = (uint16_t)atomicExch(&S.head[p], slot);
+                            } else {
+                                S.ovf = 1u;
+                            }
+                        }
                     }
                 }
-                S.depth[tid * 4] = d0; S.depth[tid * 4 + 1] = d1; S.depth[tid * 4 + 2] = d2; S.depth[tid * 4 + 3] = d3;
-                S.owner[tid] = own;
+                __syncthreads();
+                if (!S.ovf) {
+                    c_cov += cov_try;
+                    break;
+                }
+                // The chunk's fragments do not fit the pool.  Nothing has touched the tile state yet:
+                // drop them and retry with half the items.  Chunks must follow submission order, so an
+                // unsorted list is sorted first.
+                __syncthreads();
+                S.head[tid] = FR_NONE;
+                if (tid == 0) {
+                    S.nfrag = 0;
+                    S.ovf = 0;
+                }
+                if (!sorted) {
+                    need_sort = true;
+                    break;
+                }
+                cnt = max(1, cnt >> 1);
+                __syncthreads();
             }
-            __syncthreads();
-            // ---- phase 3: thread = item, shade the fragments that are still visible ----
-            if (act) {
-                uint32_t bits = pxm, r = base;
-                while (bits) {
-                    const int j = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    const uint32_t mp = S.mpost[r];
-                    const float depth0 = S.pool[r].x;
-                    r++;
-                    if (!mp) continue;
+            if (need_sort) {
+                sort_tile_list(S, bin, n);
+                sorted = true;
+                continue;
+            }
+            const int nfrag = (int)S.nfrag;
+            // ---- phase B: thread = fragment; what would the ordered replay have done with it? ----
+            for (int f = tid; f < nfrag; f += NT) {
+                const uint32_t meta = S.u.fr.meta[f];
+                const uint32_t p = (meta >> 8) & 0xFFu, m = (meta >> 16) & 0xFu;
+                const uint32_t mykey = S.it_key[meta & 0xFFu];
+                const float4 z = S.u.fr.z[f];
+                const float4 dold = *reinterpret_cast<const float4 *>(&S.depth[p * 4]);
+                uint32_t mp = m & ((z.x < dold.x ? 1u : 0u) | (z.y < dold.y ? 2u : 0u) | (z.z < dold.z ? 4u : 0u) |
+                                   (z.w < dold.w ? 8u : 0u));
+                uint32_t blocked = 0, lost = 0;
+                for (uint32_t g = S.head[p]; g != FR_NONE; g = S.u.fr.next[g]) {
+                    if ((int)g == f) continue;
+                    const uint32_t mg = S.u.fr.meta[g];
+                    const uint32_t cg = (mg >> 16) & 0xFu;
+                    const float4 zg = S.u.fr.z[g];
+                    if (S.it_key[mg & 0xFFu] < mykey) { // drawn before F: it blocks where z_G <= z_F
+                        blocked |= cg & ((zg.x <= z.x ? 1u : 0u) | (zg.y <= z.y ? 2u : 0u) | (zg.z <= z.z ? 4u : 0u) |
+                                         (zg.w <= z.w ? 8u : 0u));
+                    } else {                            // drawn after F: it overwrites where z_G < z_F
+                        lost |= cg & ((zg.x < z.x ? 1u : 0u) | (zg.y < z.y ? 2u : 0u) | (zg.z < z.z ? 4u : 0u) |
+                                      (zg.w < z.w ? 8u : 0u));
+                    }
+                }
+                mp &= ~blocked;
+                S.u.fr.fin[f] = (uint8_t)(mp | ((mp & ~lost) << 4));
+                if (mp) {
                     c_shaded++;
                     c_samples += __popc(mp);
-                    const int ry = j / bw, rx = j - ry * bw;
-                    const int p = (by0 + ry) * TW + bx0 + rx;
-                    const uint32_t own = S.owner[p];
-                    uint32_t f = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (((mp >> k) & 1u) && ((own >> (8 * k)) & 0xFFu) == (uint32_t)tid) f |= 1u << k;
-                    if (!f) continue; // overwritten later in this chunk: its colour can never be seen
-                    const uint32_t argb =
-                        shade(s, &P.attrs[rec], fs, P.tex0, tileX0 + bx0 + rx, tileY0 + by0 + ry, mp, depth0, c_oob);
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if ((f >> k) & 1u) {
-                            S.color[p * 4 + k] = argb;
-                            if (DBG) S.okey[p * 4 + k] = key;
-                        }
                 }
+            }
+            __syncthreads();
+            // ---- phase C: thread = fragment; shade what is still visible and write its samples ----
+            for (int f = tid; f < nfrag; f += NT) {
+                const uint32_t fin = S.u.fr.fin[f];
+                const uint32_t meta = S.u.fr.meta[f];
+                const uint32_t p = (meta >> 8) & 0xFFu;
+                S.head[p] = FR_NONE;
+                const uint32_t vis = fin >> 4;
+                if (!vis) continue;
+                const uint32_t it = meta & 0xFFu;
+                Setup q;
+                q.px[0] = S.it_f[0][it]; q.py[0] = S.it_f[1][it]; q.px[1] = S.it_f[2][it];
+                q.py[1] = S.it_f[3][it]; q.px[2] = S.it_f[4][it]; q.py[2] = S.it_f[5][it];
+                q.w[0] = S.it_f[10][it]; q.w[1] = S.it_f[11][it]; q.w[2] = S.it_f[12][it];
+                setup_normals(q);
+                const float4 z = S.u.fr.z[f];
+                const uint32_t argb = shade(q, &P.attrs[S.it_rec[it]], S.it_box[it] >> 24, P.tex0, S.lut,
+                                            tileX0 + (int)(p % TW), tileY0 + (int)(p / TW), fin & 0xFu, z.x, c_oob);
+                const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if ((vis >> k) & 1u) {
+                        S.color[p * 4 + k] = argb;
+                        S.depth[p * 4 + k] = zz[k];
+                        if (DBG) S.okey[p * 4 + k] = S.it_key[it];
+                    }
             }
             __syncthreads();
             pos += cnt;
@@ -436,36 +521,38 @@ __global__ void __launch_bounds__(NT) tile_kernel(FrameParams P) {
         }
     }
     if ((P.W & 3u) == 0u) {
-        S.owner[tid] = res; // stage, then 64 threads issue 128-bit row stores
+        S.head[tid] = res; // stage, then 64 threads issue 128-bit row stores
         __syncthreads();
         if (tid < TH * (TW / 4)) {
             const int row = tid / (TW / 4), q = tid % (TW / 4);
             const int Yr = tileY0 + row, Xq = tileX0 + q * 4;
             if (Yr < (int)P.H && Xq < (int)P.W)
                 *reinterpret_cast<uint4 *>(&P.out[(size_t)Yr * P.W + Xq]) =
-                    *reinterpret_cast<const uint4 *>(&S.owner[row * TW + q * 4]);
+                    *reinterpret_cast<const uint4 *>(&S.head[row * TW + q * 4]);
         }
     } else if (X < (int)P.W && Y < (int)P.H) {
         P.out[(size_t)Y * P.W + X] = res;
     }
 
     // ---- counters ----
-    c_cov = __reduce_add_sync(0xffffffffu, c_cov);
-    c_shaded = __reduce_add_sync(0xffffffffu, c_shaded);
-    c_samples = __reduce_add_sync(0xffffffffu, c_samples);
-    c_oob = __reduce_add_sync(0xffffffffu, c_oob);
-    if (lane == 0) {
-        if (c_cov) atomicAdd(&S.cnt[0], (unsigned long long)c_cov);
-        if (c_shaded) atomicAdd(&S.cnt[1], (unsigned long long)c_shaded);
-        if (c_samples) atomicAdd(&S.cnt[2], (unsigned long long)c_samples);
-        if (c_oob) atomicAdd(&S.cnt[3], (unsigned long long)c_oob);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        if (S.cnt[0]) atomicAdd(&P.fs->counters[C_COVERED_PX], S.cnt[0]);
-        if (S.cnt[1]) atomicAdd(&P.fs->counters[C_SHADED_PX], S.cnt[1]);
-        if (S.cnt[2]) atomicAdd(&P.fs->counters[C_SAMPLES], S.cnt[2]);
-        if (S.cnt[3]) atomicAdd(&P.fs->counters[C_TEX_OOB], S.cnt[3]);
+    if (n > 0) {
+        c_cov = __reduce_add_sync(0xffffffffu, c_cov);
+        c_shaded = __reduce_add_sync(0xffffffffu, c_shaded);
+        c_samples = __reduce_add_sync(0xffffffffu, c_samples);
+        c_oob = __reduce_add_sync(0xffffffffu, c_oob);
+        if (lane == 0) {
+            if (c_cov) atomicAdd(&S.cnt[0], (unsigned long long)c_cov);
+            if (c_shaded) atomicAdd(&S.cnt[1], (unsigned long long)c_shaded);
+            if (c_samples) atomicAdd(&S.cnt[2], (unsigned long long)c_samples);
+            if (c_oob) atomicAdd(&S.cnt[3], (unsigned long long)c_oob);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (S.cnt[0]) atomicAdd(&P.fs->counters[C_COVERED_PX], S.cnt[0]);
+            if (S.cnt[1]) atomicAdd(&P.fs->counters[C_SHADED_PX], S.cnt[1]);
+            if (S.cnt[2]) atomicAdd(&P.fs->counters[C_SAMPLES], S.cnt[2]);
+            if (S.cnt[3]) atomicAdd(&P.fs->counters[C_TEX_OOB], S.cnt[3]);
+        }
     }
 }
 

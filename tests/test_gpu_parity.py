@@ -104,6 +104,45 @@ def test_random_soup():
         check(s)
 
 
+def test_near_degenerate_fuzz_backface_margin():
+    """near-collinear triangles whose computed area is 0 or slightly NEGATIVE can
+    still cover a sample through the tie-break.  The geometry stage culls back-facing triangles
+    only beyond a rigorous rounding margin; this fuzz (slivers through sample points, both
+    windings, at pixel scale) must stay bit-exact, including the survey's own counterexample."""
+    rng = np.random.RandomState(11)
+    W, H = 1536, 1152
+    nt = 60000
+    # slivers: two far-apart points and a third one very close to the segment between them,
+    # nudged to pass (almost) exactly through an RGSS sample position
+    a = rng.uniform(8, 1100, (nt, 2))
+    d = rng.uniform(-60, 60, (nt, 2))
+    b = a + d
+    t = rng.uniform(0.2, 0.8, (nt, 1))
+    samp = np.array([[0.625, 0.125], [0.875, 0.625], [0.375, 0.875], [0.125, 0.375]])
+    c = np.floor(a + t * d) + samp[rng.randint(0, 4, nt)]
+    a = c - t * d
+    b = c + (1 - t) * d
+    c = c + rng.normal(0, 1, (nt, 2)) * (10.0 ** rng.uniform(-7, -2, (nt, 1)))
+    pts = np.stack([a, b, c], 1).astype(np.float32)  # screen-space xy
+    # the survey's counterexample (area2 = -3.05e-05, yet pixel (1059,1009) sample 1 is covered)
+    pts[0] = [[1045.8563232421875, 1019.8419799804688], [1098.50146484375, 981.4735717773438],
+              [1058.9920654296875, 1010.2684936523438]]
+    flip = rng.rand(nt) < 0.5
+    pts[flip] = pts[flip][:, ::-1]
+    # screen -> clip with w = 1 under identity matrices: x_ndc = 2x/W - 1, y_ndc = 1 - 2y/H
+    verts = np.zeros((nt, 3, 3), np.float32)
+    verts[..., 0] = pts[..., 0] * np.float32(2.0 / W) - np.float32(1.0)
+    verts[..., 1] = np.float32(1.0) - pts[..., 1] * np.float32(2.0 / H)
+    verts[..., 2] = rng.uniform(-0.5, 0.5, (nt, 1)).astype(np.float32)
+    attrs = rng.uniform(0, 1, (nt * 3, 6)).astype(np.float32)
+    mesh = Mesh(verts.reshape(-1, 3), np.arange(nt * 3, dtype=np.uint32), attrs)
+    s = scenes.sphere_scene(width=W, height=H, mesh=mesh, fs=1)
+    s.view, s.projection = mathx.identity(), mathx.identity()
+    s.draws[0].world = mathx.identity()
+    o, g = check(s)
+    assert o["counters"]["n_covered_px"] > 100
+
+
 def test_empty_and_degenerate_inputs():
     """Empty mesh, zero-area triangles, a frame with no draws."""
     from rusterizer_b200.render import Renderer
@@ -190,4 +229,9 @@ def test_capacity_growth_dense_tile():
     s = scenes.overdraw_scene(8, 8, width=64, height=64)
     layers = [scenes.Draw(d.mesh, d.world, d.fs) for d in s.draws] * 200  # 800 draws into 16 tiles
     s.draws = layers
+    check(s)
+    # ~5 px cells, 40 layers: chunks of 255 small items whose fragments overflow the shared-memory
+    # fragment pool -> the chunk is halved until it fits
+    s = scenes.overdraw_scene(12, 12, width=64, height=64)
+    s.draws = [scenes.Draw(d.mesh, d.world, d.fs) for d in s.draws] * 10
     check(s)
