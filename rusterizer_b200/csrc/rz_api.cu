@@ -63,6 +63,9 @@ struct rz_ctx {
     unsigned long long *d_cnt_backup = nullptr;
     float *d_dbg_depth = nullptr;
     uint32_t *d_dbg_color = nullptr, *d_dbg_owner = nullptr;
+    float4 *d_vclip = nullptr, *d_vscr = nullptr; // vertex-stage scratch, sized for the largest mesh
+    uint32_t *d_vcode = nullptr;
+    uint32_t vert_cap = 0;
     uint32_t rec_cap = 0, bin_cap = 0, large_cap = 0;
     bool debug = false;
 
@@ -121,6 +124,20 @@ static int free_frame_buffers(rz_ctx *c) {
     cudaFree(c->d_recs); c->d_recs = nullptr;
     cudaFree(c->d_attrs); c->d_attrs = nullptr;
     cudaFree(c->d_large); c->d_large = nullptr;
+    cudaFree(c->d_vclip); c->d_vclip = nullptr;
+    cudaFree(c->d_vscr); c->d_vscr = nullptr;
+    cudaFree(c->d_vcode); c->d_vcode = nullptr;
+    return RZ_OK;
+}
+
+static int ensure_vertex_scratch(rz_ctx *c, uint32_t nv) {
+    if (nv <= c->vert_cap) return RZ_OK;
+    cudaFree(c->d_vclip); cudaFree(c->d_vscr); cudaFree(c->d_vcode);
+    c->d_vclip = c->d_vscr = nullptr; c->d_vcode = nullptr; c->vert_cap = 0;
+    CU(c, cudaMalloc(&c->d_vclip, (size_t)nv * sizeof(float4)));
+    CU(c, cudaMalloc(&c->d_vscr, (size_t)nv * sizeof(float4)));
+    CU(c, cudaMalloc(&c->d_vcode, (size_t)nv * sizeof(uint32_t)));
+    c->vert_cap = nv;
     return RZ_OK;
 }
 
@@ -366,7 +383,15 @@ static FrameParams make_params(rz_ctx *c, uint32_t *out_base) {
 // Enqueue one whole frame on the ctx stream.  timed: record stage events.
 static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     uint64_t total_tris = 0;
-    for (auto &d : c->draws) total_tris += d.mesh->n_idx / 3;
+    uint32_t max_nv = 0;
+    for (auto &d : c->draws) {
+        total_tris += d.mesh->n_idx / 3;
+        max_nv = std::max(max_nv, d.mesh->nv);
+    }
+    {
+        int rc = ensure_vertex_scratch(c, max_nv);
+        if (rc != RZ_OK) return rc;
+    }
     if (total_tris > 0x1FFFFFFFull) return fail(c, RZ_E_INVALID, "frame has more than 2^29 triangles");
     {
         uint32_t want_rec = std::max<uint64_t>(c->rec_cap, total_tris + 1024);
@@ -388,8 +413,10 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
         D.pos = d.mesh->d_pos; D.attr = d.mesh->d_attr; D.idx = d.mesh->d_idx;
         D.nv = d.mesh->nv; D.nt = nt; D.tri_base = tri_base; D.fs = d.fs;
         memcpy(D.M, d.M, 64);
+        D.clip = c->d_vclip; D.scr = c->d_vscr; D.code = c->d_vcode;
+        vertex_kernel<<<(D.nv + NT - 1) / NT, NT, 0, st>>>(P, D);
         geom_kernel<<<(nt + NT - 1) / NT, NT, 0, st>>>(P, D);
-        c->launches++;
+        c->launches += 2;
         tri_base += nt;
     }
     if (timed) CU(c, cudaEventRecord(c->ev[1], st));
@@ -581,19 +608,21 @@ int rz_debug_vertex_stage(rz_ctx *c, const rz_mesh *mesh, float *out_clip) {
     if (!c || !mesh || !out_clip) return RZ_E_INVALID;
     CU(c, cudaSetDevice(c->device));
     if (mesh->nv == 0) return RZ_OK;
+    CU(c, cudaStreamSynchronize(c->stream));
+    int rc = ensure_vertex_scratch(c, mesh->nv);
+    if (rc != RZ_OK) return rc;
+    FrameParams P = make_params(c, c->d_out);
     DrawParams D;
     memset(&D, 0, sizeof D);
     float pv[16];
     mat4_mul(c->proj, c->view, pv);
     mat4_mul(pv, c->world, D.M);
-    float4 *d_out = nullptr;
-    CU(c, cudaMalloc(&d_out, (size_t)mesh->nv * 16));
-    vertex_kernel<<<(mesh->nv + NT - 1) / NT, NT, 0, c->stream>>>(mesh->d_pos, mesh->nv, D, d_out);
+    D.pos = mesh->d_pos; D.nv = mesh->nv;
+    D.clip = c->d_vclip; D.scr = c->d_vscr; D.code = c->d_vcode;
+    vertex_kernel<<<(mesh->nv + NT - 1) / NT, NT, 0, c->stream>>>(P, D);
     c->launches++;
-    cudaError_t e = cudaMemcpyAsync(out_clip, d_out, (size_t)mesh->nv * 16, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(d_out);
-    if (e != cudaSuccess) return fail(c, RZ_E_CUDA, "rz_debug_vertex_stage: %s", cudaGetErrorString(e));
+    CU(c, cudaMemcpyAsync(out_clip, c->d_vclip, (size_t)mesh->nv * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
     return RZ_OK;
 }
 

@@ -106,6 +106,25 @@ __device__ __forceinline__ uint32_t coverage_mask(const Setup &s, int X, int Y) 
     return mask;
 }
 
+// Same mask, branch-free, with the per-edge tie-break (n.x > 0 || (n.x == 0 && n.y < 0)) precomputed
+// in bits 0..2 of `tb`: edge k passes iff e > 0, or e is not < 0 (zero or NaN -- the reference
+// sends both to the normal tests) and bit k of tb is set.
+__device__ __forceinline__ uint32_t coverage_mask_tb(const Setup &s, uint32_t tb, int X, int Y) {
+    uint32_t mask = 0;
+    const float fx = (float)X, fy = (float)Y;
+    const uint32_t t0 = tb & 1u, t1 = (tb >> 1) & 1u, t2 = (tb >> 2) & 1u;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float xs = fadd(fx, rgss_x(i)), ys = fadd(fy, rgss_y(i));
+        const float e0 = edge_eval(s, 0, xs, ys), e1 = edge_eval(s, 1, xs, ys), e2 = edge_eval(s, 2, xs, ys);
+        const uint32_t p0 = (uint32_t)(e0 > 0.0f) | (t0 & (uint32_t)!(e0 < 0.0f));
+        const uint32_t p1 = (uint32_t)(e1 > 0.0f) | (t1 & (uint32_t)!(e1 < 0.0f));
+        const uint32_t p2 = (uint32_t)(e2 > 0.0f) | (t2 & (uint32_t)!(e2 < 0.0f));
+        mask |= (p0 & p1 & p2) << i;
+    }
+    return mask;
+}
+
 // interpolate_depth closure of RasterizerTriangle::fragment (rasterizer/mod.rs:226-236)
 __device__ __forceinline__ float sample_depth(const Setup &s, int X, int Y, int i) {
     float xs = fadd((float)X, rgss_x(i)), ys = fadd((float)Y, rgss_y(i));

@@ -42,26 +42,26 @@ struct GeomLocal {
     unsigned long long bbox;
 };
 
-// Rasterizer::perspective_divide + viewport_transform + RasterizerTriangle::new + bounding_box
-// (rasterizer/mod.rs:284-361) for one clip-space triangle, then cull / record / bin.
+// Rasterizer::perspective_divide + viewport_transform for one vertex (rasterizer/mod.rs:284-331):
+// clip (x,y,z,w) -> screen (x, y, depth) ; w is kept as depths_camera_space.
+__device__ __forceinline__ float4 project_vertex(const float *c, float Wf, float Hf) {
+    const float w = c[3];
+    const float nx = fdiv(c[0], w), ny = fdiv(c[1], w), nz = fdiv(c[2], w);
+    float4 r;
+    // `/ 2.0` is computed as `* 0.5`: scaling by a power of two rounds identically
+    r.x = fmul(fmul(Wf, fadd(nx, 1.0f)), 0.5f);
+    r.y = fmul(Hf, fsub(1.0f, fmul(fadd(ny, 1.0f), 0.5f)));
+    r.z = fadd(fmul(fmul(fadd(nz, 1.0f), 0.5f), 1.0f), 0.0f); // (z+1)*0.5*(zmax-zmin)+zmin
+    r.w = w;
+    return r;
+}
+
+// RasterizerTriangle::new + bounding_box (rasterizer/mod.rs:187-222,347-361) for one screen-space
+// triangle (s.px/py/z/w filled), then cull / record / bin.
 // a0,a1,a2 point at the three VertexAttributes (6 floats each; global or local memory).
-__device__ __forceinline__ void emit_triangle(const FrameParams &P, uint32_t fs_id, const float *c0, const float *c1,
-                                              const float *c2, const float *a0, const float *a1, const float *a2,
-                                              uint32_t key, GeomLocal &lc) {
-    Setup s;
-    const float Wf = (float)P.W, Hf = (float)P.H;
-    const float *cv[3] = {c0, c1, c2};
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        float w = cv[i][3];
-        float nx = fdiv(cv[i][0], w), ny = fdiv(cv[i][1], w), nz = fdiv(cv[i][2], w);
-        // `/ 2.0` is computed as `* 0.5`: scaling by a power of two rounds identically
-        s.px[i] = fmul(fmul(Wf, fadd(nx, 1.0f)), 0.5f);
-        s.py[i] = fmul(Hf, fsub(1.0f, fmul(fadd(ny, 1.0f), 0.5f)));
-        s.z[i] = fadd(fmul(fmul(fadd(nz, 1.0f), 0.5f), 1.0f), 0.0f); // (z+1)*0.5*(zmax-zmin)+zmin
-        s.w[i] = w;
-    }
-    setup_edges(s);
+__device__ __forceinline__ void emit_setup(const FrameParams &P, uint32_t fs_id, Setup &s, const float *a0,
+                                           const float *a1, const float *a2, uint32_t key, GeomLocal &lc) {
+    setup_normals(s); // inv_2x_area is recomputed by the tile stage; nothing here needs it
     lc.c[C_TRIS_SETUP]++;
 
     BBox b = pixel_bbox(s, P.W, P.H);
@@ -146,6 +146,41 @@ __device__ __forceinline__ float clip_distance(int plane, const float *p) {
     return (plane & 1) ? fsub(p[3], c) : fadd(p[3], c);
 }
 
+// outcode bits of one clip-space vertex (clipping.rs:86-104): for axis a in x,y,z
+//   bit a     : v[a] >= -w     bit 3+a : v[a] <= w     bit 6+a : v[a] < -w     bit 9+a : v[a] > w
+__device__ __forceinline__ uint32_t clip_code(const float *c) {
+    const float w = c[3], nw = -w;
+    uint32_t code = 0;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        code |= (c[a] >= nw ? 1u : 0u) << a;
+        code |= (c[a] <= w ? 1u : 0u) << (3 + a);
+        code |= (c[a] < nw ? 1u : 0u) << (6 + a);
+        code |= (c[a] > w ? 1u : 0u) << (9 + a);
+    }
+    return code;
+}
+
+// Stage 1a -- vertex stage (render.rs:104-108): one thread per mesh vertex.  The vertex shader
+// (main.rs:147-152) is ((P*V)*W) * (x,y,z,1); the matrix product is hoisted to the host in the same
+// operation order.  Besides the clip-space position it stores what every
+// triangle using the vertex would recompute: the perspective divide + viewport transform and the
+// 12 trivial-accept/reject comparisons.
+__global__ void __launch_bounds__(NT) vertex_kernel(FrameParams P, DrawParams D) {
+    const uint32_t v = blockIdx.x * NT + threadIdx.x;
+    if (v >= D.nv) return;
+    const float *p = D.pos + 3 * (size_t)v;
+    const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+    float c[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) c[r] = dot4z(D.M[4 * r], D.M[4 * r + 1], D.M[4 * r + 2], D.M[4 * r + 3], x, y, z, 1.0f);
+    D.clip[v] = make_float4(c[0], c[1], c[2], c[3]);
+    D.scr[v] = project_vertex(c, (float)P.W, (float)P.H);
+    D.code[v] = clip_code(c);
+}
+
+// Stage 1b/2 -- primitive assembly, clip, setup, binning: one thread per input triangle
+// (render.rs:75-96, rasterizer/mod.rs:425-441).
 __global__ void __launch_bounds__(NT) geom_kernel(FrameParams P, DrawParams D) {
     __shared__ unsigned long long s_cnt[C_COUNT];
     if (threadIdx.x < C_COUNT) s_cnt[threadIdx.x] = 0ull;
@@ -164,54 +199,37 @@ __global__ void __launch_bounds__(NT) geom_kernel(FrameParams P, DrawParams D) {
             atomicOr(&P.fs->err, ERR_INDEX); // the reference panics here (render.rs:83-87)
         } else {
             lc.c[C_TRIS_IN]++;
-            // vertex shader (main.rs:147-152): ((P*V)*W) * (x,y,z,1); the matrix product is hoisted
-            // to the host in the same operation order
             const uint32_t vi[3] = {i0, i1, i2};
-            float c[3][4];
-#pragma unroll
-            for (int v = 0; v < 3; v++) {
-                const float *p = D.pos + 3 * (size_t)vi[v];
-                float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
-#pragma unroll
-                for (int r = 0; r < 4; r++)
-                    c[v][r] = dot4z(D.M[4 * r], D.M[4 * r + 1], D.M[4 * r + 2], D.M[4 * r + 3], x, y, z, 1.0f);
-            }
             const uint32_t key0 = (D.tri_base + t) * 8u;
-
-            // clipping::try_clip (rasterizer/clipping.rs:62-195)
-            float a2x = cross2(fsub(c[1][0], c[0][0]), fsub(c[1][1], c[0][1]), fsub(c[2][0], c[0][0]),
-                               fsub(c[2][1], c[0][1]));
+            // clipping::try_clip (rasterizer/clipping.rs:62-195): degenerate test on clip-space xy first
+            const float2 q0 = __ldg(reinterpret_cast<const float2 *>(&D.clip[i0]));
+            const float2 q1 = __ldg(reinterpret_cast<const float2 *>(&D.clip[i1]));
+            const float2 q2 = __ldg(reinterpret_cast<const float2 *>(&D.clip[i2]));
+            const float a2x = cross2(fsub(q1.x, q0.x), fsub(q1.y, q0.y), fsub(q2.x, q0.x), fsub(q2.y, q0.y));
             if (fabsf(a2x) < 0.000001f) {
                 lc.c[C_DEGENERATE]++;
             } else {
-                bool all_in = true, any_out = false;
-#pragma unroll
-                for (int ax = 0; ax < 3; ax++) {
-                    bool in_lo = true, in_hi = true, out_lo = true, out_hi = true;
+                const uint32_t code = __ldg(&D.code[i0]) & __ldg(&D.code[i1]) & __ldg(&D.code[i2]);
+                if (code & 0xFC0u) { // all three vertices outside one plane
+                    lc.c[C_OUTSIDE]++;
+                } else if ((code & 0x3Fu) == 0x3Fu) { // all inside all planes
+                    lc.c[C_INSIDE]++;
+                    Setup s;
 #pragma unroll
                     for (int v = 0; v < 3; v++) {
-                        float val = c[v][ax], w = c[v][3], nw = -w;
-                        in_lo &= val >= nw;
-                        in_hi &= val <= w;
-                        out_lo &= val < nw;
-                        out_hi &= val > w;
+                        const float4 sv = __ldg(&D.scr[vi[v]]);
+                        s.px[v] = sv.x; s.py[v] = sv.y; s.z[v] = sv.z; s.w[v] = sv.w;
                     }
-                    all_in &= in_lo & in_hi;
-                    any_out |= out_lo | out_hi;
-                }
-                if (any_out) {
-                    lc.c[C_OUTSIDE]++;
-                } else if (all_in) {
-                    lc.c[C_INSIDE]++;
-                    emit_triangle(P, D.fs, c[0], c[1], c[2], D.attr + 6 * (size_t)i0, D.attr + 6 * (size_t)i1,
-                                  D.attr + 6 * (size_t)i2, key0, lc);
+                    emit_setup(P, D.fs, s, D.attr + 6 * (size_t)i0, D.attr + 6 * (size_t)i1, D.attr + 6 * (size_t)i2,
+                               key0, lc);
                 } else {
                     // Sutherland-Hodgman against LEFT,RIGHT,BOTTOM,TOP,NEAR,FAR (clipping.rs:118-171)
                     float pv[2][MAX_POLY][4];
                     float pa[2][MAX_POLY][6];
                     int n_out = 3, cur = 0;
                     for (int v = 0; v < 3; v++) {
-                        for (int k = 0; k < 4; k++) pv[0][v][k] = c[v][k];
+                        const float4 cv = __ldg(&D.clip[vi[v]]);
+                        pv[0][v][0] = cv.x; pv[0][v][1] = cv.y; pv[0][v][2] = cv.z; pv[0][v][3] = cv.w;
                         const float *a = D.attr + 6 * (size_t)vi[v];
                         for (int k = 0; k < 6; k++) pa[0][v][k] = __ldg(a + k);
                     }
@@ -252,9 +270,19 @@ __global__ void __launch_bounds__(NT) geom_kernel(FrameParams P, DrawParams D) {
                         lc.c[C_OUTSIDE]++; // late outside (clipping.rs:175-177)
                     } else {
                         lc.c[C_CLIPPED_IN]++;
-                        for (int i = 0; i + 2 < n_out; i++) // fan (0, i+1, i+2) (clipping.rs:185-190)
-                            emit_triangle(P, D.fs, pv[cur][0], pv[cur][i + 1], pv[cur][i + 2], pa[cur][0],
-                                          pa[cur][i + 1], pa[cur][i + 2], key0 + (uint32_t)min(i, 7), lc);
+                        const float Wf = (float)P.W, Hf = (float)P.H;
+                        const float4 s0 = project_vertex(pv[cur][0], Wf, Hf);
+                        float4 sb = project_vertex(pv[cur][1], Wf, Hf);
+                        for (int i = 0; i + 2 < n_out; i++) { // fan (0, i+1, i+2) (clipping.rs:185-190)
+                            const float4 sc = project_vertex(pv[cur][i + 2], Wf, Hf);
+                            Setup s;
+                            s.px[0] = s0.x; s.py[0] = s0.y; s.z[0] = s0.z; s.w[0] = s0.w;
+                            s.px[1] = sb.x; s.py[1] = sb.y; s.z[1] = sb.z; s.w[1] = sb.w;
+                            s.px[2] = sc.x; s.py[2] = sc.y; s.z[2] = sc.z; s.w[2] = sc.w;
+                            emit_setup(P, D.fs, s, pa[cur][0], pa[cur][i + 1], pa[cur][i + 2],
+                                       key0 + (uint32_t)min(i, 7), lc);
+                            sb = sc;
+                        }
                     }
                 }
             }
@@ -276,17 +304,6 @@ __global__ void __launch_bounds__(NT) geom_kernel(FrameParams P, DrawParams D) {
     }
     __syncthreads();
     if (threadIdx.x < C_COUNT && s_cnt[threadIdx.x]) atomicAdd(&P.fs->counters[threadIdx.x], s_cnt[threadIdx.x]);
-}
-
-// Vertex stage alone (render.rs:104-108) -- parity instrumentation for the clip-space positions.
-__global__ void __launch_bounds__(NT) vertex_kernel(const float *pos, uint32_t nv, DrawParams D, float4 *out) {
-    const uint32_t v = blockIdx.x * NT + threadIdx.x;
-    if (v >= nv) return;
-    float x = pos[3 * (size_t)v], y = pos[3 * (size_t)v + 1], z = pos[3 * (size_t)v + 2];
-    float r[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) r[k] = dot4z(D.M[4 * k], D.M[4 * k + 1], D.M[4 * k + 2], D.M[4 * k + 3], x, y, z, 1.0f);
-    out[v] = make_float4(r[0], r[1], r[2], r[3]);
 }
 
 __device__ __forceinline__ void load_setup(const RasterRec *recs, uint32_t rec, Setup &s, uint32_t &key, uint32_t &fs) {

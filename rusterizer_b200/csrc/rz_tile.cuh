@@ -163,8 +163,10 @@ struct TileSmemT {
     float lut[256];                       // (b as f32) / 255.0   (Color::from_rgba, color.rs:22-29)
     float it_f[13][NT];                   // items of the current chunk: px,py x3 | z x3 | inv | w x3
     uint32_t it_key[NT], it_rec[NT];
+    uint16_t it_rcp[NT];                  // ceil(1024 / bw): j / bw == (j * rcp) >> 10 for j < 32, bw <= 16
     uint32_t it_box[NT];                  // lx0 | ly0 << 8 | bw << 16 | fs << 24
     uint32_t pre[NT + 1];                 // exclusive prefix of the in-tile bbox areas (work units)
+    uint8_t unit_item[CHUNK * SMALL_PX];  // work unit -> item
     union {
         FragPool fr;
         unsigned long long sorted[SORT_CAP];
@@ -207,6 +209,23 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
 
     const uint32_t n_total = P.tile_count[tile];
     const int n = (int)min(n_total, P.bin_cap);
+
+    if (n == 0 && !DBG) {
+        // nothing was binned here: the box filter of four clear samples is the clear colour
+        // (buffers.rs:5,111-125) -- write it without touching shared memory
+        if ((P.W & 3u) == 0u) {
+            if (tid < TH * (TW / 4)) {
+                const int row = tid / (TW / 4), q = tid % (TW / 4);
+                const int Yr = tileY0 + row, Xq = tileX0 + q * 4;
+                if (Yr < (int)P.H && Xq < (int)P.W)
+                    *reinterpret_cast<uint4 *>(&P.out[(size_t)Yr * P.W + Xq]) =
+                        make_uint4(CLEAR_COLOR, CLEAR_COLOR, CLEAR_COLOR, CLEAR_COLOR);
+            }
+        } else if (X < (int)P.W && Y < (int)P.H) {
+            P.out[(size_t)Y * P.W + X] = CLEAR_COLOR;
+        }
+        return;
+    }
 
     // clear (the state resolve_and_clear leaves behind, rasterizer/mod.rs:497-506)
 #pragma unroll
@@ -344,7 +363,13 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                 S.it_f[9][tid] = s.inv;
                 S.it_f[10][tid] = s.w[0]; S.it_f[11][tid] = s.w[1]; S.it_f[12][tid] = s.w[2];
                 S.it_key[tid] = key; S.it_rec[tid] = rec;
-                S.it_box[tid] = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bw << 16) | (fs << 24);
+                S.it_rcp[tid] = (uint16_t)((1024 + bw - 1) / max(bw, 1));
+                // per-edge tie-break of EdgeFunctions::inside (mod.rs:159-168): n.x > 0 || (n.x == 0 && n.y < 0)
+                uint32_t tb = 0;
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    tb |= ((s.nx[k] > 0.0f || (!(s.nx[k] < 0.0f) && s.ny[k] < 0.0f)) ? 1u : 0u) << k;
+                S.it_box[tid] = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bw << 16) | (tb << 21) | (fs << 24);
             }
             uint32_t incl = area;
 #pragma unroll
@@ -362,38 +387,35 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
 #pragma unroll
             for (int k = 0; k < NT / 32; k++)
                 if (k < warp) wbase += S.scan[k];
-            S.pre[tid] = wbase + incl - area; // exclusive prefix: first work unit of item <tid>
-            if (tid == NT - 1) S.pre[NT] = wbase + incl;
+            {
+                const uint32_t first = wbase + incl - area; // exclusive prefix: first work unit of item <tid>
+                S.pre[tid] = first;
+                if (tid == NT - 1) S.pre[NT] = wbase + incl;
+                for (uint32_t k = 0; k < area; k++) S.unit_item[first + k] = (uint8_t)tid;
+            }
             __syncthreads();
 
             bool need_sort = false;
             for (;;) {
-                // ---- phase A: thread = (item, bbox pixel) work unit, spread evenly over the CTA ----
+                // ---- phase A1: thread = (item, bbox pixel) work unit, consecutive lanes = consecutive units ----
                 const int units = (int)S.pre[cnt];
                 uint32_t cov_try = 0;
                 for (int u0 = 0; u0 < units; u0 += NT) {
                     const int u = u0 + tid;
-                    uint32_t m = 0, it = 0, p = 0;
-                    Setup q;
-                    int PX = 0, PY = 0;
+                    uint32_t m = 0, p = 0, it = 0;
                     if (u < units) {
-                        int lo = 0, hi = cnt; // last item whose first unit is <= u
-                        while (hi - lo > 1) {
-                            const int mid = (lo + hi) >> 1;
-                            if ((int)S.pre[mid] <= u) lo = mid; else hi = mid;
-                        }
-                        it = (uint32_t)lo;
+                        it = S.unit_item[u];
                         const uint32_t box = S.it_box[it];
-                        const int ibw = (int)((box >> 16) & 0xFFu);
+                        const int ibw = (int)((box >> 16) & 0x1Fu);
                         const int j = u - (int)S.pre[it];
-                        const int ry = j / ibw, rx = j - ry * ibw;
+                        const int ry = (j * (int)S.it_rcp[it]) >> 10, rx = j - ry * ibw; // j / ibw, j < 32, ibw <= 16
                         const int lpx = (int)(box & 0xFFu) + rx, lpy = (int)((box >> 8) & 0xFFu) + ry;
                         p = (uint32_t)(lpy * TW + lpx);
-                        PX = tileX0 + lpx; PY = tileY0 + lpy;
+                        Setup q;
                         q.px[0] = S.it_f[0][it]; q.py[0] = S.it_f[1][it]; q.px[1] = S.it_f[2][it];
                         q.py[1] = S.it_f[3][it]; q.px[2] = S.it_f[4][it]; q.py[2] = S.it_f[5][it];
                         setup_normals(q);
-                        m = coverage_mask(q, PX, PY);
+                        m = coverage_mask_tb(q, (box >> 21) & 7u, tileX0 + lpx, tileY0 + lpy);
                     }
                     const uint32_t bal = __ballot_sync(0xffffffffu, m != 0u);
                     if (bal) { // warp-aggregated fragment allocation (ballot + popc prefix)
@@ -403,14 +425,6 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                         if (m) {
                             cov_try++;
                             if (slot < POOL) {
-                                q.z[0] = S.it_f[6][it]; q.z[1] = S.it_f[7][it]; q.z[2] = S.it_f[8][it];
-                                q.inv = S.it_f[9][it];
-                                float4 z;
-                                z.x = (m & 1u) ? sample_depth(q, PX, PY, 0) : 0.0f;
-                                z.y = (m & 2u) ? sample_depth(q, PX, PY, 1) : 0.0f;
-                                z.z = (m & 4u) ? sample_depth(q, PX, PY, 2) : 0.0f;
-                                z.w = (m & 8u) ? sample_depth(q, PX, PY, 3) : 0.0f;
-                                S.u.fr.z[slot] = z;
                                 S.u.fr.meta[slot] = it | (p << 8) | (m << 16);
                                 S.u.fr.next[slot] = (uint16_t)atomicExch(&S.head[p], slot);
                             } else {
@@ -446,6 +460,25 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                 continue;
             }
             const int nfrag = (int)S.nfrag;
+            // ---- phase A2: thread = fragment; the covered samples' depths (mod.rs:226-245) ----
+            for (int f = tid; f < nfrag; f += NT) {
+                const uint32_t meta = S.u.fr.meta[f];
+                const uint32_t it = meta & 0xFFu, p = (meta >> 8) & 0xFFu, m = (meta >> 16) & 0xFu;
+                Setup q;
+                q.px[0] = S.it_f[0][it]; q.py[0] = S.it_f[1][it]; q.px[1] = S.it_f[2][it];
+                q.py[1] = S.it_f[3][it]; q.px[2] = S.it_f[4][it]; q.py[2] = S.it_f[5][it];
+                q.z[0] = S.it_f[6][it]; q.z[1] = S.it_f[7][it]; q.z[2] = S.it_f[8][it];
+                q.inv = S.it_f[9][it];
+                setup_normals(q);
+                const int PX = tileX0 + (int)(p % TW), PY = tileY0 + (int)(p / TW);
+                float4 z;
+                z.x = (m & 1u) ? sample_depth(q, PX, PY, 0) : 0.0f;
+                z.y = (m & 2u) ? sample_depth(q, PX, PY, 1) : 0.0f;
+                z.z = (m & 4u) ? sample_depth(q, PX, PY, 2) : 0.0f;
+                z.w = (m & 8u) ? sample_depth(q, PX, PY, 3) : 0.0f;
+                S.u.fr.z[f] = z;
+            }
+            __syncthreads();
             // ---- phase B: thread = fragment; what would the ordered replay have done with it? ----
             for (int f = tid; f < nfrag; f += NT) {
                 const uint32_t meta = S.u.fr.meta[f];

@@ -101,6 +101,9 @@ struct DrawParams {
     const float *pos;      // [nv][3]
     const float *attr;     // [nv][6]
     const uint32_t *idx;   // [3*nt]
+    float4 *clip;          // [nv] vertex-stage output: clip-space position (Point4D<ClipSpace>)
+    float4 *scr;           // [nv] screen x, y, depth and clip w (perspective divide + viewport)
+    uint32_t *code;        // [nv] the 12 trivial accept/reject comparisons of the clipper
     uint32_t nv, nt;
     uint32_t tri_base;     // triangle number of this draw's first triangle inside the frame
     uint32_t fs;
