@@ -206,7 +206,7 @@ int rz_create(int device, uint32_t width, uint32_t height, rz_ctx **out) {
     CU_NEW(cudaMalloc(&c->d_state, state_bytes(c)));
     CU_NEW(cudaMemset(c->d_state, 0, state_bytes(c)));
     CU_NEW(cudaMalloc(&c->d_out, (size_t)width * height * sizeof(uint32_t)));
-    CU_NEW(cudaMalloc(&c->d_cnt_backup, sizeof(unsigned long long) * 16));
+    CU_NEW(cudaMalloc(&c->d_cnt_backup, sizeof(unsigned long long) * 16 * CNT_STRIPES));
     CU_NEW(cudaHostAlloc(&c->h_state, sizeof(FrameState), cudaHostAllocDefault));
     for (int i = 0; i < 4; i++) CU_NEW(cudaEventCreate(&c->ev[i]));
     CU_NEW(cudaFuncSetAttribute(tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemT<false>)));
@@ -424,11 +424,12 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     c->launches++;
     if (timed) CU(c, cudaEventRecord(c->ev[2], st));
     const uint32_t n_tiles = P.tiles_x * (P.ty_end - P.ty_begin);
+    const dim3 tile_grid(P.tiles_x, P.ty_end - P.ty_begin);
     if (n_tiles) {
         if (c->debug)
-            tile_kernel<true><<<n_tiles, NT, sizeof(TileSmemT<true>), st>>>(P);
+            tile_kernel<true><<<tile_grid, NT, sizeof(TileSmemT<true>), st>>>(P);
         else
-            tile_kernel<false><<<n_tiles, NT, sizeof(TileSmemT<false>), st>>>(P);
+            tile_kernel<false><<<tile_grid, NT, sizeof(TileSmemT<false>), st>>>(P);
         c->launches++;
     }
     if (timed) CU(c, cudaEventRecord(c->ev[3], st));
@@ -463,7 +464,7 @@ int rz_framebuffer(rz_ctx *c, uint32_t *out_host, const uint32_t **out_device) {
         end_frame(c);
         return map_err_flags(c, flags);
     }
-    CU(c, cudaMemcpyAsync(c->d_cnt_backup, dfs->counters, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToDevice, st));
+    CU(c, cudaMemcpyAsync(c->d_cnt_backup, dfs->counters, sizeof(unsigned long long) * 16 * CNT_STRIPES, cudaMemcpyDeviceToDevice, st));
     int rc = RZ_OK;
     for (int attempt = 0; attempt < 8; attempt++) {
         rc = enqueue_frame(c, c->d_out, true);
@@ -478,7 +479,7 @@ int rz_framebuffer(rz_ctx *c, uint32_t *out_host, const uint32_t **out_device) {
             break;
         }
         // grow what overflowed (the cursors kept counting past the capacity) and replay the frame
-        CU(c, cudaMemcpyAsync(dfs->counters, c->d_cnt_backup, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToDevice, st));
+        CU(c, cudaMemcpyAsync(dfs->counters, c->d_cnt_backup, sizeof(unsigned long long) * 16 * CNT_STRIPES, cudaMemcpyDeviceToDevice, st));
         uint32_t want_rec = c->rec_cap, want_bin = c->bin_cap, want_large = c->large_cap;
         if (flags & ERR_REC_OVF) want_rec = std::max<uint64_t>((uint64_t)c->h_state->n_records * 5 / 4 + 1024, (uint64_t)c->rec_cap * 2);
         if (flags & ERR_LARGE_OVF) want_large = std::max<uint64_t>((uint64_t)c->h_state->n_large * 5 / 4 + 1024, (uint64_t)c->large_cap * 2);
@@ -556,7 +557,9 @@ int rz_counters(rz_ctx *c, rz_counters_t *out) {
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(FrameState), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
-    const unsigned long long *k = c->h_state->counters;
+    unsigned long long k[16] = {0};
+    for (int st = 0; st < CNT_STRIPES; st++)
+        for (int i = 0; i < 16; i++) k[i] += c->h_state->counters[st][i];
     out->n_tris_in = k[C_TRIS_IN]; out->n_degenerate = k[C_DEGENERATE]; out->n_outside = k[C_OUTSIDE];
     out->n_inside = k[C_INSIDE]; out->n_clipped_in = k[C_CLIPPED_IN]; out->n_tris_setup = k[C_TRIS_SETUP];
     out->n_bbox_px = k[C_BBOX_PX]; out->n_covered_px = k[C_COVERED_PX]; out->n_shaded_px = k[C_SHADED_PX];
@@ -567,7 +570,7 @@ int rz_counters(rz_ctx *c, rz_counters_t *out) {
 int rz_reset_counters(rz_ctx *c) {
     if (!c) return RZ_E_INVALID;
     CU(c, cudaSetDevice(c->device));
-    CU(c, cudaMemsetAsync(c->d_state, 0, sizeof(unsigned long long) * 16, c->stream));
+    CU(c, cudaMemsetAsync(c->d_state, 0, sizeof(unsigned long long) * 16 * CNT_STRIPES, c->stream));
     return RZ_OK;
 }
 

@@ -106,23 +106,40 @@ __device__ __forceinline__ uint32_t coverage_mask(const Setup &s, int X, int Y) 
     return mask;
 }
 
-// Same mask, branch-free, with the per-edge tie-break (n.x > 0 || (n.x == 0 && n.y < 0)) precomputed
-// in bits 0..2 of `tb`: edge k passes iff e > 0, or e is not < 0 (zero or NaN -- the reference
-// sends both to the normal tests) and bit k of tb is set.
-__device__ __forceinline__ uint32_t coverage_mask_tb(const Setup &s, uint32_t tb, int X, int Y) {
+// Fast exact coverage for FINITE screen coordinates (the caller guarantees |coords| < 2^20, so every
+// edge value is finite).  Two observations make one compare per edge enough:
+//   * EdgeFunctions::inside (mod.rs:148-170) reduces to  e > 0 || (e == 0 && tie_k)  with the
+//     per-edge constant tie_k = n.x > 0 || (n.x == 0 && n.y < 0); that is  e >= thr_k  with
+//     thr_k = 0.0 when tie_k holds and the smallest positive subnormal otherwise (-0.0 >= 0.0 holds);
+//   * the leading `0.0 +` of Vector::dot only turns a -0.0 into +0.0, which `>=` cannot see, so it is
+//     dropped HERE (the depth / attribute paths keep it).
+// thr[k] comes from edge_thresholds().
+__device__ __forceinline__ void edge_thresholds(const Setup &s, float *thr) {
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        thr[k] = (s.nx[k] > 0.0f || (!(s.nx[k] < 0.0f) && s.ny[k] < 0.0f)) ? 0.0f : 1.401298464e-45f;
+}
+__device__ __forceinline__ uint32_t coverage_mask_fast(const Setup &s, const float *thr, int X, int Y) {
     uint32_t mask = 0;
     const float fx = (float)X, fy = (float)Y;
-    const uint32_t t0 = tb & 1u, t1 = (tb >> 1) & 1u, t2 = (tb >> 2) & 1u;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const float xs = fadd(fx, rgss_x(i)), ys = fadd(fy, rgss_y(i));
-        const float e0 = edge_eval(s, 0, xs, ys), e1 = edge_eval(s, 1, xs, ys), e2 = edge_eval(s, 2, xs, ys);
-        const uint32_t p0 = (uint32_t)(e0 > 0.0f) | (t0 & (uint32_t)!(e0 < 0.0f));
-        const uint32_t p1 = (uint32_t)(e1 > 0.0f) | (t1 & (uint32_t)!(e1 < 0.0f));
-        const uint32_t p2 = (uint32_t)(e2 > 0.0f) | (t2 & (uint32_t)!(e2 < 0.0f));
-        mask |= (p0 & p1 & p2) << i;
+        bool in = true;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float e = fadd(fmul(s.nx[k], fsub(xs, s.px[k])), fmul(s.ny[k], fsub(ys, s.py[k])));
+            in = in & (e >= thr[k]);
+        }
+        mask |= (in ? 1u : 0u) << i;
     }
     return mask;
+}
+__device__ __forceinline__ bool setup_is_tame(const Setup &s) {
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 3; k++) ok = ok & (fabsf(s.px[k]) < 1048576.0f) & (fabsf(s.py[k]) < 1048576.0f);
+    return ok; // false for NaN / inf / absurd coordinates: those take the literal path
 }
 
 // interpolate_depth closure of RasterizerTriangle::fragment (rasterizer/mod.rs:226-236)

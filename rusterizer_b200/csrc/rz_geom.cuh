@@ -182,9 +182,8 @@ __global__ void __launch_bounds__(NT) vertex_kernel(FrameParams P, DrawParams D)
 // Stage 1b/2 -- primitive assembly, clip, setup, binning: one thread per input triangle
 // (render.rs:75-96, rasterizer/mod.rs:425-441).
 __global__ void __launch_bounds__(NT) geom_kernel(FrameParams P, DrawParams D) {
-    __shared__ unsigned long long s_cnt[C_COUNT];
-    if (threadIdx.x < C_COUNT) s_cnt[threadIdx.x] = 0ull;
-    __syncthreads();
+    __shared__ uint32_t s_part[NT / 32][C_COUNT];
+    __shared__ unsigned long long s_bbox[NT / 32];
 
     GeomLocal lc;
 #pragma unroll
@@ -289,21 +288,36 @@ __global__ void __launch_bounds__(NT) geom_kernel(FrameParams P, DrawParams D) {
         }
     }
 
-    // block-level counter reduction: warp reduce, one shared atomic per warp, one global per CTA
-#pragma unroll
-    for (int k = 0; k < C_COUNT; k++) {
-        if (k == C_BBOX_PX || k == C_COVERED_PX || k == C_SHADED_PX || k == C_SAMPLES || k == C_TEX_OOB) continue;
-        uint32_t v = __reduce_add_sync(0xffffffffu, lc.c[k]);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[k], (unsigned long long)v);
-    }
+    // block-level counter reduction: warp reduce -> per-warp partials -> one striped global RED per counter
     {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+        for (int k = 0; k <= C_TRIS_SETUP; k++) {
+            const uint32_t v = __reduce_add_sync(0xffffffffu, lc.c[k]);
+            if (lane == 0) s_part[warp][k] = v;
+        }
+        {
+            const uint32_t v = __reduce_add_sync(0xffffffffu, lc.c[C_CLIP_OVF]);
+            if (lane == 0) s_part[warp][C_CLIP_OVF] = v;
+        }
         unsigned long long v = lc.bbox;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[C_BBOX_PX], v);
+        if (lane == 0) s_bbox[warp] = v;
     }
     __syncthreads();
-    if (threadIdx.x < C_COUNT && s_cnt[threadIdx.x]) atomicAdd(&P.fs->counters[threadIdx.x], s_cnt[threadIdx.x]);
+    if (threadIdx.x < C_COUNT) {
+        const int k = threadIdx.x;
+        unsigned long long sum = 0ull;
+        if (k <= C_TRIS_SETUP || k == C_CLIP_OVF) {
+#pragma unroll
+            for (int w = 0; w < NT / 32; w++) sum += s_part[w][k];
+        } else if (k == C_BBOX_PX) {
+#pragma unroll
+            for (int w = 0; w < NT / 32; w++) sum += s_bbox[w];
+        }
+        if (sum) atomicAdd(&P.fs->counters[blockIdx.x % CNT_STRIPES][k], sum);
+    }
 }
 
 __device__ __forceinline__ void load_setup(const RasterRec *recs, uint32_t rec, Setup &s, uint32_t &key, uint32_t &fs) {

@@ -175,7 +175,6 @@ struct TileSmemT {
     uint32_t head[TILE_PX];               // per-pixel fragment list heads; reused as resolve staging
     uint32_t scan[NT / 32];
     uint32_t first_big, first_small, nfrag, ovf;
-    unsigned long long cnt[4];
 };
 
 // Sort the tile's list by order key (in shared memory when it fits, else in place in HBM) and
@@ -201,7 +200,7 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
     SM &S = *reinterpret_cast<SM *>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tx = blockIdx.x % P.tiles_x, ty = P.ty_begin + blockIdx.x / P.tiles_x;
+    const uint32_t tx = blockIdx.x, ty = P.ty_begin + blockIdx.y;
     const uint32_t tile = ty * P.tiles_x + tx;
     const int tileX0 = tx * TW, tileY0 = ty * TH;
     const int lx = tid % TW, ly = tid / TW;
@@ -239,7 +238,6 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
     if (n > 0) {
         S.head[tid] = FR_NONE;
         S.lut[tid] = fdiv((float)tid, 255.0f);
-        if (tid < 4) S.cnt[tid] = 0ull;
         unsigned long long *bin = P.bins + (size_t)tile * P.bin_cap;
         bool sorted = false;
         if (n > CHUNK) {
@@ -265,7 +263,7 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                 if (x0 < x1 && y0 < y1) {
                     bx0 = x0 - tileX0; by0 = y0 - tileY0; bw = x1 - x0; bh = y1 - y0;
                 }
-                big = bw * bh > SMALL_PX;
+                big = bw * bh > SMALL_PX || (bw > 0 && !setup_is_tame(s)); // untame: literal per-pixel path
             }
             if (tid == 0) {
                 S.first_big = CHUNK + 1;
@@ -364,12 +362,7 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                 S.it_f[10][tid] = s.w[0]; S.it_f[11][tid] = s.w[1]; S.it_f[12][tid] = s.w[2];
                 S.it_key[tid] = key; S.it_rec[tid] = rec;
                 S.it_rcp[tid] = (uint16_t)((1024 + bw - 1) / max(bw, 1));
-                // per-edge tie-break of EdgeFunctions::inside (mod.rs:159-168): n.x > 0 || (n.x == 0 && n.y < 0)
-                uint32_t tb = 0;
-#pragma unroll
-                for (int k = 0; k < 3; k++)
-                    tb |= ((s.nx[k] > 0.0f || (!(s.nx[k] < 0.0f) && s.ny[k] < 0.0f)) ? 1u : 0u) << k;
-                S.it_box[tid] = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bw << 16) | (tb << 21) | (fs << 24);
+                S.it_box[tid] = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bw << 16) | (fs << 24);
             }
             uint32_t incl = area;
 #pragma unroll
@@ -415,7 +408,9 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                         q.px[0] = S.it_f[0][it]; q.py[0] = S.it_f[1][it]; q.px[1] = S.it_f[2][it];
                         q.py[1] = S.it_f[3][it]; q.px[2] = S.it_f[4][it]; q.py[2] = S.it_f[5][it];
                         setup_normals(q);
-                        m = coverage_mask_tb(q, (box >> 21) & 7u, tileX0 + lpx, tileY0 + lpy);
+                        float thr[3];
+                        edge_thresholds(q, thr);
+                        m = coverage_mask_fast(q, thr, tileX0 + lpx, tileY0 + lpy);
                     }
                     const uint32_t bal = __ballot_sync(0xffffffffu, m != 0u);
                     if (bal) { // warp-aggregated fragment allocation (ballot + popc prefix)
@@ -567,24 +562,24 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
         P.out[(size_t)Y * P.W + X] = res;
     }
 
-    // ---- counters ----
+    // ---- counters: warp reduce -> per-warp partials -> one striped global RED per counter ----
     if (n > 0) {
         c_cov = __reduce_add_sync(0xffffffffu, c_cov);
         c_shaded = __reduce_add_sync(0xffffffffu, c_shaded);
         c_samples = __reduce_add_sync(0xffffffffu, c_samples);
         c_oob = __reduce_add_sync(0xffffffffu, c_oob);
+        __syncthreads(); // S.pre is free now
         if (lane == 0) {
-            if (c_cov) atomicAdd(&S.cnt[0], (unsigned long long)c_cov);
-            if (c_shaded) atomicAdd(&S.cnt[1], (unsigned long long)c_shaded);
-            if (c_samples) atomicAdd(&S.cnt[2], (unsigned long long)c_samples);
-            if (c_oob) atomicAdd(&S.cnt[3], (unsigned long long)c_oob);
+            S.pre[warp * 4 + 0] = c_cov; S.pre[warp * 4 + 1] = c_shaded;
+            S.pre[warp * 4 + 2] = c_samples; S.pre[warp * 4 + 3] = c_oob;
         }
         __syncthreads();
-        if (tid == 0) {
-            if (S.cnt[0]) atomicAdd(&P.fs->counters[C_COVERED_PX], S.cnt[0]);
-            if (S.cnt[1]) atomicAdd(&P.fs->counters[C_SHADED_PX], S.cnt[1]);
-            if (S.cnt[2]) atomicAdd(&P.fs->counters[C_SAMPLES], S.cnt[2]);
-            if (S.cnt[3]) atomicAdd(&P.fs->counters[C_TEX_OOB], S.cnt[3]);
+        if (tid < 4) {
+            unsigned long long sum = 0ull;
+#pragma unroll
+            for (int w = 0; w < NT / 32; w++) sum += S.pre[w * 4 + tid];
+            const int slot = tid == 0 ? C_COVERED_PX : (tid == 1 ? C_SHADED_PX : (tid == 2 ? C_SAMPLES : C_TEX_OOB));
+            if (sum) atomicAdd(&P.fs->counters[tile % CNT_STRIPES][slot], sum);
         }
     }
 }

@@ -39,8 +39,9 @@ enum {
 // Device-side frame bookkeeping.  `counters` and `err` persist across frames (read by rz_counters /
 // rz_sync); everything from `n_records` on, and tile_count[] which follows in the same allocation,
 // is zeroed by one memset at the start of every frame.
+constexpr int CNT_STRIPES = 32; // counters are striped over CTAs to spread the global atomics
 struct FrameState {
-    unsigned long long counters[16];
+    unsigned long long counters[CNT_STRIPES][16];
     uint32_t err;         // sticky ERR_* flags
     uint32_t pad0[3];
     uint32_t n_records;   // emitted (post-clip, post-cull) triangles       <- per-frame part starts here

@@ -1,0 +1,169 @@
+"""CPU-side tests (no GPU): host helpers, scene definitions, the C-ABI surface, multi-rank sharding."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_checkerboard_matches_reference_fixture_hash():
+    """decoded images/checkerboard.png = 400x400 RGBA, 4x4 squares, top-left black."""
+    from rusterizer_b200.texture import CHECKERBOARD_SHA256, Texture
+
+    t = Texture.checkerboard()
+    assert t.texels.shape == (400, 400, 4) and t.texel_width == 4
+    assert t.sha256() == CHECKERBOARD_SHA256
+    assert tuple(t.texels[0, 0]) == (0, 0, 0, 255) and tuple(t.texels[0, 100]) == (255, 255, 255, 255)
+
+
+def test_default_camera_and_projection():
+    """camera.rs:46-54 + main.rs:137-142 (values quoted in SURVEY.md section 8d)."""
+    from rusterizer_b200 import mathx
+    from rusterizer_b200.camera import Camera
+    from rusterizer_b200.scenes import default_projection
+
+    v = Camera().get_view_matrix()
+    assert np.array_equal(np.abs(v), np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 5], [0, 0, 0, 1]], np.float32))
+    assert v[2, 2] == -1 and v[2, 3] == -5
+    p = default_projection(1280, 720)
+    assert p[0, 0] == np.float32(1.0) and abs(p[1, 1] - 1.7777778) < 1e-6
+    assert abs(p[2, 2] + 1.0100503) < 1e-6 and abs(p[2, 3] + 2.0100503) < 1e-6 and p[3, 2] == -1
+    # orbit camera at angle 0 is the default camera
+    assert np.array_equal(Camera.orbit(0.0).get_view_matrix(), v)
+    assert mathx.vlen(Camera.orbit(1.0).pos) == pytest.approx(5.0, abs=1e-5)
+
+
+def test_mesh_generators():
+    """mesh.rs:15-207"""
+    from rusterizer_b200 import mesh
+
+    c = mesh.cube(1.0)
+    assert c.n_vertices == 24 and c.n_triangles == 12
+    assert list(c.indices[:6]) == [0, 1, 2, 0, 2, 3]
+    assert np.array_equal(c.attributes[:4, 4:], [[0, 0], [1, 0], [1, 1], [0, 1]])
+    s = mesh.sphere(0.5)
+    assert s.n_vertices == 17 * 9 and s.n_triangles == 256
+    assert list(s.indices[:6]) == [0, 1, 18, 0, 18, 17]
+    assert np.allclose(np.linalg.norm(s.vertices, axis=1), 0.5, atol=1e-6)
+    assert np.array_equal(s.attributes[:, 0:3], np.abs(s.vertices))
+    assert mesh.triangle().n_triangles == 1 and mesh.centered_quad(2.0).n_triangles == 2
+
+
+def test_benchmark_scene_sizes():
+    """BASELINE.md section 4 / SURVEY.md section 8d: C2 has exactly 1 000 000 triangles, 501 501 vertices and
+    38 988 628 algorithmic bytes; C3 has 250 000 triangles."""
+    from rusterizer_b200 import scenes
+
+    c2 = scenes.sphere_scene()
+    assert (c2.n_triangles, c2.n_vertices, c2.width, c2.height) == (1_000_000, 501_501, 1920, 1080)
+    assert c2.algorithmic_bytes() == 38_988_628
+    c3 = scenes.near_clip_scene()
+    assert c3.n_triangles == 250_000 and (c3.width, c3.height) == (3840, 2160)
+    assert scenes.overdraw_scene().n_triangles == 1_000_000
+    assert len(scenes.orbit_cameras(1024)) == 1024
+
+
+def _header_symbols():
+    text = (ROOT / "include" / "rz.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rz_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    """The drop-in boundary: librz_b200.so must export exactly what include/rz.h declares."""
+    import __graft_entry__ as g
+    from rusterizer_b200 import render
+
+    if not render.library_path().exists():
+        g.build()
+    lib = ctypes.CDLL(str(render.library_path()))
+    declared = _header_symbols()
+    assert declared == sorted(render.ABI_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/rz.h but not exported"
+    lib.rz_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.rz_version()
+    lib.rz_tile_width.restype = ctypes.c_uint32
+    assert lib.rz_tile_width() == 16 and lib.rz_tile_height() == 16
+
+
+def test_no_cpu_fallback_without_gpu():
+    """The product path fails loudly when there is no CUDA device (rz_create -> RZ_E_NO_DEVICE)."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from rusterizer_b200.render import Renderer, RzError
+
+    with pytest.raises(RzError) as e:
+        Renderer(64, 64)
+    assert e.value.code == -3 and "no CPU fallback" in str(e.value)
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under rusterizer_b200/ may import, load or call it."""
+    for path in (ROOT / "rusterizer_b200").rglob("*"):
+        if path.suffix in (".py", ".cu", ".cuh", ".h", ".hpp") and path.is_file():
+            text = path.read_text()
+            assert "liboracle" not in text and "rz_oracle" not in text, path
+            assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), path
+
+
+def test_row_ranges_partition_the_framebuffer():
+    from rusterizer_b200 import sharding
+
+    for H in (1080, 8192, 720, 17, 16):
+        for world in (1, 2, 3, 4, 8):
+            rows = [sharding.row_range(r, world, H, 16) for r in range(world)]
+            assert rows[0][0] == 0 and rows[-1][1] == H
+            for (a0, a1), (b0, b1) in zip(rows, rows[1:]):
+                assert a1 == b0 and a0 <= a1
+            for a0, a1 in rows:
+                assert a0 == a1 or (a0 % 16 == 0 and (a1 % 16 == 0 or a1 == H))  # empty strips allowed at the tail
+    assert sharding.frame_ids(1, 4, 10) == [1, 5, 9]
+    assert sorted(sum((sharding.frame_ids(r, 8, 1024) for r in range(8)), [])) == list(range(1024))
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+import numpy as np, torch, torch.distributed as dist
+from rusterizer_b200 import scenes, sharding
+from helpers import oracle_render
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+# tile-row sharding: every rank holds its strip of the frame, the gather must reassemble the frame
+sc = scenes.default_scene(1.0, width=200, height=120)
+full = oracle_render(sc)["fb"]
+r0, r1 = sharding.row_range(rank, world, sc.height, 16)
+per = sharding.strip_rows(sc.height, world, 16)
+strip = np.zeros((per, sc.width), np.uint32)
+strip[: r1 - r0] = full[r0:r1]
+out = sharding.gather_strips(torch.from_numpy(strip.view(np.int32)), sc.height).numpy().view(np.uint32)
+assert out.shape == full.shape and np.array_equal(out, full), "gathered frame differs"
+# frame sharding: the union of the ranks' frame ids covers the sweep exactly once
+ids = sharding.frame_ids(rank, world, 10)
+gathered = [None] * world
+dist.all_gather_object(gathered, ids)
+assert sorted(sum(gathered, [])) == list(range(10))
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_sharding_world_size_2_gloo(tmp_path):
+    """N>1 host logic on CPU: 2 ranks over gloo -- strip gather reassembles the oracle's frame."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER.format(root=str(ROOT)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29531", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
