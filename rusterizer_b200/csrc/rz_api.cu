@@ -57,14 +57,17 @@ struct rz_ctx {
     unsigned char *d_state = nullptr; // FrameState + tile_count[]
     unsigned long long *d_bins = nullptr;
     RasterRec *d_recs = nullptr;
+    ShadeRec *d_shade = nullptr;
     AttrRec *d_attrs = nullptr;
+    DrawInfo *d_draws = nullptr;
+    std::vector<DrawInfo> h_draws;
+    uint32_t draw_cap = 0, attr_cap = 0;
     LargeItem *d_large = nullptr;
     uint32_t *d_out = nullptr;
     unsigned long long *d_cnt_backup = nullptr;
     float *d_dbg_depth = nullptr;
     uint32_t *d_dbg_color = nullptr, *d_dbg_owner = nullptr;
-    float4 *d_vclip = nullptr, *d_vscr = nullptr; // vertex-stage scratch, sized for the largest mesh
-    uint32_t *d_vcode = nullptr;
+    float4 *d_vtx = nullptr; // vertex-stage scratch [vert_cap][2], sized for the largest mesh
     uint32_t vert_cap = 0;
     uint32_t rec_cap = 0, bin_cap = 0, large_cap = 0;
     bool debug = false;
@@ -122,26 +125,24 @@ static size_t state_bytes(const rz_ctx *c) { return sizeof(FrameState) + sizeof(
 static int free_frame_buffers(rz_ctx *c) {
     cudaFree(c->d_bins); c->d_bins = nullptr;
     cudaFree(c->d_recs); c->d_recs = nullptr;
+    cudaFree(c->d_shade); c->d_shade = nullptr;
     cudaFree(c->d_attrs); c->d_attrs = nullptr;
+    cudaFree(c->d_draws); c->d_draws = nullptr;
     cudaFree(c->d_large); c->d_large = nullptr;
-    cudaFree(c->d_vclip); c->d_vclip = nullptr;
-    cudaFree(c->d_vscr); c->d_vscr = nullptr;
-    cudaFree(c->d_vcode); c->d_vcode = nullptr;
+    cudaFree(c->d_vtx); c->d_vtx = nullptr;
     return RZ_OK;
 }
 
 static int ensure_vertex_scratch(rz_ctx *c, uint32_t nv) {
     if (nv <= c->vert_cap) return RZ_OK;
-    cudaFree(c->d_vclip); cudaFree(c->d_vscr); cudaFree(c->d_vcode);
-    c->d_vclip = c->d_vscr = nullptr; c->d_vcode = nullptr; c->vert_cap = 0;
-    CU(c, cudaMalloc(&c->d_vclip, (size_t)nv * sizeof(float4)));
-    CU(c, cudaMalloc(&c->d_vscr, (size_t)nv * sizeof(float4)));
-    CU(c, cudaMalloc(&c->d_vcode, (size_t)nv * sizeof(uint32_t)));
+    cudaFree(c->d_vtx);
+    c->d_vtx = nullptr; c->vert_cap = 0;
+    CU(c, cudaMalloc(&c->d_vtx, (size_t)nv * 2 * sizeof(float4)));
     c->vert_cap = nv;
     return RZ_OK;
 }
 
-static int ensure_capacity(rz_ctx *c, uint32_t rec_cap, uint32_t bin_cap, uint32_t large_cap) {
+static int ensure_capacity(rz_ctx *c, uint32_t rec_cap, uint32_t bin_cap, uint32_t large_cap, uint32_t attr_cap) {
     const size_t tiles = (size_t)c->tiles_x * c->tiles_y;
     if (bin_cap > c->bin_cap) {
         cudaFree(c->d_bins); c->d_bins = nullptr;
@@ -150,10 +151,17 @@ static int ensure_capacity(rz_ctx *c, uint32_t rec_cap, uint32_t bin_cap, uint32
     }
     if (rec_cap > c->rec_cap) {
         cudaFree(c->d_recs); c->d_recs = nullptr;
-        cudaFree(c->d_attrs); c->d_attrs = nullptr;
+        cudaFree(c->d_shade); c->d_shade = nullptr;
+        c->rec_cap = 0;
         CU(c, cudaMalloc(&c->d_recs, (size_t)rec_cap * sizeof(RasterRec)));
-        CU(c, cudaMalloc(&c->d_attrs, (size_t)rec_cap * sizeof(AttrRec)));
+        CU(c, cudaMalloc(&c->d_shade, (size_t)rec_cap * sizeof(ShadeRec)));
         c->rec_cap = rec_cap;
+    }
+    if (attr_cap > c->attr_cap) {
+        cudaFree(c->d_attrs); c->d_attrs = nullptr;
+        c->attr_cap = 0;
+        CU(c, cudaMalloc(&c->d_attrs, (size_t)attr_cap * sizeof(AttrRec)));
+        c->attr_cap = attr_cap;
     }
     if (large_cap > c->large_cap) {
         cudaFree(c->d_large); c->d_large = nullptr;
@@ -368,7 +376,8 @@ static FrameParams make_params(rz_ctx *c, uint32_t *out_base) {
     P.rec_cap = c->rec_cap; P.bin_cap = c->bin_cap; P.large_cap = c->large_cap;
     P.fs = reinterpret_cast<FrameState *>(c->d_state);
     P.tile_count = reinterpret_cast<uint32_t *>(c->d_state + sizeof(FrameState));
-    P.bins = c->d_bins; P.recs = c->d_recs; P.attrs = c->d_attrs; P.large = c->d_large;
+    P.bins = c->d_bins; P.recs = c->d_recs; P.shade = c->d_shade; P.attrs = c->d_attrs; P.large = c->d_large;
+    P.draws = c->d_draws; P.attr_cap = c->attr_cap;
     P.out = out_base;
     if (c->debug) {
         P.dbg_depth = c->d_dbg_depth; P.dbg_color = c->d_dbg_color; P.dbg_owner = c->d_dbg_owner;
@@ -397,23 +406,38 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
         uint32_t want_rec = std::max<uint64_t>(c->rec_cap, total_tris + 1024);
         uint32_t want_bin = std::max<uint32_t>(c->bin_cap, 256u);
         uint32_t want_large = std::max<uint32_t>(c->large_cap, 1u << 16);
-        int rc = ensure_capacity(c, want_rec, want_bin, want_large);
+        uint32_t want_attr = std::max<uint32_t>(c->attr_cap, 1u << 14);
+        int rc = ensure_capacity(c, want_rec, want_bin, want_large, want_attr);
         if (rc != RZ_OK) return rc;
+        // per-draw table for the shading step
+        if (c->draws.size() > c->draw_cap) {
+            cudaFree(c->d_draws); c->d_draws = nullptr;
+            c->draw_cap = 0;
+            const uint32_t cap = (uint32_t)std::max<size_t>(c->draws.size() * 2, 64);
+            CU(c, cudaMalloc(&c->d_draws, (size_t)cap * sizeof(DrawInfo)));
+            c->draw_cap = cap;
+        }
+        c->h_draws.resize(c->draws.size());
+        for (size_t i = 0; i < c->draws.size(); i++) c->h_draws[i].attr = c->draws[i].mesh->d_attr;
+        if (!c->h_draws.empty())
+            CU(c, cudaMemcpyAsync(c->d_draws, c->h_draws.data(), c->h_draws.size() * sizeof(DrawInfo),
+                                  cudaMemcpyHostToDevice, c->stream));
     }
     FrameParams P = make_params(c, out_base);
     cudaStream_t st = c->stream;
     const size_t off = offsetof(FrameState, n_records);
     CU(c, cudaMemsetAsync(c->d_state + off, 0, state_bytes(c) - off, st));
     if (timed) CU(c, cudaEventRecord(c->ev[0], st));
-    uint32_t tri_base = 0;
+    uint32_t tri_base = 0, draw_index = 0;
     for (auto &d : c->draws) {
         const uint32_t nt = (uint32_t)(d.mesh->n_idx / 3);
+        const uint32_t this_draw = draw_index++;
         if (nt == 0) continue;
         DrawParams D;
         D.pos = d.mesh->d_pos; D.attr = d.mesh->d_attr; D.idx = d.mesh->d_idx;
-        D.nv = d.mesh->nv; D.nt = nt; D.tri_base = tri_base; D.fs = d.fs;
+        D.nv = d.mesh->nv; D.nt = nt; D.tri_base = tri_base; D.fs = d.fs; D.draw = this_draw;
         memcpy(D.M, d.M, 64);
-        D.clip = c->d_vclip; D.scr = c->d_vscr; D.code = c->d_vcode;
+        D.vtx = c->d_vtx;
         vertex_kernel<<<(D.nv + NT - 1) / NT, NT, 0, st>>>(P, D);
         geom_kernel<<<(nt + NT - 1) / NT, NT, 0, st>>>(P, D);
         c->launches += 2;
@@ -444,7 +468,7 @@ static void end_frame(rz_ctx *c) {
 
 static int map_err_flags(rz_ctx *c, uint32_t flags) {
     if (flags & ERR_INDEX) return fail(c, RZ_E_INDEX, "a mesh index is >= nv (the reference panics at render.rs:83-87)");
-    if (flags & (ERR_REC_OVF | ERR_BIN_OVF | ERR_LARGE_OVF))
+    if (flags & (ERR_REC_OVF | ERR_BIN_OVF | ERR_LARGE_OVF | ERR_ATTR_OVF))
         return fail(c, RZ_E_CAPACITY, "an async frame outgrew its device buffers (flags 0x%x); re-issue via rz_framebuffer()", flags);
     return RZ_OK;
 }
@@ -480,7 +504,8 @@ int rz_framebuffer(rz_ctx *c, uint32_t *out_host, const uint32_t **out_device) {
         }
         // grow what overflowed (the cursors kept counting past the capacity) and replay the frame
         CU(c, cudaMemcpyAsync(dfs->counters, c->d_cnt_backup, sizeof(unsigned long long) * 16 * CNT_STRIPES, cudaMemcpyDeviceToDevice, st));
-        uint32_t want_rec = c->rec_cap, want_bin = c->bin_cap, want_large = c->large_cap;
+        uint32_t want_rec = c->rec_cap, want_bin = c->bin_cap, want_large = c->large_cap, want_attr = c->attr_cap;
+        if (flags & ERR_ATTR_OVF) want_attr = std::max<uint64_t>((uint64_t)c->h_state->n_clip_attr * 5 / 4 + 1024, (uint64_t)c->attr_cap * 2);
         if (flags & ERR_REC_OVF) want_rec = std::max<uint64_t>((uint64_t)c->h_state->n_records * 5 / 4 + 1024, (uint64_t)c->rec_cap * 2);
         if (flags & ERR_LARGE_OVF) want_large = std::max<uint64_t>((uint64_t)c->h_state->n_large * 5 / 4 + 1024, (uint64_t)c->large_cap * 2);
         if (flags & ERR_BIN_OVF) {
@@ -496,7 +521,7 @@ int rz_framebuffer(rz_ctx *c, uint32_t *out_host, const uint32_t **out_device) {
                 break;
             }
         }
-        rc = ensure_capacity(c, want_rec, want_bin, want_large);
+        rc = ensure_capacity(c, want_rec, want_bin, want_large, want_attr);
         if (rc != RZ_OK) break;
         if (attempt == 7) rc = fail(c, RZ_E_CAPACITY, "frame still overflows after 8 growth attempts");
     }
@@ -621,11 +646,16 @@ int rz_debug_vertex_stage(rz_ctx *c, const rz_mesh *mesh, float *out_clip) {
     mat4_mul(c->proj, c->view, pv);
     mat4_mul(pv, c->world, D.M);
     D.pos = mesh->d_pos; D.nv = mesh->nv;
-    D.clip = c->d_vclip; D.scr = c->d_vscr; D.code = c->d_vcode;
+    D.vtx = c->d_vtx;
     vertex_kernel<<<(mesh->nv + NT - 1) / NT, NT, 0, c->stream>>>(P, D);
     c->launches++;
-    CU(c, cudaMemcpyAsync(out_clip, c->d_vclip, (size_t)mesh->nv * 16, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<float> tmp((size_t)mesh->nv * 8);
+    CU(c, cudaMemcpyAsync(tmp.data(), c->d_vtx, tmp.size() * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    for (size_t v = 0; v < mesh->nv; v++) { // (clip x, y, z) from word 4..6, clip w from word 3
+        out_clip[4 * v + 0] = tmp[8 * v + 4]; out_clip[4 * v + 1] = tmp[8 * v + 5];
+        out_clip[4 * v + 2] = tmp[8 * v + 6]; out_clip[4 * v + 3] = tmp[8 * v + 3];
+    }
     return RZ_OK;
 }
 

@@ -58,9 +58,10 @@ __device__ __forceinline__ float4 project_vertex(const float *c, float Wf, float
 
 // RasterizerTriangle::new + bounding_box (rasterizer/mod.rs:187-222,347-361) for one screen-space
 // triangle (s.px/py/z/w filled), then cull / record / bin.
-// a0,a1,a2 point at the three VertexAttributes (6 floats each; global or local memory).
-__device__ __forceinline__ void emit_setup(const FrameParams &P, uint32_t fs_id, Setup &s, const float *a0,
-                                           const float *a1, const float *a2, uint32_t key, GeomLocal &lc) {
+// Unclipped triangles pass their vertex indices (ca == nullptr); clipped ones pass the three
+// interpolated VertexAttributes ca[0..2] (6 floats each, local memory).
+__device__ __forceinline__ void emit_setup(const FrameParams &P, const DrawParams &D, Setup &s, uint32_t i0, uint32_t i1,
+                                           uint32_t i2, const float (*ca)[6], uint32_t key, GeomLocal &lc) {
     setup_normals(s); // inv_2x_area is recomputed by the tile stage; nothing here needs it
     lc.c[C_TRIS_SETUP]++;
 
@@ -109,17 +110,27 @@ __device__ __forceinline__ void emit_setup(const FrameParams &P, uint32_t fs_id,
         atomicOr(&P.fs->err, ERR_REC_OVF);
         return;
     }
+    uint32_t clip_attr = 0;
+    if (ca) {
+        clip_attr = alloc_slot(&P.fs->n_clip_attr);
+        if (clip_attr >= P.attr_cap) {
+            atomicOr(&P.fs->err, ERR_ATTR_OVF);
+            return;
+        }
+        float4 *ar = reinterpret_cast<float4 *>(&P.attrs[clip_attr]);
+        ar[0] = make_float4(ca[0][0], ca[0][1], ca[0][2], ca[0][3]);
+        ar[1] = make_float4(ca[0][4], ca[0][5], ca[1][0], ca[1][1]);
+        ar[2] = make_float4(ca[1][2], ca[1][3], ca[1][4], ca[1][5]);
+        ar[3] = make_float4(ca[2][0], ca[2][1], ca[2][2], ca[2][3]);
+        ar[4] = make_float4(ca[2][4], ca[2][5], 0.0f, 0.0f);
+    }
     float4 *rr = reinterpret_cast<float4 *>(&P.recs[rec]);
     rr[0] = make_float4(s.px[0], s.py[0], s.px[1], s.py[1]);
     rr[1] = make_float4(s.px[2], s.py[2], s.z[0], s.z[1]);
-    rr[2] = make_float4(s.z[2], s.w[0], s.w[1], s.w[2]);
-    rr[3] = make_float4(__uint_as_float(key), __uint_as_float(fs_id), 0.0f, 0.0f);
-    float4 *ar = reinterpret_cast<float4 *>(&P.attrs[rec]);
-    ar[0] = make_float4(a0[0], a0[1], a0[2], a0[3]);
-    ar[1] = make_float4(a0[4], a0[5], a1[0], a1[1]);
-    ar[2] = make_float4(a1[2], a1[3], a1[4], a1[5]);
-    ar[3] = make_float4(a2[0], a2[1], a2[2], a2[3]);
-    ar[4] = make_float4(a2[4], a2[5], 0.0f, 0.0f);
+    rr[2] = make_float4(s.z[2], __uint_as_float(key), 0.0f, 0.0f);
+    float4 *sr = reinterpret_cast<float4 *>(&P.shade[rec]);
+    sr[0] = make_float4(s.w[0], s.w[1], s.w[2], __uint_as_float(D.fs | (ca ? 4u : 0u) | (D.draw << 3)));
+    sr[1] = make_float4(__uint_as_float(i0), __uint_as_float(i1), __uint_as_float(i2), __uint_as_float(clip_attr));
 
     if (small) {
 #pragma unroll
@@ -174,9 +185,8 @@ __global__ void __launch_bounds__(NT) vertex_kernel(FrameParams P, DrawParams D)
     float c[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) c[r] = dot4z(D.M[4 * r], D.M[4 * r + 1], D.M[4 * r + 2], D.M[4 * r + 3], x, y, z, 1.0f);
-    D.clip[v] = make_float4(c[0], c[1], c[2], c[3]);
-    D.scr[v] = project_vertex(c, (float)P.W, (float)P.H);
-    D.code[v] = clip_code(c);
+    D.vtx[2 * (size_t)v] = project_vertex(c, (float)P.W, (float)P.H);
+    D.vtx[2 * (size_t)v + 1] = make_float4(c[0], c[1], c[2], __uint_as_float(clip_code(c)));
 }
 
 // Stage 1b/2 -- primitive assembly, clip, setup, binning: one thread per input triangle
@@ -200,35 +210,36 @@ __global__ void __launch_bounds__(NT) geom_kernel(FrameParams P, DrawParams D) {
             lc.c[C_TRIS_IN]++;
             const uint32_t vi[3] = {i0, i1, i2};
             const uint32_t key0 = (D.tri_base + t) * 8u;
+            // Everything a triangle may need from its three vertices is requested up front, so the
+            // independent gathers overlap instead of paying one L2 round trip per decision.
+            const float4 sv0 = __ldg(&D.vtx[2 * (size_t)i0]), cq0 = __ldg(&D.vtx[2 * (size_t)i0 + 1]);
+            const float4 sv1 = __ldg(&D.vtx[2 * (size_t)i1]), cq1 = __ldg(&D.vtx[2 * (size_t)i1 + 1]);
+            const float4 sv2 = __ldg(&D.vtx[2 * (size_t)i2]), cq2 = __ldg(&D.vtx[2 * (size_t)i2 + 1]);
+            const float2 q0 = make_float2(cq0.x, cq0.y), q1 = make_float2(cq1.x, cq1.y), q2 = make_float2(cq2.x, cq2.y);
+            const uint32_t code = __float_as_uint(cq0.w) & __float_as_uint(cq1.w) & __float_as_uint(cq2.w);
             // clipping::try_clip (rasterizer/clipping.rs:62-195): degenerate test on clip-space xy first
-            const float2 q0 = __ldg(reinterpret_cast<const float2 *>(&D.clip[i0]));
-            const float2 q1 = __ldg(reinterpret_cast<const float2 *>(&D.clip[i1]));
-            const float2 q2 = __ldg(reinterpret_cast<const float2 *>(&D.clip[i2]));
             const float a2x = cross2(fsub(q1.x, q0.x), fsub(q1.y, q0.y), fsub(q2.x, q0.x), fsub(q2.y, q0.y));
             if (fabsf(a2x) < 0.000001f) {
                 lc.c[C_DEGENERATE]++;
             } else {
-                const uint32_t code = __ldg(&D.code[i0]) & __ldg(&D.code[i1]) & __ldg(&D.code[i2]);
                 if (code & 0xFC0u) { // all three vertices outside one plane
                     lc.c[C_OUTSIDE]++;
                 } else if ((code & 0x3Fu) == 0x3Fu) { // all inside all planes
                     lc.c[C_INSIDE]++;
                     Setup s;
-#pragma unroll
-                    for (int v = 0; v < 3; v++) {
-                        const float4 sv = __ldg(&D.scr[vi[v]]);
-                        s.px[v] = sv.x; s.py[v] = sv.y; s.z[v] = sv.z; s.w[v] = sv.w;
-                    }
-                    emit_setup(P, D.fs, s, D.attr + 6 * (size_t)i0, D.attr + 6 * (size_t)i1, D.attr + 6 * (size_t)i2,
-                               key0, lc);
+                    s.px[0] = sv0.x; s.py[0] = sv0.y; s.z[0] = sv0.z; s.w[0] = sv0.w;
+                    s.px[1] = sv1.x; s.py[1] = sv1.y; s.z[1] = sv1.z; s.w[1] = sv1.w;
+                    s.px[2] = sv2.x; s.py[2] = sv2.y; s.z[2] = sv2.z; s.w[2] = sv2.w;
+                    emit_setup(P, D, s, i0, i1, i2, nullptr, key0, lc);
                 } else {
                     // Sutherland-Hodgman against LEFT,RIGHT,BOTTOM,TOP,NEAR,FAR (clipping.rs:118-171)
                     float pv[2][MAX_POLY][4];
                     float pa[2][MAX_POLY][6];
                     int n_out = 3, cur = 0;
+                    const float4 cqs[3] = {cq0, cq1, cq2};
+                    const float ws[3] = {sv0.w, sv1.w, sv2.w};
                     for (int v = 0; v < 3; v++) {
-                        const float4 cv = __ldg(&D.clip[vi[v]]);
-                        pv[0][v][0] = cv.x; pv[0][v][1] = cv.y; pv[0][v][2] = cv.z; pv[0][v][3] = cv.w;
+                        pv[0][v][0] = cqs[v].x; pv[0][v][1] = cqs[v].y; pv[0][v][2] = cqs[v].z; pv[0][v][3] = ws[v];
                         const float *a = D.attr + 6 * (size_t)vi[v];
                         for (int k = 0; k < 6; k++) pa[0][v][k] = __ldg(a + k);
                     }
@@ -278,8 +289,11 @@ __global__ void __launch_bounds__(NT) geom_kernel(FrameParams P, DrawParams D) {
                             s.px[0] = s0.x; s.py[0] = s0.y; s.z[0] = s0.z; s.w[0] = s0.w;
                             s.px[1] = sb.x; s.py[1] = sb.y; s.z[1] = sb.z; s.w[1] = sb.w;
                             s.px[2] = sc.x; s.py[2] = sc.y; s.z[2] = sc.z; s.w[2] = sc.w;
-                            emit_setup(P, D.fs, s, pa[cur][0], pa[cur][i + 1], pa[cur][i + 2],
-                                       key0 + (uint32_t)min(i, 7), lc);
+                            float ca[3][6];
+                            for (int k = 0; k < 6; k++) {
+                                ca[0][k] = pa[cur][0][k]; ca[1][k] = pa[cur][i + 1][k]; ca[2][k] = pa[cur][i + 2][k];
+                            }
+                            emit_setup(P, D, s, 0u, 0u, 0u, ca, key0 + (uint32_t)min(i, 7), lc);
                             sb = sc;
                         }
                     }
@@ -320,14 +334,14 @@ __global__ void __launch_bounds__(NT) geom_kernel(FrameParams P, DrawParams D) {
     }
 }
 
-__device__ __forceinline__ void load_setup(const RasterRec *recs, uint32_t rec, Setup &s, uint32_t &key, uint32_t &fs) {
+__device__ __forceinline__ void load_setup(const RasterRec *recs, uint32_t rec, Setup &s, uint32_t &key) {
     const float4 *rr = reinterpret_cast<const float4 *>(&recs[rec]);
-    float4 r0 = __ldg(rr), r1 = __ldg(rr + 1), r2 = __ldg(rr + 2), r3 = __ldg(rr + 3);
+    const float4 r0 = __ldg(rr), r1 = __ldg(rr + 1), r2 = __ldg(rr + 2);
     s.px[0] = r0.x; s.py[0] = r0.y; s.px[1] = r0.z; s.py[1] = r0.w;
     s.px[2] = r1.x; s.py[2] = r1.y; s.z[0] = r1.z; s.z[1] = r1.w;
-    s.z[2] = r2.x; s.w[0] = r2.y; s.w[1] = r2.z; s.w[2] = r2.w;
-    key = __float_as_uint(r3.x);
-    fs = __float_as_uint(r3.y);
+    s.z[2] = r2.x;
+    key = __float_as_uint(r2.y);
+    s.w[0] = s.w[1] = s.w[2] = 1.0f;
     setup_edges(s);
 }
 
@@ -346,8 +360,8 @@ __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
         if (item >= n) break;
         const LargeItem li = P.large[item];
         Setup s;
-        uint32_t key, fs;
-        load_setup(P.recs, li.rec, s, key, fs);
+        uint32_t key;
+        load_setup(P.recs, li.rec, s, key);
         BBox b = pixel_bbox(s, P.W, P.H);
         b.y0 = max(b.y0, P.row_begin);
         b.y1 = min(b.y1, P.row_end);

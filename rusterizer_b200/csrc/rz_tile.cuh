@@ -84,9 +84,26 @@ __device__ __forceinline__ uint32_t sample_texture_argb(const TexInfo &t, const 
 // Fragment::interpolate (rasterizer/mod.rs:69-100) + the built-in fragment shaders
 // (main.rs:67-77) + Color::to_argb.  mpost is the POST-depth-test mask, depth0 the pre-test
 // sampled depth of sample 0 (0.0 when uncovered), as FragCoords.depths[0] (mod.rs:458-463).
-__device__ __forceinline__ uint32_t shade(const Setup &s, const AttrRec *ar, uint32_t fs, const TexInfo &tex,
-                                          const float *lut, int X, int Y, uint32_t mpost, float depth0, uint32_t &oob) {
+// `s` needs the screen points and edge normals only; depths_camera_space, the shader id and the
+// attribute locations come from the triangle's ShadeRec.
+__device__ __forceinline__ uint32_t shade(const FrameParams &P, const Setup &s, uint32_t rec, const float *lut, int X,
+                                          int Y, uint32_t mpost, float depth0, uint32_t &oob) {
+    const float4 *sr = reinterpret_cast<const float4 *>(&P.shade[rec]);
+    const float4 s0 = __ldg(sr);
+    const uint32_t info = __float_as_uint(s0.w), fs = info & 3u;
     if (fs == 2u) return to_argb(depth0, depth0, depth0, 1.0f); // Color::grayscale(depths[0])
+    const float4 s1 = __ldg(sr + 1);
+    const float *a0, *a1, *a2;
+    if (info & 4u) { // clipped: interpolated attributes live in an AttrRec
+        a0 = P.attrs[__float_as_uint(s1.w)].a;
+        a1 = a0 + 6;
+        a2 = a0 + 12;
+    } else {         // unclipped: straight from the mesh
+        const float *attr = P.draws[info >> 3].attr;
+        a0 = attr + 6 * (size_t)__float_as_uint(s1.x);
+        a1 = attr + 6 * (size_t)__float_as_uint(s1.y);
+        a2 = attr + 6 * (size_t)__float_as_uint(s1.z);
+    }
     float xs, ys;
     if (mpost == 0xFu) {
         xs = fadd((float)X, 0.5f);
@@ -97,17 +114,16 @@ __device__ __forceinline__ uint32_t shade(const Setup &s, const AttrRec *ar, uin
         ys = fadd((float)Y, rgss_y(i));
     }
     const float e0 = edge_eval(s, 0, xs, ys), e1 = edge_eval(s, 1, xs, ys), e2 = edge_eval(s, 2, xs, ys);
-    const float fu = fdiv(e1, s.w[0]), fv = fdiv(e2, s.w[1]), fw = fdiv(e0, s.w[2]);
+    const float fu = fdiv(e1, s0.x), fv = fdiv(e2, s0.y), fw = fdiv(e0, s0.z);
     const float sum = fadd(fadd(fu, fv), fw);
     const float u = clamp01(fdiv(fu, sum));
     const float v = clamp01(fdiv(fv, sum));
     const float w = clamp01(fsub(fsub(1.0f, u), v));
-    const float *a = ar->a; // vertex k, component c at a[6k + c]
-#define RZ_INTERP(c) fadd(fadd(fmul(__ldg(a + (c)), u), fmul(__ldg(a + 6 + (c)), v)), fmul(__ldg(a + 12 + (c)), w))
+#define RZ_INTERP(c) fadd(fadd(fmul(__ldg(a0 + (c)), u), fmul(__ldg(a1 + (c)), v)), fmul(__ldg(a2 + (c)), w))
     if (fs == 1u) return to_argb(RZ_INTERP(0), RZ_INTERP(1), RZ_INTERP(2), RZ_INTERP(3));
     const float tu = RZ_INTERP(4), tv = RZ_INTERP(5);
 #undef RZ_INTERP
-    return sample_texture_argb(tex, lut, tu, tv, oob);
+    return sample_texture_argb(P.tex0, lut, tu, tv, oob);
 }
 
 // Bitonic network in its "flip then halve" form: every compare-exchange puts the smaller key at
@@ -138,13 +154,13 @@ __device__ __forceinline__ void block_sort(T *a, int n) {
 
 // A large item staged in shared memory for the pixel-parallel walk (24 words).
 struct __align__(16) BigSetup {
-    float px[3], py[3], nx[3], ny[3], z[3], w[3];
+    float px[3], py[3], nx[3], ny[3], z[3];
     float inv;
-    uint32_t key, fs, rec;
+    uint32_t key, rec;
     uint32_t box; // lx0 | ly0 << 8 | bw << 16 | bh << 24   (tile-local)
     uint32_t pad;
 };
-static_assert(sizeof(BigSetup) == 96, "BigSetup must be 24 words");
+static_assert(sizeof(BigSetup) == 80, "BigSetup must be 20 words");
 
 constexpr uint32_t FR_NONE = 0xFFFFu;
 
@@ -161,10 +177,10 @@ struct TileSmemT {
     uint32_t color[TILE_PX * 4];
     uint32_t okey[DBG ? TILE_PX * 4 : 4]; // owner keys (parity instrumentation only)
     float lut[256];                       // (b as f32) / 255.0   (Color::from_rgba, color.rs:22-29)
-    float it_f[13][NT];                   // items of the current chunk: px,py x3 | z x3 | inv | w x3
+    float it_f[10][NT];                   // items of the current chunk: px,py x3 | z x3 | inv
     uint32_t it_key[NT], it_rec[NT];
     uint16_t it_rcp[NT];                  // ceil(1024 / bw): j / bw == (j * rcp) >> 10 for j < 32, bw <= 16
-    uint32_t it_box[NT];                  // lx0 | ly0 << 8 | bw << 16 | fs << 24
+    uint32_t it_box[NT];                  // lx0 | ly0 << 8 | bw << 16
     uint32_t pre[NT + 1];                 // exclusive prefix of the in-tile bbox areas (work units)
     uint8_t unit_item[CHUNK * SMALL_PX];  // work unit -> item
     union {
@@ -251,12 +267,12 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
             const int item = pos + tid;
             const bool valid = tid < CHUNK && item < n;
             Setup s;
-            uint32_t rec = 0, key = 0, fs = 0;
+            uint32_t rec = 0, key = 0;
             int bx0 = 0, by0 = 0, bw = 0, bh = 0; // in-tile bbox, tile-local origin
             bool big = false;
             if (valid) {
                 rec = (uint32_t)__ldcg(bin + item);
-                load_setup(P.recs, rec, s, key, fs);
+                load_setup(P.recs, rec, s, key);
                 BBox b = pixel_bbox(s, P.W, P.H);
                 const int x0 = max((int)b.x0, tileX0), x1 = min((int)b.x1, tileX0 + TW);
                 const int y0 = max((int)b.y0, tileY0), y1 = min((int)b.y1, tileY0 + TH);
@@ -291,9 +307,9 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
 #pragma unroll
                     for (int k = 0; k < 3; k++) {
                         b.px[k] = s.px[k]; b.py[k] = s.py[k]; b.nx[k] = s.nx[k]; b.ny[k] = s.ny[k];
-                        b.z[k] = s.z[k]; b.w[k] = s.w[k];
+                        b.z[k] = s.z[k];
                     }
-                    b.inv = s.inv; b.key = key; b.fs = fs; b.rec = rec;
+                    b.inv = s.inv; b.key = key; b.rec = rec;
                     b.box = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bw << 16) | ((uint32_t)bh << 24);
                 }
                 __syncthreads();
@@ -313,7 +329,7 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
 #pragma unroll
                     for (int k = 0; k < 3; k++) {
                         q.px[k] = B[it].px[k]; q.py[k] = B[it].py[k]; q.nx[k] = B[it].nx[k]; q.ny[k] = B[it].ny[k];
-                        q.z[k] = B[it].z[k]; q.w[k] = B[it].w[k];
+                        q.z[k] = B[it].z[k];
                     }
                     q.inv = B[it].inv;
                     const uint32_t m = coverage_mask(q, X, Y);
@@ -329,8 +345,7 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                     if (!mp) continue;
                     c_shaded++;
                     c_samples += __popc(mp);
-                    const uint32_t argb =
-                        shade(q, &P.attrs[B[it].rec], B[it].fs, P.tex0, S.lut, X, Y, mp, zs[0], c_oob);
+                    const uint32_t argb = shade(P, q, B[it].rec, S.lut, X, Y, mp, zs[0], c_oob);
 #pragma unroll
                     for (int k = 0; k < 4; k++)
                         if ((mp >> k) & 1u) {
@@ -359,10 +374,9 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                 S.it_f[3][tid] = s.py[1]; S.it_f[4][tid] = s.px[2]; S.it_f[5][tid] = s.py[2];
                 S.it_f[6][tid] = s.z[0]; S.it_f[7][tid] = s.z[1]; S.it_f[8][tid] = s.z[2];
                 S.it_f[9][tid] = s.inv;
-                S.it_f[10][tid] = s.w[0]; S.it_f[11][tid] = s.w[1]; S.it_f[12][tid] = s.w[2];
                 S.it_key[tid] = key; S.it_rec[tid] = rec;
                 S.it_rcp[tid] = (uint16_t)((1024 + bw - 1) / max(bw, 1));
-                S.it_box[tid] = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bw << 16) | (fs << 24);
+                S.it_box[tid] = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bw << 16);
             }
             uint32_t incl = area;
 #pragma unroll
@@ -517,11 +531,10 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                 Setup q;
                 q.px[0] = S.it_f[0][it]; q.py[0] = S.it_f[1][it]; q.px[1] = S.it_f[2][it];
                 q.py[1] = S.it_f[3][it]; q.px[2] = S.it_f[4][it]; q.py[2] = S.it_f[5][it];
-                q.w[0] = S.it_f[10][it]; q.w[1] = S.it_f[11][it]; q.w[2] = S.it_f[12][it];
                 setup_normals(q);
                 const float4 z = S.u.fr.z[f];
-                const uint32_t argb = shade(q, &P.attrs[S.it_rec[it]], S.it_box[it] >> 24, P.tex0, S.lut,
-                                            tileX0 + (int)(p % TW), tileY0 + (int)(p / TW), fin & 0xFu, z.x, c_oob);
+                const uint32_t argb = shade(P, q, S.it_rec[it], S.lut, tileX0 + (int)(p % TW), tileY0 + (int)(p / TW),
+                                            fin & 0xFu, z.x, c_oob);
                 const float zz[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
                 for (int k = 0; k < 4; k++)

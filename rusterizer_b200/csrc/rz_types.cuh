@@ -28,6 +28,7 @@ enum : uint32_t {
     ERR_BIN_OVF = 2u,    // a tile list outgrew its bin
     ERR_LARGE_OVF = 4u,  // large-triangle queue too small
     ERR_INDEX = 8u,      // mesh index >= nv
+    ERR_ATTR_OVF = 16u,  // clipped-attribute array too small
 };
 
 // counter slots in FrameState::counters (same order as rz_counters_t)
@@ -46,24 +47,39 @@ struct FrameState {
     uint32_t pad0[3];
     uint32_t n_records;   // emitted (post-clip, post-cull) triangles       <- per-frame part starts here
     uint32_t n_large;     // large-triangle binning work items
+    uint32_t n_clip_attr; // AttrRec slots handed out to clipped triangles
     uint32_t large_next;  // work-stealing cursor of the large binning kernel
-    uint32_t pad1;
 };
 
-// Raster record: everything the tile stage needs to re-create RasterizerTriangle
-// (rasterizer/mod.rs:178-184) except the attributes.  64 B = 4 x float4.
+// Raster record: what coverage + depth need to re-create RasterizerTriangle (rasterizer/mod.rs:178-184):
+// the three screen points and depths, and the submission-order key.  48 B = 3 x float4.
 struct __align__(16) RasterRec {
     float p0x, p0y, p1x, p1y;
     float p2x, p2y, z0, z1;
-    float z2, w0, w1, w2;
+    float z2;
     uint32_t key;   // submission order: 8 * (triangle number in frame) + fan index
-    uint32_t fs;    // fragment shader id of the draw
     uint32_t pad0, pad1;
 };
 
-// Attribute record: VertexAttribute x3 (graphics_primitives.rs:10-13), 18 floats padded to 80 B.
+// Shade record: what only visible fragments need -- depths_camera_space, the fragment shader id and
+// where the three VertexAttributes live.  Unclipped triangles point at the mesh's own attribute
+// array through their vertex indices (nothing is copied); clipped ones at an AttrRec.  32 B.
+struct __align__(16) ShadeRec {
+    float w0, w1, w2;
+    uint32_t info;        // fs | clipped << 2 | draw << 3
+    uint32_t i0, i1, i2;  // vertex indices into the draw's attribute array (unclipped)
+    uint32_t clip_attr;   // index into FrameParams::attrs (clipped)
+};
+
+// Interpolated attributes of a clipped triangle: VertexAttribute x3 (graphics_primitives.rs:10-13),
+// 18 floats padded to 80 B.
 struct __align__(16) AttrRec {
     float a[20];
+};
+
+// Per-draw data the shading step dereferences
+struct DrawInfo {
+    const float *attr; // [nv][6]
 };
 
 // Large-triangle binning work item
@@ -88,7 +104,10 @@ struct FrameParams {
     uint32_t *tile_count;        // [tiles_x * tiles_y]
     unsigned long long *bins;    // [tiles][bin_cap]  (key << 32 | rec)
     RasterRec *recs;
-    AttrRec *attrs;
+    ShadeRec *shade;
+    AttrRec *attrs;              // clipped triangles only
+    const DrawInfo *draws;
+    uint32_t attr_cap;
     LargeItem *large;
     uint32_t *out;               // resolved framebuffer u32[H][W]
     float *dbg_depth;            // optional [H][W][4]
@@ -102,12 +121,13 @@ struct DrawParams {
     const float *pos;      // [nv][3]
     const float *attr;     // [nv][6]
     const uint32_t *idx;   // [3*nt]
-    float4 *clip;          // [nv] vertex-stage output: clip-space position (Point4D<ClipSpace>)
-    float4 *scr;           // [nv] screen x, y, depth and clip w (perspective divide + viewport)
-    uint32_t *code;        // [nv] the 12 trivial accept/reject comparisons of the clipper
+    float4 *vtx;           // [nv][2] vertex-stage output, one 32 B sector per vertex:
+                           //   [0] = screen x, y, depth, clip w   (perspective divide + viewport)
+                           //   [1] = clip x, y, z, bits(the 12 trivial accept/reject comparisons)
     uint32_t nv, nt;
     uint32_t tri_base;     // triangle number of this draw's first triangle inside the frame
     uint32_t fs;
+    uint32_t draw;         // index into FrameParams::draws
     float M[16];           // (projection * view) * world, row-major (main.rs:147-152)
 };
 
