@@ -150,6 +150,9 @@ uint64_t rz_launch_count(rz_ctx *ctx);
  * triangle that last wrote each sample.  Each array is [height][width][4]; any may be NULL. */
 int rz_debug_capture(rz_ctx *ctx, int enable);
 int rz_debug_read(rz_ctx *ctx, float *depth, uint32_t *color, uint32_t *owner);
+/* Profiling aid (capture must be enabled): for every non-empty tile of the last frame, 4 u64 words:
+ * tile id | list length << 32, start and end of its processing in GPU nanoseconds, SM id. */
+int rz_debug_tile_times(rz_ctx *ctx, uint64_t *out, uint32_t max_tiles, uint32_t *n_written);
 /* Vertex stage only (render.rs:104-108): clip-space positions f32[nv][4] of a mesh under the
  * current uniform block. */
 int rz_debug_vertex_stage(rz_ctx *ctx, const rz_mesh *mesh, float *out_clip);

@@ -67,6 +67,7 @@ struct rz_ctx {
     unsigned long long *d_cnt_backup = nullptr;
     float *d_dbg_depth = nullptr;
     uint32_t *d_dbg_color = nullptr, *d_dbg_owner = nullptr;
+    unsigned long long *d_dbg_time = nullptr;
     float4 *d_vtx = nullptr; // vertex-stage scratch [vert_cap][2], sized for the largest mesh
     uint32_t vert_cap = 0;
     uint32_t rec_cap = 0, bin_cap = 0, large_cap = 0;
@@ -120,7 +121,9 @@ static void mat4_mul(const float *A, const float *B, float *R) {
     memcpy(R, out, sizeof out);
 }
 
-static size_t state_bytes(const rz_ctx *c) { return sizeof(FrameState) + sizeof(uint32_t) * (size_t)c->tiles_x * c->tiles_y; }
+// FrameState, then tile_count[tiles] (zeroed every frame), then busy[tiles] (not zeroed)
+static size_t zeroed_state_bytes(const rz_ctx *c) { return sizeof(FrameState) + sizeof(uint32_t) * (size_t)c->tiles_x * c->tiles_y; }
+static size_t state_bytes(const rz_ctx *c) { return zeroed_state_bytes(c) + sizeof(uint32_t) * (size_t)c->tiles_x * c->tiles_y; }
 
 static int free_frame_buffers(rz_ctx *c) {
     cudaFree(c->d_bins); c->d_bins = nullptr;
@@ -230,7 +233,7 @@ void rz_destroy(rz_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_frame_buffers(c);
     cudaFree(c->d_state); cudaFree(c->d_out); cudaFree(c->d_cnt_backup);
-    cudaFree(c->d_dbg_depth); cudaFree(c->d_dbg_color); cudaFree(c->d_dbg_owner);
+    cudaFree(c->d_dbg_depth); cudaFree(c->d_dbg_color); cudaFree(c->d_dbg_owner); cudaFree(c->d_dbg_time);
     for (auto &t : c->textures) cudaFree(t.d_data);
     for (auto *m : c->staging) rz_mesh_destroy(m);
     if (c->h_state) cudaFreeHost(c->h_state);
@@ -376,11 +379,13 @@ static FrameParams make_params(rz_ctx *c, uint32_t *out_base) {
     P.rec_cap = c->rec_cap; P.bin_cap = c->bin_cap; P.large_cap = c->large_cap;
     P.fs = reinterpret_cast<FrameState *>(c->d_state);
     P.tile_count = reinterpret_cast<uint32_t *>(c->d_state + sizeof(FrameState));
+    P.busy = P.tile_count + (size_t)c->tiles_x * c->tiles_y;
     P.bins = c->d_bins; P.recs = c->d_recs; P.shade = c->d_shade; P.attrs = c->d_attrs; P.large = c->d_large;
     P.draws = c->d_draws; P.attr_cap = c->attr_cap;
     P.out = out_base;
     if (c->debug) {
         P.dbg_depth = c->d_dbg_depth; P.dbg_color = c->d_dbg_color; P.dbg_owner = c->d_dbg_owner;
+        P.dbg_tile_time = c->d_dbg_time;
     }
     if (!c->textures.empty()) {
         const Texture &t = c->textures[0];
@@ -426,7 +431,7 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     FrameParams P = make_params(c, out_base);
     cudaStream_t st = c->stream;
     const size_t off = offsetof(FrameState, n_records);
-    CU(c, cudaMemsetAsync(c->d_state + off, 0, state_bytes(c) - off, st));
+    CU(c, cudaMemsetAsync(c->d_state + off, 0, zeroed_state_bytes(c) - off, st));
     if (timed) CU(c, cudaEventRecord(c->ev[0], st));
     uint32_t tri_base = 0, draw_index = 0;
     for (auto &d : c->draws) {
@@ -448,7 +453,7 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     c->launches++;
     if (timed) CU(c, cudaEventRecord(c->ev[2], st));
     const uint32_t n_tiles = P.tiles_x * (P.ty_end - P.ty_begin);
-    const dim3 tile_grid(P.tiles_x, P.ty_end - P.ty_begin);
+    const dim3 tile_grid(std::min<uint32_t>(n_tiles, (uint32_t)c->num_sms * 3u)); // persistent CTAs, 3 per SM
     if (n_tiles) {
         if (c->debug)
             tile_kernel<true><<<tile_grid, NT, sizeof(TileSmemT<true>), st>>>(P);
@@ -615,6 +620,8 @@ int rz_debug_capture(rz_ctx *c, int enable) {
         CU(c, cudaMalloc(&c->d_dbg_depth, n * 4));
         CU(c, cudaMalloc(&c->d_dbg_color, n * 4));
         CU(c, cudaMalloc(&c->d_dbg_owner, n * 4));
+        CU(c, cudaMalloc(&c->d_dbg_time, (size_t)c->tiles_x * c->tiles_y * 32));
+        CU(c, cudaMemset(c->d_dbg_time, 0, (size_t)c->tiles_x * c->tiles_y * 32));
     }
     c->debug = enable != 0;
     return RZ_OK;
@@ -629,6 +636,17 @@ int rz_debug_read(rz_ctx *c, float *depth, uint32_t *color, uint32_t *owner) {
     if (depth) CU(c, cudaMemcpy(depth, c->d_dbg_depth, bytes, cudaMemcpyDeviceToHost));
     if (color) CU(c, cudaMemcpy(color, c->d_dbg_color, bytes, cudaMemcpyDeviceToHost));
     if (owner) CU(c, cudaMemcpy(owner, c->d_dbg_owner, bytes, cudaMemcpyDeviceToHost));
+    return RZ_OK;
+}
+
+int rz_debug_tile_times(rz_ctx *c, uint64_t *out, uint32_t max_tiles, uint32_t *n_written) {
+    if (!c || !out || !n_written) return RZ_E_INVALID;
+    if (!c->d_dbg_time) return fail(c, RZ_E_INVALID, "rz_debug_tile_times: capture was never enabled");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    const uint32_t n = std::min<uint32_t>(max_tiles, c->tiles_x * c->tiles_y);
+    CU(c, cudaMemcpy(out, c->d_dbg_time, (size_t)n * 32, cudaMemcpyDeviceToHost));
+    *n_written = n;
     return RZ_OK;
 }
 

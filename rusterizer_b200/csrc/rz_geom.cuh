@@ -31,6 +31,7 @@ __device__ __forceinline__ uint32_t alloc_slot(uint32_t *cursor) {
 
 __device__ __forceinline__ void push_bin(const FrameParams &P, uint32_t tile, uint32_t key, uint32_t rec) {
     uint32_t slot = atomicAdd(&P.tile_count[tile], 1u);
+    if (slot == 0u) P.busy[atomicAdd(&P.fs->n_busy, 1u)] = tile; // first triangle of this tile
     if (slot < P.bin_cap)
         P.bins[(size_t)tile * P.bin_cap + slot] = ((unsigned long long)key << 32) | rec;
     else

@@ -190,7 +190,7 @@ struct TileSmemT {
     } u;
     uint32_t head[TILE_PX];               // per-pixel fragment list heads; reused as resolve staging
     uint32_t scan[NT / 32];
-    uint32_t first_big, first_small, nfrag, ovf;
+    uint32_t first_big, first_small, nfrag, ovf, cur_tile;
 };
 
 // Sort the tile's list by order key (in shared memory when it fits, else in place in HBM) and
@@ -216,31 +216,63 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
     SM &S = *reinterpret_cast<SM *>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tx = blockIdx.x, ty = P.ty_begin + blockIdx.y;
-    const uint32_t tile = ty * P.tiles_x + tx;
-    const int tileX0 = tx * TW, tileY0 = ty * TH;
     const int lx = tid % TW, ly = tid / TW;
-    const int X = tileX0 + lx, Y = tileY0 + ly;
+    uint32_t c_cov = 0, c_shaded = 0, c_samples = 0, c_oob = 0;
 
-    const uint32_t n_total = P.tile_count[tile];
-    const int n = (int)min(n_total, P.bin_cap);
-
-    if (n == 0 && !DBG) {
-        // nothing was binned here: the box filter of four clear samples is the clear colour
-        // (buffers.rs:5,111-125) -- write it without touching shared memory
-        if ((P.W & 3u) == 0u) {
-            if (tid < TH * (TW / 4)) {
-                const int row = tid / (TW / 4), q = tid % (TW / 4);
-                const int Yr = tileY0 + row, Xq = tileX0 + q * 4;
-                if (Yr < (int)P.H && Xq < (int)P.W)
-                    *reinterpret_cast<uint4 *>(&P.out[(size_t)Yr * P.W + Xq]) =
-                        make_uint4(CLEAR_COLOR, CLEAR_COLOR, CLEAR_COLOR, CLEAR_COLOR);
+    // ---- phase 0: tiles nothing was binned into.  The box filter of four clear samples is the clear
+    // colour (buffers.rs:5,111-125): one warp writes such a tile as 64 128-bit stores. ----
+    {
+        const uint32_t shard_tiles = P.tiles_x * (P.ty_end - P.ty_begin);
+        for (uint32_t i = blockIdx.x * (NT / 32) + warp; i < shard_tiles; i += gridDim.x * (NT / 32)) {
+            const uint32_t t = P.ty_begin * P.tiles_x + i;
+            if (P.tile_count[t] != 0u) continue;
+            const int x0 = (int)(t % P.tiles_x) * TW, y0 = (int)(t / P.tiles_x) * TH;
+            if ((P.W & 3u) == 0u) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int e = lane + 32 * h, row = e / (TW / 4), q = e % (TW / 4);
+                    const int Yr = y0 + row, Xq = x0 + q * 4;
+                    if (Yr < (int)P.H && Xq < (int)P.W)
+                        *reinterpret_cast<uint4 *>(&P.out[(size_t)Yr * P.W + Xq]) =
+                            make_uint4(CLEAR_COLOR, CLEAR_COLOR, CLEAR_COLOR, CLEAR_COLOR);
+                }
+            } else {
+                for (int e = lane; e < TILE_PX; e += 32) {
+                    const int Yr = y0 + e / TW, Xq = x0 + e % TW;
+                    if (Yr < (int)P.H && Xq < (int)P.W) P.out[(size_t)Yr * P.W + Xq] = CLEAR_COLOR;
+                }
             }
-        } else if (X < (int)P.W && Y < (int)P.H) {
-            P.out[(size_t)Y * P.W + X] = CLEAR_COLOR;
+            if (DBG) {
+                for (int e = lane; e < TILE_PX; e += 32) {
+                    const int Yr = y0 + e / TW, Xq = x0 + e % TW;
+                    if (Yr >= (int)P.H || Xq >= (int)P.W) continue;
+                    const size_t o = ((size_t)Yr * P.W + Xq) * 4;
+                    for (int k = 0; k < 4; k++) {
+                        if (P.dbg_depth) P.dbg_depth[o + k] = CLEAR_DEPTH;
+                        if (P.dbg_color) P.dbg_color[o + k] = CLEAR_COLOR;
+                        if (P.dbg_owner) P.dbg_owner[o + k] = NO_OWNER;
+                    }
+                }
+            }
         }
-        return;
     }
+
+    // ---- phase 1: persistent loop over the tiles that received triangles (dynamic work stealing) ----
+    S.lut[tid] = fdiv((float)tid, 255.0f);
+    const uint32_t n_busy = P.fs->n_busy;
+    for (;;) {
+    __syncthreads(); // previous tile fully retired (also covers S.lut on the first trip)
+    if (tid == 0) S.cur_tile = atomicAdd(&P.fs->tile_cursor, 1u);
+    __syncthreads();
+    const uint32_t work = S.cur_tile;
+    if (work >= n_busy) break;
+    const uint32_t tile = P.busy[work];
+    const uint32_t tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+    const int tileX0 = tx * TW, tileY0 = ty * TH;
+    const int X = tileX0 + lx, Y = tileY0 + ly;
+    const int n = (int)min(P.tile_count[tile], P.bin_cap);
+    unsigned long long t_start = 0;
+    if (DBG && P.dbg_tile_time && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
 
     // clear (the state resolve_and_clear leaves behind, rasterizer/mod.rs:497-506)
 #pragma unroll
@@ -249,11 +281,9 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
         S.color[tid * 4 + k] = CLEAR_COLOR;
         if (DBG) S.okey[tid * 4 + k] = NO_OWNER;
     }
-    uint32_t c_cov = 0, c_shaded = 0, c_samples = 0, c_oob = 0;
 
     if (n > 0) {
         S.head[tid] = FR_NONE;
-        S.lut[tid] = fdiv((float)tid, 255.0f);
         unsigned long long *bin = P.bins + (size_t)tile * P.bin_cap;
         bool sorted = false;
         if (n > CHUNK) {
@@ -575,8 +605,19 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
         P.out[(size_t)Y * P.W + X] = res;
     }
 
+    if (DBG && P.dbg_tile_time && tid == 0) {
+        unsigned long long t_end;
+        uint32_t smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned long long *o = P.dbg_tile_time + 4 * (size_t)work;
+        o[0] = (unsigned long long)tile | ((unsigned long long)n << 32);
+        o[1] = t_start; o[2] = t_end; o[3] = smid;
+    }
+    } // persistent tile loop
+
     // ---- counters: warp reduce -> per-warp partials -> one striped global RED per counter ----
-    if (n > 0) {
+    {
         c_cov = __reduce_add_sync(0xffffffffu, c_cov);
         c_shaded = __reduce_add_sync(0xffffffffu, c_shaded);
         c_samples = __reduce_add_sync(0xffffffffu, c_samples);
@@ -592,7 +633,7 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
 #pragma unroll
             for (int w = 0; w < NT / 32; w++) sum += S.pre[w * 4 + tid];
             const int slot = tid == 0 ? C_COVERED_PX : (tid == 1 ? C_SHADED_PX : (tid == 2 ? C_SAMPLES : C_TEX_OOB));
-            if (sum) atomicAdd(&P.fs->counters[tile % CNT_STRIPES][slot], sum);
+            if (sum) atomicAdd(&P.fs->counters[blockIdx.x % CNT_STRIPES][slot], sum);
         }
     }
 }

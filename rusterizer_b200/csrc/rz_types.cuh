@@ -49,6 +49,9 @@ struct FrameState {
     uint32_t n_large;     // large-triangle binning work items
     uint32_t n_clip_attr; // AttrRec slots handed out to clipped triangles
     uint32_t large_next;  // work-stealing cursor of the large binning kernel
+    uint32_t n_busy;      // tiles that received at least one triangle (entries of FrameParams::busy)
+    uint32_t tile_cursor; // work-stealing cursor of the tile kernel
+    uint32_t pad1[2];
 };
 
 // Raster record: what coverage + depth need to re-create RasterizerTriangle (rasterizer/mod.rs:178-184):
@@ -102,6 +105,7 @@ struct FrameParams {
     uint32_t rec_cap, bin_cap, large_cap;
     FrameState *fs;
     uint32_t *tile_count;        // [tiles_x * tiles_y]
+    uint32_t *busy;              // [tiles_x * tiles_y] ids of the non-empty tiles, in no particular order
     unsigned long long *bins;    // [tiles][bin_cap]  (key << 32 | rec)
     RasterRec *recs;
     ShadeRec *shade;
@@ -113,6 +117,7 @@ struct FrameParams {
     float *dbg_depth;            // optional [H][W][4]
     uint32_t *dbg_color;
     uint32_t *dbg_owner;
+    unsigned long long *dbg_tile_time; // optional [tiles][4]: tile id | n << 32, start ns, end ns, SM id
     TexInfo tex0;
 };
 

@@ -36,7 +36,7 @@ ABI_SYMBOLS = (
     "rz_mesh_create", "rz_mesh_destroy", "rz_render", "rz_render_host", "rz_framebuffer",
     "rz_framebuffer_async", "rz_sync", "rz_set_row_range", "rz_tile_width", "rz_tile_height",
     "rz_counters", "rz_reset_counters", "rz_timings", "rz_launch_count", "rz_debug_capture",
-    "rz_debug_read", "rz_debug_vertex_stage", "rz_last_error", "rz_version",
+    "rz_debug_read", "rz_debug_tile_times", "rz_debug_vertex_stage", "rz_last_error", "rz_version",
 )
 
 ERROR_NAMES = {0: "RZ_OK", -1: "RZ_E_INVALID", -2: "RZ_E_CUDA", -3: "RZ_E_NO_DEVICE", -4: "RZ_E_TEXTURE",
@@ -102,6 +102,7 @@ def load_library() -> C.CDLL:
     L.rz_launch_count.restype = C.c_uint64
     L.rz_debug_capture.argtypes = [vp, C.c_int]
     L.rz_debug_read.argtypes = [vp, vp, vp, vp]
+    L.rz_debug_tile_times.argtypes = [vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
     L.rz_debug_vertex_stage.argtypes = [vp, vp, fp]
     L.rz_last_error.argtypes = [vp]
     L.rz_last_error.restype = C.c_char_p
@@ -307,6 +308,14 @@ class Renderer:
         d, c, o = np.empty(shape, np.float32), np.empty(shape, np.uint32), np.empty(shape, np.uint32)
         self._check(self._L.rz_debug_read(self._ctx, d.ctypes.data, c.ctypes.data, o.ctypes.data))
         return d, c, o
+
+    def tile_times(self) -> np.ndarray:
+        """(n_tiles, 4) u64: tile id | n << 32, start ns, end ns, SM id (zeros for unused rows)."""
+        n = ((self.width + 15) // 16) * ((self.height + 15) // 16)
+        out = np.zeros((n, 4), np.uint64)
+        got = C.c_uint32()
+        self._check(self._L.rz_debug_tile_times(self._ctx, out.ctypes.data, n, C.byref(got)))
+        return out[: got.value]
 
     def vertex_stage(self, mesh: DeviceMesh) -> np.ndarray:
         out = np.empty((mesh.n_vertices, 4), np.float32)

@@ -1,0 +1,25 @@
+import sys; sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+import numpy as np
+from rusterizer_b200 import scenes
+from rusterizer_b200.render import Renderer
+sc = scenes.sphere_scene()
+r = Renderer(sc.width, sc.height); r.uniforms().bind_texture(0, sc.texture)
+dm = r.upload(sc.draws[0].mesh)
+r.debug_capture(True)
+for i in range(3):
+    scenes.render_scene(r, sc, [dm]); r.framebuffer_device()
+print(r.timings())
+t = r.tile_times(); t = t[t[:,2] > 0]
+n = (t[:,0] >> np.uint64(32)).astype(int); dur = (t[:,2]-t[:,1]).astype(float)/1e3
+t0 = t[:,1].min(); print("tiles", len(t), "span us", (t[:,2].max()-t0)/1e3)
+print("dur us: mean %.1f p50 %.1f p90 %.1f p99 %.1f max %.1f" % (dur.mean(), np.percentile(dur,50), np.percentile(dur,90), np.percentile(dur,99), dur.max()))
+o = np.argsort(-dur)[:12]
+for k in o: print("  tile", int(t[k,0] & np.uint64(0xffffffff)), "n", n[k], "dur %.1f start %.1f sm %d" % (dur[k], (t[k,1]-t0)/1e3, t[k,3]))
+for lo,hi in [(1,32),(32,64),(64,128),(128,256),(256,512),(512,4096)]:
+    m = (n>=lo)&(n<hi)
+    if m.any(): print(f"n in [{lo},{hi}): tiles {m.sum():5d} mean dur {dur[m].mean():6.1f} us  total {dur[m].sum()/1e3:7.2f} ms")
+print("sum of durations ms", dur.sum()/1e3, " / (444 slots) = us", dur.sum()/444)
+# per SM busy time
+sm = t[:,3].astype(int)
+bus = np.bincount(sm, weights=dur)
+print("per-SM sum dur: min %.0f mean %.0f max %.0f (x1/3 if 3 CTAs overlap)" % (bus[bus>0].min(), bus[bus>0].mean(), bus.max()))
