@@ -235,3 +235,19 @@ def test_capacity_growth_dense_tile():
     s = scenes.overdraw_scene(12, 12, width=64, height=64)
     s.draws = [scenes.Draw(d.mesh, d.world, d.fs) for d in s.draws] * 10
     check(s)
+
+
+def test_cpp_host_demo_runs():
+    """The C++ mirror of the crate API renders the Mode::Demo frame on the GPU (main.rs:93-105)."""
+    import re
+    import subprocess
+    from pathlib import Path
+
+    demo = Path(__file__).resolve().parent.parent / "rusterizer_b200" / "host" / "rz_demo"
+    p = subprocess.run([str(demo), "1.0"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    m = re.search(r"tris_in=(\d+) samples_written=(\d+) touched_px=(\d+)", p.stdout)
+    assert m and int(m.group(1)) == 268
+    o = oracle_render(scenes.default_scene(1.0))
+    # libm vs Python trig may differ in the last bit of a matrix entry, so compare loosely
+    assert abs(int(m.group(2)) - o["counters"]["n_samples_written"]) < 0.01 * o["counters"]["n_samples_written"]

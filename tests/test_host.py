@@ -106,6 +106,22 @@ def test_no_cpu_fallback_without_gpu():
     assert e.value.code == -3 and "no CPU fallback" in str(e.value)
 
 
+def test_cpp_host_mirror_builds_and_fails_loudly_without_gpu():
+    """rusterizer.hpp + demo_main.cpp (the crate's Mode::Demo frame) compile and link against the C ABI;
+    without a GPU the demo must stop at rz_create with RZ_E_NO_DEVICE."""
+    import torch
+
+    import __graft_entry__ as g
+
+    g.build()
+    demo = ROOT / "rusterizer_b200" / "host" / "rz_demo"
+    assert demo.exists()
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present (the demo is run by the gpu tests)")
+    p = subprocess.run([str(demo)], capture_output=True, text=True)
+    assert p.returncode == 1 and "no CUDA device" in p.stderr
+
+
 def test_product_package_never_imports_the_oracle():
     """oracle/ is test infrastructure: nothing under rusterizer_b200/ may import, load or call it."""
     for path in (ROOT / "rusterizer_b200").rglob("*"):
