@@ -89,12 +89,12 @@ __device__ __forceinline__ void emit_setup(const FrameParams &P, const DrawParam
         const float tau = 1.1920929e-07f * (34.0f * Bw * Bh + 14.0f * (Bw + Bh)) + 1e-30f;
         if (area2 < -tau) return;
     }
-    const bool small = bw <= GEOM_SMALL_DIM && bh <= GEOM_SMALL_DIM && bw * bh <= GEOM_SMALL_PX;
+    const bool small = bw <= GEOM_SMALL_DIM && bh <= GEOM_SMALL_DIM;
     const uint32_t tx0 = b.x0 / TW, ty0 = b.y0 / TH;
     uint32_t tmask = 0;
     if (small) {
         const uint32_t tx1 = (b.x1 - 1) / TW, ty1 = (b.y1 - 1) / TH;
-        if (area2 < GEOM_THIN_AREA2) {
+        if (area2 < GEOM_THIN_AREA2 && bw * bh <= GEOM_THIN_PX) {
             // (2) thin / tiny triangles usually touch no sample at all: rasterise them exactly right
             // here so they never reach a tile list (pole slivers of a UV-sphere, distant meshes)
             for (uint32_t Y = b.y0; Y < b.y1; Y++)
@@ -346,18 +346,17 @@ __device__ __forceinline__ void load_setup(const RasterRec *recs, uint32_t rec, 
     setup_edges(s);
 }
 
-// Large-triangle binning: persistent CTAs steal (triangle, slab of tile rows) items; the 256
-// threads test the slab's tiles in parallel.  A tile is skipped only when, for some edge, the
+// Large-triangle binning: persistent warps steal (triangle, slab of tile rows) items; the 32
+// lanes test the slab's tiles in parallel.  A tile is skipped only when, for some edge, the
 // most favourable sample position of tile-cap-bbox already fails that edge -- exact because the
 // f32 edge function is monotone in x and in y.
 __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
-    __shared__ uint32_t s_item;
     const uint32_t n = min(P.fs->n_large, P.large_cap);
-    for (;;) {
-        if (threadIdx.x == 0) s_item = atomicAdd(&P.fs->large_next, 1u);
-        __syncthreads();
-        const uint32_t item = s_item;
-        __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (;;) { // one warp per (triangle, slab) item, stolen from a global cursor
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(&P.fs->large_next, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n) break;
         const LargeItem li = P.large[item];
         Setup s;
@@ -368,7 +367,7 @@ __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
         b.y1 = min(b.y1, P.row_end);
         const uint32_t tx0 = b.x0 / TW, tx1 = (b.x1 - 1) / TW + 1, ntx = tx1 - tx0;
         const uint32_t total = ntx * (li.ty1 - li.ty0);
-        for (uint32_t t = threadIdx.x; t < total; t += NT) {
+        for (uint32_t t = lane; t < total; t += 32) {
             const uint32_t tx = tx0 + t % ntx, ty = li.ty0 + t / ntx;
             const uint32_t X0 = max(b.x0, tx * TW), X1 = min(b.x1, tx * TW + TW);
             const uint32_t Y0 = max(b.y0, ty * TH), Y1 = min(b.y1, ty * TH + TH);

@@ -5,7 +5,7 @@
 // memory from clear to resolve and only the box-filtered u32 image goes back to HBM.
 //
 // Submission order is honoured exactly, but without serialising on it.
-// Within a chunk of <= 255 SMALL items (in-tile bbox <= 32 px) every covered pixel of every item
+// Within a chunk of <= 255 items (and <= 8192 bbox pixels) every covered pixel of every item
 // becomes a FRAGMENT record {item, pixel, coverage, 4 sample depths} on a per-pixel list, and
 // each fragment F decides by itself, from the other fragments G of its pixel, what the ordered
 // replay of the reference would have done:
@@ -18,9 +18,9 @@
 //   phase A  thread = item     exact coverage over its bbox; sample depths -> fragment records
 //   phase B  thread = fragment m(F), v(F) from the pixel's list
 //   phase C  thread = fragment interpolate + fragment shader + pack; write samples
-// Tiles that need several chunks, or that contain LARGE items, sort their list by order key first;
-// runs of large items are walked pixel-parallel (a thread owns a pixel for the whole run, so it
-// applies the triangles in order by construction).
+// Tiles that need several chunks sort their list by order key first.  Items with non-finite or absurd
+// coordinates take a literal pixel-parallel walk (a thread owns a pixel for the whole run, so it
+// applies the triangles in order by construction) that evaluates EdgeFunctions::inside verbatim.
 #pragma once
 #include "rz_exact.cuh"
 #include "rz_geom.cuh"
@@ -179,10 +179,10 @@ struct TileSmemT {
     float lut[256];                       // (b as f32) / 255.0   (Color::from_rgba, color.rs:22-29)
     float it_f[10][NT];                   // items of the current chunk: px,py x3 | z x3 | inv
     uint32_t it_key[NT], it_rec[NT];
-    uint16_t it_rcp[NT];                  // ceil(1024 / bw): j / bw == (j * rcp) >> 10 for j < 32, bw <= 16
+    uint32_t it_rcp[NT];                  // ceil(65536 / bw): j / bw == (j * rcp) >> 16 for j < 256, bw <= 16
     uint32_t it_box[NT];                  // lx0 | ly0 << 8 | bw << 16
     uint32_t pre[NT + 1];                 // exclusive prefix of the in-tile bbox areas (work units)
-    uint8_t unit_item[CHUNK * SMALL_PX];  // work unit -> item
+    uint8_t unit_item[UNIT_CAP];          // work unit -> item
     union {
         FragPool fr;
         unsigned long long sorted[SORT_CAP];
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                 if (x0 < x1 && y0 < y1) {
                     bx0 = x0 - tileX0; by0 = y0 - tileY0; bw = x1 - x0; bh = y1 - y0;
                 }
-                big = bw * bh > SMALL_PX || (bw > 0 && !setup_is_tame(s)); // untame: literal per-pixel path
+                big = bw > 0 && !setup_is_tame(s); // NaN / inf / absurd coordinates: literal per-pixel path
             }
             if (tid == 0) {
                 S.first_big = CHUNK + 1;
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                 S.it_f[6][tid] = s.z[0]; S.it_f[7][tid] = s.z[1]; S.it_f[8][tid] = s.z[2];
                 S.it_f[9][tid] = s.inv;
                 S.it_key[tid] = key; S.it_rec[tid] = rec;
-                S.it_rcp[tid] = (uint16_t)((1024 + bw - 1) / max(bw, 1));
+                S.it_rcp[tid] = (65536u + (uint32_t)bw - 1u) / (uint32_t)max(bw, 1);
                 S.it_box[tid] = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bw << 16);
             }
             uint32_t incl = area;
@@ -428,9 +428,24 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                 const uint32_t first = wbase + incl - area; // exclusive prefix: first work unit of item <tid>
                 S.pre[tid] = first;
                 if (tid == NT - 1) S.pre[NT] = wbase + incl;
-                for (uint32_t k = 0; k < area; k++) S.unit_item[first + k] = (uint8_t)tid;
+                for (uint32_t k = 0; k < area && first + k < (uint32_t)UNIT_CAP; k++) S.unit_item[first + k] = (uint8_t)tid;
             }
             __syncthreads();
+            if (S.pre[cnt] > (uint32_t)UNIT_CAP) {
+                // more work units than the chunk can index: keep the longest prefix of items that fits
+                // (chunks must follow submission order, so an unsorted list is sorted first)
+                if (!sorted) {
+                    sort_tile_list(S, bin, n);
+                    sorted = true;
+                    continue;
+                }
+                int lo = 1, hi = cnt; // largest c with pre[c] <= UNIT_CAP (pre[1] <= 256 always fits)
+                while (hi - lo > 0) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (S.pre[mid] <= (uint32_t)UNIT_CAP) lo = mid; else hi = mid - 1;
+                }
+                cnt = lo;
+            }
 
             bool need_sort = false;
             for (;;) {
@@ -445,7 +460,7 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                         const uint32_t box = S.it_box[it];
                         const int ibw = (int)((box >> 16) & 0x1Fu);
                         const int j = u - (int)S.pre[it];
-                        const int ry = (j * (int)S.it_rcp[it]) >> 10, rx = j - ry * ibw; // j / ibw, j < 32, ibw <= 16
+                        const int ry = (int)(((uint32_t)j * S.it_rcp[it]) >> 16), rx = j - ry * ibw; // j / ibw, j < 256, ibw <= 16
                         const int lpx = (int)(box & 0xFFu) + rx, lpy = (int)((box >> 8) & 0xFFu) + ry;
                         p = (uint32_t)(lpy * TW + lpx);
                         Setup q;

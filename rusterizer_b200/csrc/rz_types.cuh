@@ -9,11 +9,11 @@ constexpr int TH = 16;              // screen tile height (pixels)
 constexpr int TILE_PX = TW * TH;    // 256 = threads per tile CTA
 constexpr int NT = 256;             // threads per CTA in every kernel
 constexpr int CHUNK = 255;          // items per triangle-parallel chunk (item id fits u8, 0xFF = none)
-constexpr int SMALL_PX = 32;        // in-tile bbox area handled by one thread (4 x 32-bit coverage words)
+constexpr int UNIT_CAP = 8192;      // (item, pixel) work units per chunk (one byte each in shared memory)
 constexpr int POOL = 1536;          // per-chunk fragment records held in shared memory
 constexpr int SORT_CAP = 4096;      // tile lists up to this length are sorted in shared memory
-constexpr int GEOM_SMALL_PX = 64;   // bbox area up to which the geometry stage rasterises exactly
-constexpr int GEOM_SMALL_DIM = 16;  //   ... and max bbox extent (so it spans at most 2x2 tiles)
+constexpr int GEOM_SMALL_DIM = 16;  // bbox extent up to which a triangle is binned directly (spans at most 2x2 tiles)
+constexpr int GEOM_THIN_PX = 64;    // bbox area up to which a thin triangle is pre-rasterised exactly
 constexpr float GEOM_THIN_AREA2 = 1.0f; // 2x screen area below which a small triangle is pre-rasterised
 constexpr int LARGE_SLAB_ROWS = 8;  // tile rows per large-triangle binning work item
 constexpr int MAX_POLY = 10;        // clipped polygon vertex budget (=> <= 8 fan triangles, 3 key bits)
