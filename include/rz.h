@@ -150,8 +150,10 @@ uint64_t rz_launch_count(rz_ctx *ctx);
  * triangle that last wrote each sample.  Each array is [height][width][4]; any may be NULL. */
 int rz_debug_capture(rz_ctx *ctx, int enable);
 int rz_debug_read(rz_ctx *ctx, float *depth, uint32_t *color, uint32_t *owner);
-/* Profiling aid (capture must be enabled): for every non-empty tile of the last frame, 4 u64 words:
- * tile id | list length << 32, start and end of its processing in GPU nanoseconds, SM id. */
+/* Profiling aid (capture must be enabled): for every non-empty tile of the last frame, 8 u64 words:
+ * [0] tile id | list length << 32, [1],[2] start and end of its processing in GPU nanoseconds,
+ * [3] SM id, [4] four 16-bit phase stamps of the first chunk (A0,A1,A2,B done; units of 16 ns
+ * after start), [5] ns after start when phase C of the first chunk was done. */
 int rz_debug_tile_times(rz_ctx *ctx, uint64_t *out, uint32_t max_tiles, uint32_t *n_written);
 /* Vertex stage only (render.rs:104-108): clip-space positions f32[nv][4] of a mesh under the
  * current uniform block. */

@@ -408,7 +408,8 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     }
     if (total_tris > 0x1FFFFFFFull) return fail(c, RZ_E_INVALID, "frame has more than 2^29 triangles");
     {
-        uint32_t want_rec = std::max<uint64_t>(c->rec_cap, total_tris + 1024);
+        // records are allocated from REC_STRIPES arenas filled round-robin by CTA: leave 25 % headroom
+        uint32_t want_rec = std::max<uint64_t>(c->rec_cap, (total_tris * 5 / 4 + 256 * REC_STRIPES + REC_STRIPES - 1) / REC_STRIPES * REC_STRIPES);
         uint32_t want_bin = std::max<uint32_t>(c->bin_cap, 256u);
         uint32_t want_large = std::max<uint32_t>(c->large_cap, 1u << 16);
         uint32_t want_attr = std::max<uint32_t>(c->attr_cap, 1u << 14);
@@ -453,7 +454,7 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     c->launches++;
     if (timed) CU(c, cudaEventRecord(c->ev[2], st));
     const uint32_t n_tiles = P.tiles_x * (P.ty_end - P.ty_begin);
-    const dim3 tile_grid(std::min<uint32_t>(n_tiles, (uint32_t)c->num_sms * 3u)); // persistent CTAs, 3 per SM
+    const dim3 tile_grid(std::min<uint32_t>(n_tiles, (uint32_t)c->num_sms * (c->debug ? 3u : 4u))); // persistent CTAs, 4 per SM
     if (n_tiles) {
         if (c->debug)
             tile_kernel<true><<<tile_grid, NT, sizeof(TileSmemT<true>), st>>>(P);
@@ -511,7 +512,11 @@ int rz_framebuffer(rz_ctx *c, uint32_t *out_host, const uint32_t **out_device) {
         CU(c, cudaMemcpyAsync(dfs->counters, c->d_cnt_backup, sizeof(unsigned long long) * 16 * CNT_STRIPES, cudaMemcpyDeviceToDevice, st));
         uint32_t want_rec = c->rec_cap, want_bin = c->bin_cap, want_large = c->large_cap, want_attr = c->attr_cap;
         if (flags & ERR_ATTR_OVF) want_attr = std::max<uint64_t>((uint64_t)c->h_state->n_clip_attr * 5 / 4 + 1024, (uint64_t)c->attr_cap * 2);
-        if (flags & ERR_REC_OVF) want_rec = std::max<uint64_t>((uint64_t)c->h_state->n_records * 5 / 4 + 1024, (uint64_t)c->rec_cap * 2);
+        if (flags & ERR_REC_OVF) {
+            uint32_t mx = 0; // the fullest stripe decides (cursors keep counting past the capacity)
+            for (int i = 0; i < REC_STRIPES; i++) mx = std::max(mx, c->h_state->rec_cursor[i]);
+            want_rec = std::max<uint64_t>(((uint64_t)mx * 5 / 4 + 64) * REC_STRIPES, (uint64_t)c->rec_cap * 3 / 2);
+        }
         if (flags & ERR_LARGE_OVF) want_large = std::max<uint64_t>((uint64_t)c->h_state->n_large * 5 / 4 + 1024, (uint64_t)c->large_cap * 2);
         if (flags & ERR_BIN_OVF) {
             std::vector<uint32_t> counts((size_t)c->tiles_x * c->tiles_y);
@@ -620,8 +625,8 @@ int rz_debug_capture(rz_ctx *c, int enable) {
         CU(c, cudaMalloc(&c->d_dbg_depth, n * 4));
         CU(c, cudaMalloc(&c->d_dbg_color, n * 4));
         CU(c, cudaMalloc(&c->d_dbg_owner, n * 4));
-        CU(c, cudaMalloc(&c->d_dbg_time, (size_t)c->tiles_x * c->tiles_y * 32));
-        CU(c, cudaMemset(c->d_dbg_time, 0, (size_t)c->tiles_x * c->tiles_y * 32));
+        CU(c, cudaMalloc(&c->d_dbg_time, (size_t)c->tiles_x * c->tiles_y * 64));
+        CU(c, cudaMemset(c->d_dbg_time, 0, (size_t)c->tiles_x * c->tiles_y * 64));
     }
     c->debug = enable != 0;
     return RZ_OK;
@@ -645,7 +650,7 @@ int rz_debug_tile_times(rz_ctx *c, uint64_t *out, uint32_t max_tiles, uint32_t *
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->stream));
     const uint32_t n = std::min<uint32_t>(max_tiles, c->tiles_x * c->tiles_y);
-    CU(c, cudaMemcpy(out, c->d_dbg_time, (size_t)n * 32, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(out, c->d_dbg_time, (size_t)n * 64, cudaMemcpyDeviceToHost));
     *n_written = n;
     return RZ_OK;
 }

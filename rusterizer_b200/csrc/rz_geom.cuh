@@ -29,9 +29,19 @@ __device__ __forceinline__ uint32_t alloc_slot(uint32_t *cursor) {
     return base + __popc(m & lanemask_lt());
 }
 
+// Append (key, rec) to a tile's bin.  Neighbouring triangles land in the same tile, so the lanes
+// that are converged here are first grouped by tile (match.any): one atomic per group reserves the
+// slots, instead of up to 32 same-address atomics serialising in L2.
 __device__ __forceinline__ void push_bin(const FrameParams &P, uint32_t tile, uint32_t key, uint32_t rec) {
-    uint32_t slot = atomicAdd(&P.tile_count[tile], 1u);
-    if (slot == 0u) P.busy[atomicAdd(&P.fs->n_busy, 1u)] = tile; // first triangle of this tile
+    const unsigned peers = __match_any_sync(__activemask(), tile);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if ((int)(threadIdx.x & 31) == leader) {
+        base = atomicAdd(&P.tile_count[tile], (uint32_t)__popc(peers));
+        if (base == 0u) P.busy[atomicAdd(&P.fs->n_busy, 1u)] = tile; // first triangle(s) of this tile
+    }
+    base = __shfl_sync(peers, base, leader);
+    const uint32_t slot = base + __popc(peers & lanemask_lt());
     if (slot < P.bin_cap)
         P.bins[(size_t)tile * P.bin_cap + slot] = ((unsigned long long)key << 32) | rec;
     else
@@ -106,12 +116,19 @@ __device__ __forceinline__ void emit_setup(const FrameParams &P, const DrawParam
         }
     }
 
-    const uint32_t rec = alloc_slot(&P.fs->n_records);
-    if (rec >= P.rec_cap) {
+    const uint32_t stripe = blockIdx.x % REC_STRIPES, stripe_cap = P.rec_cap / REC_STRIPES;
+    const uint32_t local = alloc_slot(&P.fs->rec_cursor[stripe]);
+    if (local >= stripe_cap) {
         atomicOr(&P.fs->err, ERR_REC_OVF);
         return;
     }
+    const uint32_t rec = stripe * stripe_cap + local;
     uint32_t clip_attr = 0;
+    if (!ca) { // the fragment shader will gather these from the mesh: pull them into L2 now (fire and forget)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(D.attr + 6 * (size_t)i0));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(D.attr + 6 * (size_t)i1));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(D.attr + 6 * (size_t)i2));
+    }
     if (ca) {
         clip_attr = alloc_slot(&P.fs->n_clip_attr);
         if (clip_attr >= P.attr_cap) {

@@ -58,26 +58,47 @@ __device__ __forceinline__ void read_texel(const TexInfo &t, const float *lut, u
     rgba[3] = lut[b3];
 }
 
-// Texture::sample (texture.rs:65-83) + Color::to_argb
+// Texture::sample (texture.rs:65-83) + Color::to_argb.  ALPHA = false skips the alpha channel: it only
+// lands in bits 24..31 of the packed colour (channels bleed upwards, never downwards, color.rs:15-20)
+// and the resolve forces those bits to 0xFF (buffers.rs:121-124), so the image is identical; the
+// parity instrumentation keeps it to compare the per-sample colours bit for bit.
+template <bool ALPHA>
 __device__ __forceinline__ uint32_t sample_texture_argb(const TexInfo &t, const float *lut, float u, float v,
                                                         uint32_t &oob) {
     const float x = fmul(u, (float)(t.w - 1)), y = fmul(v, (float)(t.h - 1));
     const uint32_t x0 = sat_u32(floorf(x)), x1 = sat_u32(ceilf(x));
     const uint32_t y0 = sat_u32(floorf(y)), y1 = sat_u32(ceilf(y));
-    float tl[4], tr[4], bl[4], br[4];
-    read_texel(t, lut, x0, y0, tl, oob);
-    read_texel(t, lut, x1, y0, tr, oob);
-    read_texel(t, lut, x0, y1, bl, oob);
-    read_texel(t, lut, x1, y1, br, oob);
     const float xf = fsub(x, truncf(x)), yf = fsub(y, truncf(y)); // f32::fract
     const float omx = fsub(1.0f, xf), omy = fsub(1.0f, yf);
+    float tl[4], tr[4], bl[4], br[4];
+    const unsigned long long rs = (unsigned long long)t.tw * t.w; // bytes per texel row
+    const unsigned long long r0 = (unsigned long long)y0 * rs, r1 = (unsigned long long)y1 * rs;
+    const unsigned long long c0 = (unsigned long long)x0 * t.tw, c1 = (unsigned long long)x1 * t.tw;
+    if (t.tw == 4 && r1 + c1 + 3 < t.len && r1 + c0 + 3 < t.len && r0 + c1 + 3 < t.len) {
+        // common case: RGBA8, all four texels inside the buffer -> four 32-bit loads
+        const uint32_t v00 = __ldg(reinterpret_cast<const uint32_t *>(t.data + r0 + c0));
+        const uint32_t v10 = __ldg(reinterpret_cast<const uint32_t *>(t.data + r0 + c1));
+        const uint32_t v01 = __ldg(reinterpret_cast<const uint32_t *>(t.data + r1 + c0));
+        const uint32_t v11 = __ldg(reinterpret_cast<const uint32_t *>(t.data + r1 + c1));
+#pragma unroll
+        for (int k = 0; k < (ALPHA ? 4 : 3); k++) {
+            tl[k] = lut[(v00 >> (8 * k)) & 0xFFu]; tr[k] = lut[(v10 >> (8 * k)) & 0xFFu];
+            bl[k] = lut[(v01 >> (8 * k)) & 0xFFu]; br[k] = lut[(v11 >> (8 * k)) & 0xFFu];
+        }
+    } else {
+        read_texel(t, lut, x0, y0, tl, oob);
+        read_texel(t, lut, x1, y0, tr, oob);
+        read_texel(t, lut, x0, y1, bl, oob);
+        read_texel(t, lut, x1, y1, br, oob);
+    }
     float o[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const float r0 = fadd(fmul(tl[k], omx), fmul(tr[k], xf));
-        const float r1 = fadd(fmul(bl[k], omx), fmul(br[k], xf));
-        o[k] = fadd(fmul(r0, omy), fmul(r1, yf));
+    for (int k = 0; k < (ALPHA ? 4 : 3); k++) {
+        const float q0 = fadd(fmul(tl[k], omx), fmul(tr[k], xf));
+        const float q1 = fadd(fmul(bl[k], omx), fmul(br[k], xf));
+        o[k] = fadd(fmul(q0, omy), fmul(q1, yf));
     }
+    if (!ALPHA) return 0xFF000000u | to_argb(o[0], o[1], o[2], 0.0f);
     return to_argb(o[0], o[1], o[2], o[3]);
 }
 
@@ -86,6 +107,7 @@ __device__ __forceinline__ uint32_t sample_texture_argb(const TexInfo &t, const 
 // sampled depth of sample 0 (0.0 when uncovered), as FragCoords.depths[0] (mod.rs:458-463).
 // `s` needs the screen points and edge normals only; depths_camera_space, the shader id and the
 // attribute locations come from the triangle's ShadeRec.
+template <bool ALPHA>
 __device__ __forceinline__ uint32_t shade(const FrameParams &P, const Setup &s, uint32_t rec, const float *lut, int X,
                                           int Y, uint32_t mpost, float depth0, uint32_t &oob) {
     const float4 *sr = reinterpret_cast<const float4 *>(&P.shade[rec]);
@@ -123,7 +145,7 @@ __device__ __forceinline__ uint32_t shade(const FrameParams &P, const Setup &s, 
     if (fs == 1u) return to_argb(RZ_INTERP(0), RZ_INTERP(1), RZ_INTERP(2), RZ_INTERP(3));
     const float tu = RZ_INTERP(4), tv = RZ_INTERP(5);
 #undef RZ_INTERP
-    return sample_texture_argb(P.tex0, lut, tu, tv, oob);
+    return sample_texture_argb<ALPHA>(P.tex0, lut, tu, tv, oob);
 }
 
 // Bitonic network in its "flip then halve" form: every compare-exchange puts the smaller key at
@@ -210,7 +232,7 @@ __device__ __forceinline__ void sort_tile_list(SM &S, unsigned long long *bin, i
 }
 
 template <bool DBG>
-__global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
+__global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef TileSmemT<DBG> SM;
     SM &S = *reinterpret_cast<SM *>(smem_raw);
@@ -271,7 +293,9 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
     const int tileX0 = tx * TW, tileY0 = ty * TH;
     const int X = tileX0 + lx, Y = tileY0 + ly;
     const int n = (int)min(P.tile_count[tile], P.bin_cap);
-    unsigned long long t_start = 0;
+    unsigned long long t_start = 0, t_ph[5] = {0, 0, 0, 0, 0};
+#define RZ_STAMP(k)                                                                                  \
+    if (DBG && P.dbg_tile_time && tid == 0 && t_ph[k] == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[k]));
     if (DBG && P.dbg_tile_time && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
 
     // clear (the state resolve_and_clear leaves behind, rasterizer/mod.rs:497-506)
@@ -375,7 +399,7 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                     if (!mp) continue;
                     c_shaded++;
                     c_samples += __popc(mp);
-                    const uint32_t argb = shade(P, q, B[it].rec, S.lut, X, Y, mp, zs[0], c_oob);
+                    const uint32_t argb = shade<true>(P, q, B[it].rec, S.lut, X, Y, mp, zs[0], c_oob);
 #pragma unroll
                     for (int k = 0; k < 4; k++)
                         if ((mp >> k) & 1u) {
@@ -447,6 +471,7 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                 cnt = lo;
             }
 
+            RZ_STAMP(0) // A0 done (list + records loaded, item table + scan)
             bool need_sort = false;
             for (;;) {
                 // ---- phase A1: thread = (item, bbox pixel) work unit, consecutive lanes = consecutive units ----
@@ -513,6 +538,7 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                 sorted = true;
                 continue;
             }
+            RZ_STAMP(1) // A1 done
             const int nfrag = (int)S.nfrag;
             // ---- phase A2: thread = fragment; the covered samples' depths (mod.rs:226-245) ----
             for (int f = tid; f < nfrag; f += NT) {
@@ -533,6 +559,7 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                 S.u.fr.z[f] = z;
             }
             __syncthreads();
+            RZ_STAMP(2) // A2 done
             // ---- phase B: thread = fragment; what would the ordered replay have done with it? ----
             for (int f = tid; f < nfrag; f += NT) {
                 const uint32_t meta = S.u.fr.meta[f];
@@ -564,6 +591,7 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                 }
             }
             __syncthreads();
+            RZ_STAMP(3) // B done
             // ---- phase C: thread = fragment; shade what is still visible and write its samples ----
             for (int f = tid; f < nfrag; f += NT) {
                 const uint32_t fin = S.u.fr.fin[f];
@@ -578,7 +606,7 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                 q.py[1] = S.it_f[3][it]; q.px[2] = S.it_f[4][it]; q.py[2] = S.it_f[5][it];
                 setup_normals(q);
                 const float4 z = S.u.fr.z[f];
-                const uint32_t argb = shade(P, q, S.it_rec[it], S.lut, tileX0 + (int)(p % TW), tileY0 + (int)(p / TW),
+                const uint32_t argb = shade<DBG>(P, q, S.it_rec[it], S.lut, tileX0 + (int)(p % TW), tileY0 + (int)(p / TW),
                                             fin & 0xFu, z.x, c_oob);
                 const float zz[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
@@ -590,6 +618,7 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
                     }
             }
             __syncthreads();
+            RZ_STAMP(4) // C done
             pos += cnt;
         }
     }
@@ -625,9 +654,17 @@ __global__ void __launch_bounds__(NT, 3) tile_kernel(FrameParams P) {
         uint32_t smid;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        unsigned long long *o = P.dbg_tile_time + 4 * (size_t)work;
+        unsigned long long *o = P.dbg_tile_time + 8 * (size_t)work;
         o[0] = (unsigned long long)tile | ((unsigned long long)n << 32);
         o[1] = t_start; o[2] = t_end; o[3] = smid;
+        unsigned long long pk = 0; // first-chunk phase stamps: 16-bit deltas in units of 16 ns
+        for (int k = 0; k < 4; k++) {
+            unsigned long long d = t_ph[k] > t_start ? (t_ph[k] - t_start) >> 4 : 0;
+            pk |= (d > 0xFFFFull ? 0xFFFFull : d) << (16 * k);
+        }
+        o[4] = pk;
+        o[5] = t_ph[4] > t_start ? t_ph[4] - t_start : 0;
+        o[6] = 0; o[7] = 0;
     }
     } // persistent tile loop
 

@@ -9,9 +9,9 @@ constexpr int TH = 16;              // screen tile height (pixels)
 constexpr int TILE_PX = TW * TH;    // 256 = threads per tile CTA
 constexpr int NT = 256;             // threads per CTA in every kernel
 constexpr int CHUNK = 255;          // items per triangle-parallel chunk (item id fits u8, 0xFF = none)
-constexpr int UNIT_CAP = 8192;      // (item, pixel) work units per chunk (one byte each in shared memory)
-constexpr int POOL = 1536;          // per-chunk fragment records held in shared memory
-constexpr int SORT_CAP = 4096;      // tile lists up to this length are sorted in shared memory
+constexpr int UNIT_CAP = 6144;      // (item, pixel) work units per chunk (one byte each in shared memory)
+constexpr int POOL = 1024;          // per-chunk fragment records held in shared memory
+constexpr int SORT_CAP = 2048;      // tile lists up to this length are sorted in shared memory
 constexpr int GEOM_SMALL_DIM = 16;  // bbox extent up to which a triangle is binned directly (spans at most 2x2 tiles)
 constexpr int GEOM_THIN_PX = 64;    // bbox area up to which a thin triangle is pre-rasterised exactly
 constexpr float GEOM_THIN_AREA2 = 1.0f; // 2x screen area below which a small triangle is pre-rasterised
@@ -40,18 +40,21 @@ enum {
 // Device-side frame bookkeeping.  `counters` and `err` persist across frames (read by rz_counters /
 // rz_sync); everything from `n_records` on, and tile_count[] which follows in the same allocation,
 // is zeroed by one memset at the start of every frame.
+constexpr int REC_STRIPES = 64; // record slots are handed out from per-stripe cursors (CTA id % stripes):
+                                // one hot cursor would serialise ~10^4 same-address atomics in L2
 constexpr int CNT_STRIPES = 32; // counters are striped over CTAs to spread the global atomics
 struct FrameState {
     unsigned long long counters[CNT_STRIPES][16];
     uint32_t err;         // sticky ERR_* flags
     uint32_t pad0[3];
-    uint32_t n_records;   // emitted (post-clip, post-cull) triangles       <- per-frame part starts here
+    uint32_t n_records;   // (unused; kept for layout)                      <- per-frame part starts here
     uint32_t n_large;     // large-triangle binning work items
     uint32_t n_clip_attr; // AttrRec slots handed out to clipped triangles
     uint32_t large_next;  // work-stealing cursor of the large binning kernel
     uint32_t n_busy;      // tiles that received at least one triangle (entries of FrameParams::busy)
     uint32_t tile_cursor; // work-stealing cursor of the tile kernel
     uint32_t pad1[2];
+    uint32_t rec_cursor[REC_STRIPES]; // emitted (post-clip, post-cull) triangles per stripe
 };
 
 // Raster record: what coverage + depth need to re-create RasterizerTriangle (rasterizer/mod.rs:178-184):

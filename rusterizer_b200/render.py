@@ -310,9 +310,9 @@ class Renderer:
         return d, c, o
 
     def tile_times(self) -> np.ndarray:
-        """(n_tiles, 4) u64: tile id | n << 32, start ns, end ns, SM id (zeros for unused rows)."""
+        """(n_tiles, 8) u64 rows, see rz_debug_tile_times in include/rz.h (zeros for unused rows)."""
         n = ((self.width + 15) // 16) * ((self.height + 15) // 16)
-        out = np.zeros((n, 4), np.uint64)
+        out = np.zeros((n, 8), np.uint64)
         got = C.c_uint32()
         self._check(self._L.rz_debug_tile_times(self._ctx, out.ctypes.data, n, C.byref(got)))
         return out[: got.value]

@@ -18,6 +18,12 @@ for k in o: print("  tile", int(t[k,0] & np.uint64(0xffffffff)), "n", n[k], "dur
 for lo,hi in [(1,32),(32,64),(64,128),(128,256),(256,512),(512,4096)]:
     m = (n>=lo)&(n<hi)
     if m.any(): print(f"n in [{lo},{hi}): tiles {m.sum():5d} mean dur {dur[m].mean():6.1f} us  total {dur[m].sum()/1e3:7.2f} ms")
+ph = np.stack([((t[:,4] >> np.uint64(16*k)) & np.uint64(0xFFFF)).astype(float)*16/1e3 for k in range(4)] + [t[:,5].astype(float)/1e3], 1)
+m = (n >= 64) & (n < 128)
+names = ["A0 done", "A1 done", "A2 done", "B done", "C done"]
+print("first-chunk phase completion (us after tile start), tiles with 64<=n<128:")
+for k in range(5): print(f"   {names[k]:8s} mean {ph[m,k].mean():6.2f}  p50 {np.percentile(ph[m,k],50):6.2f}")
+print("   tile end  mean %6.2f" % dur[m].mean())
 print("sum of durations ms", dur.sum()/1e3, " / (444 slots) = us", dur.sum()/444)
 # per SM busy time
 sm = t[:,3].astype(int)
