@@ -123,7 +123,7 @@ static void mat4_mul(const float *A, const float *B, float *R) {
 
 // FrameState, then tile_count[tiles] (zeroed every frame), then busy[tiles] (not zeroed)
 static size_t zeroed_state_bytes(const rz_ctx *c) { return sizeof(FrameState) + sizeof(uint32_t) * (size_t)c->tiles_x * c->tiles_y; }
-static size_t state_bytes(const rz_ctx *c) { return zeroed_state_bytes(c) + sizeof(uint32_t) * (size_t)c->tiles_x * c->tiles_y; }
+static size_t state_bytes(const rz_ctx *c) { return zeroed_state_bytes(c) + sizeof(uint32_t) * ORDER_BUCKETS * (size_t)c->tiles_x * c->tiles_y; }
 
 static int free_frame_buffers(rz_ctx *c) {
     cudaFree(c->d_bins); c->d_bins = nullptr;
@@ -452,8 +452,12 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     if (timed) CU(c, cudaEventRecord(c->ev[1], st));
     large_bin_kernel<<<c->num_sms * 2, NT, 0, st>>>(P);
     c->launches++;
-    if (timed) CU(c, cudaEventRecord(c->ev[2], st));
     const uint32_t n_tiles = P.tiles_x * (P.ty_end - P.ty_begin);
+    if (n_tiles) {
+        order_kernel<<<(n_tiles + NT - 1) / NT, NT, 0, st>>>(P);
+        c->launches++;
+    }
+    if (timed) CU(c, cudaEventRecord(c->ev[2], st));
     const dim3 tile_grid(std::min<uint32_t>(n_tiles, (uint32_t)c->num_sms * (c->debug ? 3u : 4u))); // persistent CTAs, 4 per SM
     if (n_tiles) {
         if (c->debug)

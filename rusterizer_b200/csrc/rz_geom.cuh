@@ -38,7 +38,6 @@ __device__ __forceinline__ void push_bin(const FrameParams &P, uint32_t tile, ui
     uint32_t base = 0;
     if ((int)(threadIdx.x & 31) == leader) {
         base = atomicAdd(&P.tile_count[tile], (uint32_t)__popc(peers));
-        if (base == 0u) P.busy[atomicAdd(&P.fs->n_busy, 1u)] = tile; // first triangle(s) of this tile
     }
     base = __shfl_sync(peers, base, leader);
     const uint32_t slot = base + __popc(peers & lanemask_lt());
@@ -401,6 +400,28 @@ __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
             if (keep) push_bin(P, ty * P.tiles_x + tx, key, li.rec);
         }
     }
+}
+
+// Work order of the tile stage: tiles are handed out longest-list-first (LPT scheduling), so the few
+// tiles with hundreds of triangles start early instead of forming the tail of the frame.  One thread
+// per tile of the shard files its tile under a list-length class.
+__device__ __forceinline__ uint32_t order_class(uint32_t n) {
+    return n >= 512u ? 0u : n >= 384u ? 1u : n >= 256u ? 2u : n >= 192u ? 3u : n >= 128u ? 4u : n >= 96u ? 5u : n >= 48u ? 6u : 7u;
+}
+__global__ void __launch_bounds__(NT) order_kernel(FrameParams P) {
+    const uint32_t shard_tiles = P.tiles_x * (P.ty_end - P.ty_begin);
+    const uint32_t i = blockIdx.x * NT + threadIdx.x;
+    if (i >= shard_tiles) return;
+    const uint32_t tile = P.ty_begin * P.tiles_x + i;
+    const uint32_t n = P.tile_count[tile];
+    if (n == 0u) return;
+    const uint32_t b = order_class(n);
+    const unsigned peers = __match_any_sync(__activemask(), b);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&P.fs->bucket_n[b], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    P.busy[(size_t)b * P.tiles_x * P.tiles_y + base + __popc(peers & lanemask_lt())] = tile;
 }
 
 } // namespace rz

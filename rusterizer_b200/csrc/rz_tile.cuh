@@ -281,14 +281,33 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
 
     // ---- phase 1: persistent loop over the tiles that received triangles (dynamic work stealing) ----
     S.lut[tid] = fdiv((float)tid, 255.0f);
-    const uint32_t n_busy = P.fs->n_busy;
+    uint32_t bucket_end[ORDER_BUCKETS]; // prefix of the class sizes: work item w belongs to the first class with w < end
+    {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int b = 0; b < ORDER_BUCKETS; b++) {
+            acc += P.fs->bucket_n[b];
+            bucket_end[b] = acc;
+        }
+    }
+    const uint32_t n_busy = bucket_end[ORDER_BUCKETS - 1];
     for (;;) {
     __syncthreads(); // previous tile fully retired (also covers S.lut on the first trip)
     if (tid == 0) S.cur_tile = atomicAdd(&P.fs->tile_cursor, 1u);
     __syncthreads();
     const uint32_t work = S.cur_tile;
     if (work >= n_busy) break;
-    const uint32_t tile = P.busy[work];
+    uint32_t tile;
+    {
+        uint32_t b = 0, start = 0;
+#pragma unroll
+        for (int k = 0; k < ORDER_BUCKETS - 1; k++)
+            if (work >= bucket_end[k]) {
+                b = k + 1;
+                start = bucket_end[k];
+            }
+        tile = P.busy[(size_t)b * P.tiles_x * P.tiles_y + (work - start)];
+    }
     const uint32_t tx = tile % P.tiles_x, ty = tile / P.tiles_x;
     const int tileX0 = tx * TW, tileY0 = ty * TH;
     const int X = tileX0 + lx, Y = tileY0 + ly;

@@ -40,6 +40,7 @@ enum {
 // Device-side frame bookkeeping.  `counters` and `err` persist across frames (read by rz_counters /
 // rz_sync); everything from `n_records` on, and tile_count[] which follows in the same allocation,
 // is zeroed by one memset at the start of every frame.
+constexpr int ORDER_BUCKETS = 8; // busy tiles are handed out longest-list-first in 8 classes
 constexpr int REC_STRIPES = 64; // record slots are handed out from per-stripe cursors (CTA id % stripes):
                                 // one hot cursor would serialise ~10^4 same-address atomics in L2
 constexpr int CNT_STRIPES = 32; // counters are striped over CTAs to spread the global atomics
@@ -51,10 +52,11 @@ struct FrameState {
     uint32_t n_large;     // large-triangle binning work items
     uint32_t n_clip_attr; // AttrRec slots handed out to clipped triangles
     uint32_t large_next;  // work-stealing cursor of the large binning kernel
-    uint32_t n_busy;      // tiles that received at least one triangle (entries of FrameParams::busy)
+    uint32_t n_busy;      // (unused; kept for layout)
     uint32_t tile_cursor; // work-stealing cursor of the tile kernel
     uint32_t pad1[2];
     uint32_t rec_cursor[REC_STRIPES]; // emitted (post-clip, post-cull) triangles per stripe
+    uint32_t bucket_n[ORDER_BUCKETS]; // non-empty tiles per list-length class (class 0 = longest lists)
 };
 
 // Raster record: what coverage + depth need to re-create RasterizerTriangle (rasterizer/mod.rs:178-184):
@@ -108,7 +110,7 @@ struct FrameParams {
     uint32_t rec_cap, bin_cap, large_cap;
     FrameState *fs;
     uint32_t *tile_count;        // [tiles_x * tiles_y]
-    uint32_t *busy;              // [tiles_x * tiles_y] ids of the non-empty tiles, in no particular order
+    uint32_t *busy;              // [ORDER_BUCKETS][tiles_x * tiles_y] ids of the non-empty tiles per class
     unsigned long long *bins;    // [tiles][bin_cap]  (key << 32 | rec)
     RasterRec *recs;
     ShadeRec *shade;
