@@ -218,6 +218,11 @@ __global__ void __launch_bounds__(NT) geom_kernel(FrameParams P, DrawParams D) {
     lc.bbox = 0ull;
 
     const uint32_t t = blockIdx.x * NT + threadIdx.x;
+    {   // CTAs are dispatched roughly in order: pull the indices of the CTA that will run in this slot
+        // ~one wave from now into L2, so its first load is an L2 hit instead of a DRAM round trip
+        const size_t ahead = (size_t)t + (size_t)GEOM_PREFETCH_CTAS * NT;
+        if (ahead < D.nt && (threadIdx.x & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(D.idx + 3 * ahead));
+    }
     if (t < D.nt) {
         const uint32_t i0 = __ldg(&D.idx[3 * (size_t)t]), i1 = __ldg(&D.idx[3 * (size_t)t + 1]),
                        i2 = __ldg(&D.idx[3 * (size_t)t + 2]);

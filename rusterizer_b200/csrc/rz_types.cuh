@@ -15,6 +15,7 @@ constexpr int SORT_CAP = 2048;      // tile lists up to this length are sorted i
 constexpr int GEOM_SMALL_DIM = 16;  // bbox extent up to which a triangle is binned directly (spans at most 2x2 tiles)
 constexpr int GEOM_THIN_PX = 64;    // bbox area up to which a thin triangle is pre-rasterised exactly
 constexpr float GEOM_THIN_AREA2 = 1.0f; // 2x screen area below which a small triangle is pre-rasterised
+constexpr int GEOM_PREFETCH_CTAS = 592; // index prefetch distance of the geometry stage (~ one wave of CTAs)
 constexpr int LARGE_SLAB_ROWS = 8;  // tile rows per large-triangle binning work item
 constexpr int MAX_POLY = 10;        // clipped polygon vertex budget (=> <= 8 fan triangles, 3 key bits)
 
