@@ -15,9 +15,11 @@
 // shading position (rasterizer/mod.rs:70-83) and feeds the counters; only fragments with v(F) != 0
 // are shaded, and they write colour + depth of exactly the samples in v(F).  Nothing in a chunk
 // depends on the order in which threads run, so a tile whose list fits one chunk is never sorted.
-//   phase A  thread = item     exact coverage over its bbox; sample depths -> fragment records
-//   phase B  thread = fragment m(F), v(F) from the pixel's list
-//   phase C  thread = fragment interpolate + fragment shader + pack; write samples
+//   phase A0 thread = item          record load, setup, bbox, scan of the bbox areas
+//   phase A1 thread = (item, pixel) exact coverage -> fragment records on per-pixel lists
+//   phase A2 thread = fragment      sample depths
+//   phase B  thread = pixel         m(F), v(F): the pixel's few fragments replayed in key order
+//   phase C  thread = fragment      interpolate + fragment shader + pack; write the visible samples
 // Tiles that need several chunks sort their list by order key first.  Items with non-finite or absurd
 // coordinates take a literal pixel-parallel walk (a thread owns a pixel for the whole run, so it
 // applies the triangles in order by construction) that evaluates EdgeFunctions::inside verbatim.
@@ -579,34 +581,48 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
             }
             __syncthreads();
             RZ_STAMP(2) // A2 done
-            // ---- phase B: thread = fragment; what would the ordered replay have done with it? ----
-            for (int f = tid; f < nfrag; f += NT) {
-                const uint32_t meta = S.u.fr.meta[f];
-                const uint32_t p = (meta >> 8) & 0xFFu, m = (meta >> 16) & 0xFu;
-                const uint32_t mykey = S.it_key[meta & 0xFFu];
-                const float4 z = S.u.fr.z[f];
-                const float4 dold = *reinterpret_cast<const float4 *>(&S.depth[p * 4]);
-                uint32_t mp = m & ((z.x < dold.x ? 1u : 0u) | (z.y < dold.y ? 2u : 0u) | (z.z < dold.z ? 4u : 0u) |
-                                   (z.w < dold.w ? 8u : 0u));
-                uint32_t blocked = 0, lost = 0;
-                for (uint32_t g = S.head[p]; g != FR_NONE; g = S.u.fr.next[g]) {
-                    if ((int)g == f) continue;
-                    const uint32_t mg = S.u.fr.meta[g];
-                    const uint32_t cg = (mg >> 16) & 0xFu;
-                    const float4 zg = S.u.fr.z[g];
-                    if (S.it_key[mg & 0xFFu] < mykey) { // drawn before F: it blocks where z_G <= z_F
-                        blocked |= cg & ((zg.x <= z.x ? 1u : 0u) | (zg.y <= z.y ? 2u : 0u) | (zg.z <= z.z ? 4u : 0u) |
-                                         (zg.w <= z.w ? 8u : 0u));
-                    } else {                            // drawn after F: it overwrites where z_G < z_F
-                        lost |= cg & ((zg.x < z.x ? 1u : 0u) | (zg.y < z.y ? 2u : 0u) | (zg.z < z.z ? 4u : 0u) |
-                                      (zg.w < z.w ? 8u : 0u));
+            // ---- phase B: thread = pixel; replay this pixel's fragments in submission order ----
+            // (depth test exactly as Rasterizer::depth_coverage + write_pixel, mod.rs:363-397).  A pixel
+            // holds 2-3 fragments on average, so the next one in key order is found by re-walking its
+            // list; the last writer of every sample is the fragment that stays visible.
+            {
+                const uint32_t h = S.head[tid];
+                if (h != FR_NONE) {
+                    float4 d = *reinterpret_cast<const float4 *>(&S.depth[tid * 4]);
+                    uint32_t own0 = FR_NONE, own1 = FR_NONE, own2 = FR_NONE, own3 = FR_NONE;
+                    uint32_t last_key = 0;
+                    bool first = true;
+                    for (;;) {
+                        uint32_t best = FR_NONE, best_key = 0xFFFFFFFFu;
+                        for (uint32_t g = h; g != FR_NONE; g = S.u.fr.next[g]) {
+                            const uint32_t k = S.it_key[S.u.fr.meta[g] & 0xFFu];
+                            if ((first || k > last_key) && k < best_key) {
+                                best = g;
+                                best_key = k;
+                            }
+                        }
+                        if (best == FR_NONE) break;
+                        const uint32_t m = (S.u.fr.meta[best] >> 16) & 0xFu;
+                        const float4 z = S.u.fr.z[best];
+                        uint32_t mp = 0;
+                        if ((m & 1u) && z.x < d.x) { mp |= 1u; d.x = z.x; own0 = best; } // strict < (mod.rs:374)
+                        if ((m & 2u) && z.y < d.y) { mp |= 2u; d.y = z.y; own1 = best; }
+                        if ((m & 4u) && z.z < d.z) { mp |= 4u; d.z = z.z; own2 = best; }
+                        if ((m & 8u) && z.w < d.w) { mp |= 8u; d.w = z.w; own3 = best; }
+                        S.u.fr.fin[best] = (uint8_t)mp; // post-depth mask; the visible bits are added below
+                        if (mp) {
+                            c_shaded++;
+                            c_samples += __popc(mp);
+                        }
+                        last_key = best_key;
+                        first = false;
                     }
-                }
-                mp &= ~blocked;
-                S.u.fr.fin[f] = (uint8_t)(mp | ((mp & ~lost) << 4));
-                if (mp) {
-                    c_shaded++;
-                    c_samples += __popc(mp);
+                    if (own0 != FR_NONE) S.u.fr.fin[own0] |= 0x10u;
+                    if (own1 != FR_NONE) S.u.fr.fin[own1] |= 0x20u;
+                    if (own2 != FR_NONE) S.u.fr.fin[own2] |= 0x40u;
+                    if (own3 != FR_NONE) S.u.fr.fin[own3] |= 0x80u;
+                    *reinterpret_cast<float4 *>(&S.depth[tid * 4]) = d;
+                    S.head[tid] = FR_NONE;
                 }
             }
             __syncthreads();
@@ -616,7 +632,6 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 const uint32_t fin = S.u.fr.fin[f];
                 const uint32_t meta = S.u.fr.meta[f];
                 const uint32_t p = (meta >> 8) & 0xFFu;
-                S.head[p] = FR_NONE;
                 const uint32_t vis = fin >> 4;
                 if (!vis) continue;
                 const uint32_t it = meta & 0xFFu;
@@ -627,12 +642,10 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 const float4 z = S.u.fr.z[f];
                 const uint32_t argb = shade<DBG>(P, q, S.it_rec[it], S.lut, tileX0 + (int)(p % TW), tileY0 + (int)(p / TW),
                                             fin & 0xFu, z.x, c_oob);
-                const float zz[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
                 for (int k = 0; k < 4; k++)
                     if ((vis >> k) & 1u) {
                         S.color[p * 4 + k] = argb;
-                        S.depth[p * 4 + k] = zz[k];
                         if (DBG) S.okey[p * 4 + k] = S.it_key[it];
                     }
             }
