@@ -22,6 +22,7 @@ using namespace rz;
 
 struct rz_mesh {
     rz_ctx *ctx;
+    int device = 0; // kept here too: a mesh may be destroyed after its ctx
     float *d_pos = nullptr;
     float *d_attr = nullptr;
     uint32_t *d_idx = nullptr;
@@ -310,6 +311,7 @@ int rz_mesh_create(rz_ctx *c, const float *positions, const float *attributes, u
     rz_mesh *m = new (std::nothrow) rz_mesh();
     if (!m) return fail(c, RZ_E_NOMEM, "rz_mesh_create: out of host memory");
     m->ctx = c;
+    m->device = c->device;
     int rc = mesh_upload(c, m, positions, attributes, nv, indices, n_idx);
     if (rc == RZ_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(c, RZ_E_CUDA, "rz_mesh_create: sync failed");
     if (rc != RZ_OK) {
@@ -322,7 +324,7 @@ int rz_mesh_create(rz_ctx *c, const float *positions, const float *attributes, u
 
 void rz_mesh_destroy(rz_mesh *m) {
     if (!m) return;
-    if (m->ctx) cudaSetDevice(m->ctx->device);
+    cudaSetDevice(m->device);
     cudaFree(m->d_pos); cudaFree(m->d_attr); cudaFree(m->d_idx);
     delete m;
 }
@@ -358,6 +360,7 @@ int rz_render_host(rz_ctx *c, const float *positions, const float *attributes, u
         rz_mesh *m = new (std::nothrow) rz_mesh();
         if (!m) return fail(c, RZ_E_NOMEM, "rz_render_host: out of host memory");
         m->ctx = c;
+        m->device = c->device;
         c->staging.push_back(m);
     }
     rz_mesh *m = c->staging[c->staging_used];
@@ -431,6 +434,7 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     }
     FrameParams P = make_params(c, out_base);
     cudaStream_t st = c->stream;
+    (void)cudaGetLastError(); // do not blame this frame for a stale, non-sticky error of an earlier call
     const size_t off = offsetof(FrameState, n_records);
     CU(c, cudaMemsetAsync(c->d_state + off, 0, zeroed_state_bytes(c) - off, st));
     if (timed) CU(c, cudaEventRecord(c->ev[0], st));

@@ -722,4 +722,6 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
     }
 }
 
+static_assert(4 * (sizeof(TileSmemT<false>) + 1024) <= 227 * 1024, "tile kernel must fit 4 CTAs per SM");
+
 } // namespace rz
