@@ -85,6 +85,22 @@ struct rz_ctx {
 
 static thread_local std::string g_err;
 
+// Launch with programmatic stream serialization (PDL): see pdl_wait() in rz_exact.cuh.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static int fail(rz_ctx *ctx, int code, const char *fmt, ...) {
     char buf[512];
     va_list ap;
@@ -435,8 +451,13 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     FrameParams P = make_params(c, out_base);
     cudaStream_t st = c->stream;
     (void)cudaGetLastError(); // do not blame this frame for a stale, non-sticky error of an earlier call
-    const size_t off = offsetof(FrameState, n_records);
-    CU(c, cudaMemsetAsync(c->d_state + off, 0, zeroed_state_bytes(c) - off, st));
+    const size_t off = offsetof(FrameState, n_records); // 16-byte aligned by construction
+    {
+        const uint32_t n16 = (uint32_t)((zeroed_state_bytes(c) - off + 15) / 16);
+        CU(c, launch_pdl(frame_begin_kernel, dim3((n16 + NT - 1) / NT), dim3(NT), 0, st,
+                         reinterpret_cast<uint4 *>(c->d_state + off), n16));
+        c->launches++;
+    }
     if (timed) CU(c, cudaEventRecord(c->ev[0], st));
     uint32_t tri_base = 0, draw_index = 0;
     for (auto &d : c->draws) {
@@ -448,26 +469,26 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
         D.nv = d.mesh->nv; D.nt = nt; D.tri_base = tri_base; D.fs = d.fs; D.draw = this_draw;
         memcpy(D.M, d.M, 64);
         D.vtx = c->d_vtx;
-        vertex_kernel<<<(D.nv + NT - 1) / NT, NT, 0, st>>>(P, D);
-        geom_kernel<<<(nt + NT - 1) / NT, NT, 0, st>>>(P, D);
+        CU(c, launch_pdl(vertex_kernel, dim3((D.nv + NT - 1) / NT), dim3(NT), 0, st, P, D));
+        CU(c, launch_pdl(geom_kernel, dim3((nt + NT - 1) / NT), dim3(NT), 0, st, P, D));
         c->launches += 2;
         tri_base += nt;
     }
     if (timed) CU(c, cudaEventRecord(c->ev[1], st));
-    large_bin_kernel<<<c->num_sms * 2, NT, 0, st>>>(P);
+    CU(c, launch_pdl(large_bin_kernel, dim3(c->num_sms * 2), dim3(NT), 0, st, P));
     c->launches++;
     const uint32_t n_tiles = P.tiles_x * (P.ty_end - P.ty_begin);
     if (n_tiles) {
-        order_kernel<<<(n_tiles + NT - 1) / NT, NT, 0, st>>>(P);
+        CU(c, launch_pdl(order_kernel, dim3((n_tiles + NT - 1) / NT), dim3(NT), 0, st, P));
         c->launches++;
     }
     if (timed) CU(c, cudaEventRecord(c->ev[2], st));
     const dim3 tile_grid(std::min<uint32_t>(n_tiles, (uint32_t)c->num_sms * (c->debug ? 3u : 4u))); // persistent CTAs, 4 per SM
     if (n_tiles) {
         if (c->debug)
-            tile_kernel<true><<<tile_grid, NT, sizeof(TileSmemT<true>), st>>>(P);
+            CU(c, launch_pdl(tile_kernel<true>, tile_grid, dim3(NT), sizeof(TileSmemT<true>), st, P));
         else
-            tile_kernel<false><<<tile_grid, NT, sizeof(TileSmemT<false>), st>>>(P);
+            CU(c, launch_pdl(tile_kernel<false>, tile_grid, dim3(NT), sizeof(TileSmemT<false>), st, P));
         c->launches++;
     }
     if (timed) CU(c, cudaEventRecord(c->ev[3], st));
@@ -678,7 +699,7 @@ int rz_debug_vertex_stage(rz_ctx *c, const rz_mesh *mesh, float *out_clip) {
     mat4_mul(pv, c->world, D.M);
     D.pos = mesh->d_pos; D.nv = mesh->nv;
     D.vtx = c->d_vtx;
-    vertex_kernel<<<(mesh->nv + NT - 1) / NT, NT, 0, c->stream>>>(P, D);
+    CU(c, launch_pdl(vertex_kernel, dim3((mesh->nv + NT - 1) / NT), dim3(NT), 0, c->stream, P, D));
     c->launches++;
     std::vector<float> tmp((size_t)mesh->nv * 8);
     CU(c, cudaMemcpyAsync(tmp.data(), c->d_vtx, tmp.size() * 4, cudaMemcpyDeviceToHost, c->stream));

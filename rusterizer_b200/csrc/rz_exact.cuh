@@ -11,6 +11,14 @@
 
 namespace rz {
 
+// Programmatic dependent launch (PDL): every kernel of the frame is launched with
+// programmaticStreamSerializationAllowed, so its CTAs may become resident while the previous kernel
+// is still running; pdl_wait() blocks until that kernel has completed and its writes are visible.
+// Each kernel calls pdl_launch() + pdl_wait() before touching global memory, which keeps the stream's
+// sequential semantics and only hides the launch latency between the dependent kernels.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }

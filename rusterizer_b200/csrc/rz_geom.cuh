@@ -195,6 +195,8 @@ __device__ __forceinline__ uint32_t clip_code(const float *c) {
 // triangle using the vertex would recompute: the perspective divide + viewport transform and the
 // 12 trivial-accept/reject comparisons.
 __global__ void __launch_bounds__(NT) vertex_kernel(FrameParams P, DrawParams D) {
+    pdl_launch();
+    pdl_wait();
     const uint32_t v = blockIdx.x * NT + threadIdx.x;
     if (v >= D.nv) return;
     const float *p = D.pos + 3 * (size_t)v;
@@ -211,6 +213,8 @@ __global__ void __launch_bounds__(NT) vertex_kernel(FrameParams P, DrawParams D)
 __global__ void __launch_bounds__(NT) geom_kernel(FrameParams P, DrawParams D) {
     __shared__ uint32_t s_part[NT / 32][C_COUNT];
     __shared__ unsigned long long s_bbox[NT / 32];
+    pdl_launch();
+    pdl_wait();
 
     GeomLocal lc;
 #pragma unroll
@@ -372,6 +376,8 @@ __device__ __forceinline__ void load_setup(const RasterRec *recs, uint32_t rec, 
 // most favourable sample position of tile-cap-bbox already fails that edge -- exact because the
 // f32 edge function is monotone in x and in y.
 __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
+    pdl_launch();
+    pdl_wait();
     const uint32_t n = min(P.fs->n_large, P.large_cap);
     const int lane = threadIdx.x & 31;
     for (;;) { // one warp per (triangle, slab) item, stolen from a global cursor
@@ -414,6 +420,8 @@ __device__ __forceinline__ uint32_t order_class(uint32_t n) {
     return n >= 512u ? 0u : n >= 384u ? 1u : n >= 256u ? 2u : n >= 192u ? 3u : n >= 128u ? 4u : n >= 96u ? 5u : n >= 48u ? 6u : 7u;
 }
 __global__ void __launch_bounds__(NT) order_kernel(FrameParams P) {
+    pdl_launch();
+    pdl_wait();
     const uint32_t shard_tiles = P.tiles_x * (P.ty_end - P.ty_begin);
     const uint32_t i = blockIdx.x * NT + threadIdx.x;
     if (i >= shard_tiles) return;
@@ -427,6 +435,14 @@ __global__ void __launch_bounds__(NT) order_kernel(FrameParams P) {
     if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&P.fs->bucket_n[b], (uint32_t)__popc(peers));
     base = __shfl_sync(peers, base, leader);
     P.busy[(size_t)b * P.tiles_x * P.tiles_y + base + __popc(peers & lanemask_lt())] = tile;
+}
+
+// First kernel of a frame: zero the per-frame part of the frame state and the tile counters.
+__global__ void __launch_bounds__(NT) frame_begin_kernel(uint4 *p, uint32_t n16) {
+    pdl_launch();
+    pdl_wait();
+    const uint32_t i = blockIdx.x * NT + threadIdx.x;
+    if (i < n16) p[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 } // namespace rz

@@ -242,6 +242,8 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lx = tid % TW, ly = tid / TW;
     uint32_t c_cov = 0, c_shaded = 0, c_samples = 0, c_oob = 0;
+    pdl_launch();
+    pdl_wait();
 
     // ---- phase 0: tiles nothing was binned into.  The box filter of four clear samples is the clear
     // colour (buffers.rs:5,111-125): one warp writes such a tile as 64 128-bit stores. ----
