@@ -333,24 +333,47 @@ def main():
     pos_h = torch.from_numpy(mesh.vertices).pin_memory()
     att_h = torch.from_numpy(mesh.attributes).pin_memory()
     idx_h = torch.from_numpy(mesh.indices.view(np.int32)).pin_memory()
-    out_h = torch.empty((H, W), dtype=torch.int32).pin_memory()
-    e2e_steps = max(3, min(K, 20))
+    out_h = [torch.empty((H, W), dtype=torch.int32).pin_memory() for _ in range(2)]
+    e2e_steps = max(3, min(K, 30))
 
-    def frame_e2e(i):
+    def frame_e2e_sync(i):
         blk.view = views[i % len(views)]
         r.render_arrays(pos_h.data_ptr(), att_h.data_ptr(), mesh.n_vertices, idx_h.data_ptr(), mesh.indices.size, 0, 0)
-        r.framebuffer_into(out_h.data_ptr())  # synchronises; D2H of the resolved image
+        r.framebuffer_into(out_h[0].data_ptr())  # synchronises; D2H of the resolved image
+
+    def frame_e2e(i):
+        # the streaming form of render() + display(): every step uploads the host mesh (H2D), runs the frame
+        # and reads the image back (D2H); copies of neighbouring steps overlap the kernels (rz.h)
+        blk.view = views[i % len(views)]
+        r.render_arrays(pos_h.data_ptr(), att_h.data_ptr(), mesh.n_vertices, idx_h.data_ptr(), mesh.indices.size, 0, 0)
+        r.framebuffer_host_async(out_h[i % 2].data_ptr())
+
+    # one-step latency of the synchronous call (no overlap), for reference
+    for i in range(2):
+        frame_e2e_sync(i)
+    t0 = time.perf_counter()
+    for i in range(5):
+        frame_e2e_sync(i)
+    e2e_sync_ms = (time.perf_counter() - t0) / 5 * 1e3
+    ref_img = out_h[0].clone()  # view index 4
 
     for i in range(3):
         frame_e2e(i)
+    r.sync()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         frame_e2e(i)
+    r.sync()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # the streamed images are the ones the synchronous call returns (same view -> same bits)
+    frame_e2e(4)
+    r.sync()
+    if not torch.equal(out_h[0], ref_img):
+        raise SystemExit("bench.py: streamed e2e frame differs from the synchronous frame")
     e2 = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2, op=dist.ReduceOp.MAX)
@@ -397,6 +420,16 @@ def main():
         "note": "no dense contraction on this path (no tensor cores); DRAM throughput is < 3 % in ncu, the kernels are "
                 "bound by instruction issue and latency of the exact non-FMA f32 arithmetic (DESIGN.md section 4)",
     }
+    # secondary bound: algorithmic f32 operations of the reference algorithm (FMA is off:
+    # 1 flop/lane/clock) from the work counters, against 148 SMs x 128 lanes x the max SM clock
+    cpf = {k: v / K for k, v in cnt.items()}
+    f_alg = (28 * scene.n_vertices + 40 * cpf["n_tris_in"] + 60 * cpf["n_tris_setup"] + 72 * cpf["n_bbox_px"]
+             + 30 * cpf["n_samples_written"] + 180 * cpf["n_shaded_px"])
+    sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+    fp32_peak = 148 * 128 * sm_mhz * 1e6 / 1e12
+    roofline["fp32"] = {"algorithmic_gflop_per_frame": f_alg / 1e9, "achieved": f_alg / (ms_per_step / 1e3) / 1e12,
+                        "peak": fp32_peak, "unit": "TFLOP/s (non-FMA f32)", "frac": f_alg / (ms_per_step / 1e3) / 1e12 / fp32_peak,
+                        "formula": "28*Nv + 40*Nt_in + 60*Nt_setup + 72*N_bbox_px + 30*N_samples + 180*N_shaded_px (texture FS)"}
     cb = None
     if not args.no_cpu_baseline and not tiles_mode:
         cb = cpu_baseline(scene, budget_s=args.cpu_budget)
@@ -408,7 +441,11 @@ def main():
         "gsamples_per_s": gsamples, "ms_per_frame": ms_per_step,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": float(e2.item()) / e2e_steps * 1e3, "steps": e2e_steps},
+                "ms_per_step": float(e2.item()) / e2e_steps * 1e3, "steps": e2e_steps,
+                "sync_call_latency_ms": e2e_sync_ms,
+                "how": "rz_render_host (pinned host mesh, H2D on the upload stream) + rz_framebuffer_host_async (D2H of the "
+                       "image on the download stream) every step; copies of neighbouring steps overlap the kernels, "
+                       "wall clock over all steps incl. the final rz_sync"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cb,

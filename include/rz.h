@@ -126,6 +126,16 @@ int rz_framebuffer(rz_ctx *ctx, uint32_t *out_host, const uint32_t **out_device)
  * e.g. a slice of an NCCL gather buffer.  Errors of the frame surface at the next rz_sync. */
 int rz_framebuffer_async(rz_ctx *ctx, uint32_t *device_dst, const uint32_t **out_device);
 
+/* Streaming form of Renderer::display (render.rs:116-127) for a caller that presents every frame
+ * on the host: executes the frame like rz_framebuffer_async and copies the resolved image (this
+ * ctx's rows) to out_host (width*height u32, ideally pinned) on a separate copy stream, without host
+ * synchronisation.  Together with rz_render_host -- whose uploads run on their own stream into one
+ * of two alternating staging sets -- the H2D copy of frame i+1, the kernels of frame i and the
+ * D2H copy of frame i-1 overlap.  out_host is valid after the next rz_sync(); at most two frames
+ * are in flight per output buffer, so alternate between two host buffers.  With pinned host memory
+ * the arrays passed to rz_render_host must stay unchanged until that rz_sync(). */
+int rz_framebuffer_host_async(rz_ctx *ctx, uint32_t *out_host);
+
 /* Wait for all enqueued frames and report their sticky status (RZ_E_CAPACITY, RZ_E_INDEX ...). */
 int rz_sync(rz_ctx *ctx);
 

@@ -51,8 +51,18 @@ struct rz_ctx {
     float world[16], view[16], proj[16];
     std::vector<Texture> textures;
     std::vector<DrawCmd> draws;
-    std::vector<rz_mesh *> staging; // host-mesh draws of the current frame use staging[k]
+    // Host-mesh draws (rz_render_host) of the current frame use staging[parity][k].  The uploads run on
+    // their own stream and the two staging sets alternate per frame, so the H2D copy of frame i+1
+    // overlaps the kernels of frame i (and the D2H copy of frame i-1 on `down_stream`).
+    std::vector<rz_mesh *> staging[2];
     size_t staging_used = 0;
+    int parity = 0, out_parity = 0;
+    cudaStream_t up_stream = nullptr, down_stream = nullptr;
+    cudaEvent_t ev_uploaded = nullptr;
+    cudaEvent_t ev_consumed[2] = {nullptr, nullptr};  // the frame that read staging[p] has finished
+    cudaEvent_t ev_frame_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_d2h_done[2] = {nullptr, nullptr};  // the image in d_out_ring[p] has reached the host
+    uint32_t *d_out_ring[2] = {nullptr, nullptr};     // [0] aliases d_out
 
     // device buffers
     unsigned char *d_state = nullptr; // FrameState + tile_count[]
@@ -237,6 +247,15 @@ int rz_create(int device, uint32_t width, uint32_t height, rz_ctx **out) {
     CU_NEW(cudaMalloc(&c->d_cnt_backup, sizeof(unsigned long long) * 16 * CNT_STRIPES));
     CU_NEW(cudaHostAlloc(&c->h_state, sizeof(FrameState), cudaHostAllocDefault));
     for (int i = 0; i < 4; i++) CU_NEW(cudaEventCreate(&c->ev[i]));
+    CU_NEW(cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking));
+    CU_NEW(cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
+    CU_NEW(cudaEventCreateWithFlags(&c->ev_uploaded, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) {
+        CU_NEW(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
+        CU_NEW(cudaEventCreateWithFlags(&c->ev_frame_done[i], cudaEventDisableTiming));
+        CU_NEW(cudaEventCreateWithFlags(&c->ev_d2h_done[i], cudaEventDisableTiming));
+    }
+    c->d_out_ring[0] = c->d_out;
     CU_NEW(cudaFuncSetAttribute(tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemT<false>)));
     CU_NEW(cudaFuncSetAttribute(tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemT<true>)));
 #undef CU_NEW
@@ -248,14 +267,25 @@ void rz_destroy(rz_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->up_stream) cudaStreamSynchronize(c->up_stream);
+    if (c->down_stream) cudaStreamSynchronize(c->down_stream);
     free_frame_buffers(c);
-    cudaFree(c->d_state); cudaFree(c->d_out); cudaFree(c->d_cnt_backup);
+    cudaFree(c->d_state); cudaFree(c->d_out); cudaFree(c->d_out_ring[1]); cudaFree(c->d_cnt_backup);
     cudaFree(c->d_dbg_depth); cudaFree(c->d_dbg_color); cudaFree(c->d_dbg_owner); cudaFree(c->d_dbg_time);
     for (auto &t : c->textures) cudaFree(t.d_data);
-    for (auto *m : c->staging) rz_mesh_destroy(m);
+    for (int p = 0; p < 2; p++)
+        for (auto *m : c->staging[p]) rz_mesh_destroy(m);
     if (c->h_state) cudaFreeHost(c->h_state);
     for (int i = 0; i < 4; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->ev_uploaded) cudaEventDestroy(c->ev_uploaded);
+    for (int i = 0; i < 2; i++) {
+        if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
+        if (c->ev_frame_done[i]) cudaEventDestroy(c->ev_frame_done[i]);
+        if (c->ev_d2h_done[i]) cudaEventDestroy(c->ev_d2h_done[i]);
+    }
+    if (c->up_stream) cudaStreamDestroy(c->up_stream);
+    if (c->down_stream) cudaStreamDestroy(c->down_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -304,14 +334,14 @@ int rz_read_block(rz_ctx *c, float *world, float *view, float *projection) {
 }
 
 static int mesh_upload(rz_ctx *c, rz_mesh *m, const float *pos, const float *attr, uint32_t nv, const uint32_t *idx,
-                       uint64_t n_idx) {
+                       uint64_t n_idx, cudaStream_t st) {
     const size_t bp = (size_t)nv * 12, ba = (size_t)nv * 24, bi = (size_t)n_idx * 4;
     if (bp > m->cap_pos) { cudaFree(m->d_pos); m->d_pos = nullptr; m->cap_pos = 0; CU(c, cudaMalloc(&m->d_pos, bp)); m->cap_pos = bp; }
     if (ba > m->cap_attr) { cudaFree(m->d_attr); m->d_attr = nullptr; m->cap_attr = 0; CU(c, cudaMalloc(&m->d_attr, ba)); m->cap_attr = ba; }
     if (bi > m->cap_idx) { cudaFree(m->d_idx); m->d_idx = nullptr; m->cap_idx = 0; CU(c, cudaMalloc(&m->d_idx, bi)); m->cap_idx = bi; }
-    if (bp) CU(c, cudaMemcpyAsync(m->d_pos, pos, bp, cudaMemcpyHostToDevice, c->stream));
-    if (ba) CU(c, cudaMemcpyAsync(m->d_attr, attr, ba, cudaMemcpyHostToDevice, c->stream));
-    if (bi) CU(c, cudaMemcpyAsync(m->d_idx, idx, bi, cudaMemcpyHostToDevice, c->stream));
+    if (bp) CU(c, cudaMemcpyAsync(m->d_pos, pos, bp, cudaMemcpyHostToDevice, st));
+    if (ba) CU(c, cudaMemcpyAsync(m->d_attr, attr, ba, cudaMemcpyHostToDevice, st));
+    if (bi) CU(c, cudaMemcpyAsync(m->d_idx, idx, bi, cudaMemcpyHostToDevice, st));
     m->nv = nv;
     m->n_idx = n_idx;
     return RZ_OK;
@@ -328,7 +358,7 @@ int rz_mesh_create(rz_ctx *c, const float *positions, const float *attributes, u
     if (!m) return fail(c, RZ_E_NOMEM, "rz_mesh_create: out of host memory");
     m->ctx = c;
     m->device = c->device;
-    int rc = mesh_upload(c, m, positions, attributes, nv, indices, n_idx);
+    int rc = mesh_upload(c, m, positions, attributes, nv, indices, n_idx, c->stream);
     if (rc == RZ_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(c, RZ_E_CUDA, "rz_mesh_create: sync failed");
     if (rc != RZ_OK) {
         rz_mesh_destroy(m);
@@ -372,15 +402,18 @@ int rz_render_host(rz_ctx *c, const float *positions, const float *attributes, u
     if ((nv && (!positions || !attributes)) || (n_idx && !indices) || n_idx % 3 != 0 || n_idx / 3 > 0x1FFFFFFFull)
         return fail(c, RZ_E_INVALID, "rz_render_host: bad arguments");
     CU(c, cudaSetDevice(c->device));
-    if (c->staging_used == c->staging.size()) {
+    auto &staging = c->staging[c->parity];
+    if (c->staging_used == staging.size()) {
         rz_mesh *m = new (std::nothrow) rz_mesh();
         if (!m) return fail(c, RZ_E_NOMEM, "rz_render_host: out of host memory");
         m->ctx = c;
         m->device = c->device;
-        c->staging.push_back(m);
+        staging.push_back(m);
     }
-    rz_mesh *m = c->staging[c->staging_used];
-    int rc = mesh_upload(c, m, positions, attributes, nv, indices, n_idx);
+    // this staging set was last read two frames ago: wait (on the upload stream only) for that frame
+    if (c->staging_used == 0) CU(c, cudaStreamWaitEvent(c->up_stream, c->ev_consumed[c->parity], 0));
+    rz_mesh *m = staging[c->staging_used];
+    int rc = mesh_upload(c, m, positions, attributes, nv, indices, n_idx, c->up_stream);
     if (rc != RZ_OK) return rc;
     rc = record_draw(c, m, vs_id, fs_id);
     if (rc == RZ_OK) c->staging_used++;
@@ -451,6 +484,10 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     FrameParams P = make_params(c, out_base);
     cudaStream_t st = c->stream;
     (void)cudaGetLastError(); // do not blame this frame for a stale, non-sticky error of an earlier call
+    if (c->staging_used) { // host-mesh draws: the frame starts when their uploads have landed
+        CU(c, cudaEventRecord(c->ev_uploaded, c->up_stream));
+        CU(c, cudaStreamWaitEvent(st, c->ev_uploaded, 0));
+    }
     const size_t off = offsetof(FrameState, n_records); // 16-byte aligned by construction
     {
         const uint32_t n16 = (uint32_t)((zeroed_state_bytes(c) - off + 15) / 16);
@@ -492,12 +529,14 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
         c->launches++;
     }
     if (timed) CU(c, cudaEventRecord(c->ev[3], st));
+    if (c->staging_used) CU(c, cudaEventRecord(c->ev_consumed[c->parity], st));
     CU(c, cudaGetLastError());
     return RZ_OK;
 }
 
 static void end_frame(rz_ctx *c) {
     c->draws.clear();
+    if (c->staging_used) c->parity ^= 1;
     c->staging_used = 0;
 }
 
@@ -592,6 +631,27 @@ int rz_framebuffer_async(rz_ctx *c, uint32_t *device_dst, const uint32_t **out_d
     return RZ_OK;
 }
 
+int rz_framebuffer_host_async(rz_ctx *c, uint32_t *out_host) {
+    if (!c || !out_host) return RZ_E_INVALID;
+    if (c->sticky != RZ_OK) return c->sticky;
+    CU(c, cudaSetDevice(c->device));
+    const int p = c->out_parity;
+    if (!c->d_out_ring[p]) CU(c, cudaMalloc(&c->d_out_ring[p], (size_t)c->W * c->H * sizeof(uint32_t)));
+    // the image rendered into this buffer two frames ago must have left for the host
+    CU(c, cudaStreamWaitEvent(c->stream, c->ev_d2h_done[p], 0));
+    int rc = enqueue_frame(c, c->d_out_ring[p], false);
+    end_frame(c);
+    if (rc != RZ_OK) return rc;
+    CU(c, cudaEventRecord(c->ev_frame_done[p], c->stream));
+    CU(c, cudaStreamWaitEvent(c->down_stream, c->ev_frame_done[p], 0));
+    const size_t off = (size_t)c->row_begin * c->W, cnt = (size_t)(c->row_end - c->row_begin) * c->W;
+    CU(c, cudaMemcpyAsync(out_host + off, c->d_out_ring[p] + off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                          c->down_stream));
+    CU(c, cudaEventRecord(c->ev_d2h_done[p], c->down_stream));
+    c->out_parity ^= 1;
+    return RZ_OK;
+}
+
 int rz_sync(rz_ctx *c) {
     if (!c) return RZ_E_INVALID;
     if (c->sticky != RZ_OK) return c->sticky;
@@ -599,6 +659,7 @@ int rz_sync(rz_ctx *c) {
     FrameState *dfs = reinterpret_cast<FrameState *>(c->d_state);
     CU(c, cudaMemcpyAsync(c->h_state, dfs, sizeof(FrameState), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaStreamSynchronize(c->down_stream));
     if (c->h_state->err) {
         const uint32_t flags = c->h_state->err;
         CU(c, cudaMemsetAsync(&dfs->err, 0, sizeof(uint32_t), c->stream));

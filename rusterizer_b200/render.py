@@ -34,7 +34,7 @@ COUNTER_FIELDS = (
 ABI_SYMBOLS = (
     "rz_create", "rz_destroy", "rz_set_stream", "rz_bind_texture", "rz_write_block", "rz_read_block",
     "rz_mesh_create", "rz_mesh_destroy", "rz_render", "rz_render_host", "rz_framebuffer",
-    "rz_framebuffer_async", "rz_sync", "rz_set_row_range", "rz_tile_width", "rz_tile_height",
+    "rz_framebuffer_async", "rz_framebuffer_host_async", "rz_sync", "rz_set_row_range", "rz_tile_width", "rz_tile_height",
     "rz_counters", "rz_reset_counters", "rz_timings", "rz_launch_count", "rz_debug_capture",
     "rz_debug_read", "rz_debug_tile_times", "rz_debug_vertex_stage", "rz_last_error", "rz_version",
 )
@@ -91,6 +91,7 @@ def load_library() -> C.CDLL:
     L.rz_render_host.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_uint64, C.c_uint32, C.c_uint32]
     L.rz_framebuffer.argtypes = [vp, vp, C.POINTER(vp)]
     L.rz_framebuffer_async.argtypes = [vp, vp, C.POINTER(vp)]
+    L.rz_framebuffer_host_async.argtypes = [vp, vp]
     L.rz_sync.argtypes = [vp]
     L.rz_set_row_range.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.rz_tile_width.restype = C.c_uint32
@@ -272,6 +273,10 @@ class Renderer:
         p = C.c_void_p()
         self._check(self._L.rz_framebuffer_async(self._ctx, device_dst, C.byref(p)))
         return p.value
+
+    def framebuffer_host_async(self, host_ptr: int):
+        """Streaming display: frame + D2H of the image on a copy stream, no host sync (valid after sync())."""
+        self._check(self._L.rz_framebuffer_host_async(self._ctx, host_ptr))
 
     def sync(self):
         self._check(self._L.rz_sync(self._ctx))
