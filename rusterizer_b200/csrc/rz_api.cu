@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -68,6 +69,7 @@ struct rz_ctx {
     unsigned char *d_state = nullptr; // FrameState + tile_count[]
     unsigned long long *d_bins = nullptr;
     RasterRec *d_recs = nullptr;
+    unsigned long long *d_clipq = nullptr;
     ShadeRec *d_shade = nullptr;
     AttrRec *d_attrs = nullptr;
     DrawInfo *d_draws = nullptr;
@@ -156,6 +158,7 @@ static int free_frame_buffers(rz_ctx *c) {
     cudaFree(c->d_bins); c->d_bins = nullptr;
     cudaFree(c->d_recs); c->d_recs = nullptr;
     cudaFree(c->d_shade); c->d_shade = nullptr;
+    cudaFree(c->d_clipq); c->d_clipq = nullptr;
     cudaFree(c->d_attrs); c->d_attrs = nullptr;
     cudaFree(c->d_draws); c->d_draws = nullptr;
     cudaFree(c->d_large); c->d_large = nullptr;
@@ -182,9 +185,11 @@ static int ensure_capacity(rz_ctx *c, uint32_t rec_cap, uint32_t bin_cap, uint32
     if (rec_cap > c->rec_cap) {
         cudaFree(c->d_recs); c->d_recs = nullptr;
         cudaFree(c->d_shade); c->d_shade = nullptr;
+        cudaFree(c->d_clipq); c->d_clipq = nullptr;
         c->rec_cap = 0;
         CU(c, cudaMalloc(&c->d_recs, (size_t)rec_cap * sizeof(RasterRec)));
         CU(c, cudaMalloc(&c->d_shade, (size_t)rec_cap * sizeof(ShadeRec)));
+        CU(c, cudaMalloc(&c->d_clipq, (size_t)rec_cap * sizeof(unsigned long long)));
         c->rec_cap = rec_cap;
     }
     if (attr_cap > c->attr_cap) {
@@ -432,7 +437,7 @@ static FrameParams make_params(rz_ctx *c, uint32_t *out_base) {
     P.fs = reinterpret_cast<FrameState *>(c->d_state);
     P.tile_count = reinterpret_cast<uint32_t *>(c->d_state + sizeof(FrameState));
     P.busy = P.tile_count + (size_t)c->tiles_x * c->tiles_y;
-    P.bins = c->d_bins; P.recs = c->d_recs; P.shade = c->d_shade; P.attrs = c->d_attrs; P.large = c->d_large;
+    P.bins = c->d_bins; P.recs = c->d_recs; P.shade = c->d_shade; P.clipq = c->d_clipq; P.attrs = c->d_attrs; P.large = c->d_large;
     P.draws = c->d_draws; P.attr_cap = c->attr_cap;
     P.out = out_base;
     if (c->debug) {
@@ -476,7 +481,15 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
             c->draw_cap = cap;
         }
         c->h_draws.resize(c->draws.size());
-        for (size_t i = 0; i < c->draws.size(); i++) c->h_draws[i].attr = c->draws[i].mesh->d_attr;
+        uint32_t base = 0;
+        for (size_t i = 0; i < c->draws.size(); i++) {
+            DrawInfo &di = c->h_draws[i];
+            const rz_mesh *m = c->draws[i].mesh;
+            di.attr = m->d_attr; di.pos = m->d_pos; di.idx = m->d_idx;
+            di.nv = m->nv; di.tri_base = base; di.fs = c->draws[i].fs; di.pad = 0;
+            memcpy(di.M, c->draws[i].M, 64);
+            base += (uint32_t)(m->n_idx / 3);
+        }
         if (!c->h_draws.empty())
             CU(c, cudaMemcpyAsync(c->d_draws, c->h_draws.data(), c->h_draws.size() * sizeof(DrawInfo),
                                   cudaMemcpyHostToDevice, c->stream));
@@ -488,12 +501,14 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
         CU(c, cudaEventRecord(c->ev_uploaded, c->up_stream));
         CU(c, cudaStreamWaitEvent(st, c->ev_uploaded, 0));
     }
-    const size_t off = offsetof(FrameState, n_records); // 16-byte aligned by construction
-    {
-        const uint32_t n16 = (uint32_t)((zeroed_state_bytes(c) - off + 15) / 16);
-        CU(c, launch_pdl(frame_begin_kernel, dim3((n16 + NT - 1) / NT), dim3(NT), 0, st,
-                         reinterpret_cast<uint4 *>(c->d_state + off), n16));
+    const size_t off = offsetof(FrameState, n_clipq); // 16-byte aligned by construction
+    const uint32_t n16 = (uint32_t)((zeroed_state_bytes(c) - off + 15) / 16);
+    uint4 *zero16 = reinterpret_cast<uint4 *>(c->d_state + off);
+    bool zeroed = false; // the first vertex kernel of the frame zeroes the frame state; frames without one do it here
+    if (total_tris == 0) {
+        CU(c, launch_pdl(frame_begin_kernel, dim3((n16 + NT - 1) / NT), dim3(NT), 0, st, zero16, n16));
         c->launches++;
+        zeroed = true;
     }
     if (timed) CU(c, cudaEventRecord(c->ev[0], st));
     uint32_t tri_base = 0, draw_index = 0;
@@ -506,10 +521,19 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
         D.nv = d.mesh->nv; D.nt = nt; D.tri_base = tri_base; D.fs = d.fs; D.draw = this_draw;
         memcpy(D.M, d.M, 64);
         D.vtx = c->d_vtx;
-        CU(c, launch_pdl(vertex_kernel, dim3((D.nv + NT - 1) / NT), dim3(NT), 0, st, P, D));
-        CU(c, launch_pdl(geom_kernel, dim3((nt + NT - 1) / NT), dim3(NT), 0, st, P, D));
+        CU(c, launch_pdl(vertex_kernel, dim3(std::max(1u, (D.nv + NT * VERTEX_PER_THREAD - 1) / (NT * VERTEX_PER_THREAD))), dim3(NT), 0, st, P, D, zeroed ? (uint4 *)nullptr : zero16,
+                         zeroed ? 0u : n16));
+        zeroed = true;
+        static const int tune_geom = getenv("RZ_TUNE_GEOM_CTAS_PER_SM") ? atoi(getenv("RZ_TUNE_GEOM_CTAS_PER_SM")) : RZ_GEOM_MIN_CTAS;
+        const uint32_t geom_ctas = tune_geom > 0 ? std::min<uint32_t>((nt + NT - 1) / NT, (uint32_t)c->num_sms * tune_geom) : (nt + NT - 1) / NT;
+        CU(c, launch_pdl(geom_kernel, dim3(geom_ctas), dim3(NT), 0, st, P, D));
         c->launches += 2;
         tri_base += nt;
+    }
+    if (tri_base) { // triangles that straddle a clip plane, all draws of the frame (persistent grid)
+        const uint32_t ctas = (uint32_t)std::min<uint64_t>((uint64_t)c->num_sms * 4, (tri_base + NT - 1) / NT);
+        CU(c, launch_pdl(clip_kernel, dim3(ctas), dim3(NT), 0, st, P));
+        c->launches++;
     }
     if (timed) CU(c, cudaEventRecord(c->ev[1], st));
     CU(c, launch_pdl(large_bin_kernel, dim3(c->num_sms * 2), dim3(NT), 0, st, P));
@@ -760,7 +784,8 @@ int rz_debug_vertex_stage(rz_ctx *c, const rz_mesh *mesh, float *out_clip) {
     mat4_mul(pv, c->world, D.M);
     D.pos = mesh->d_pos; D.nv = mesh->nv;
     D.vtx = c->d_vtx;
-    CU(c, launch_pdl(vertex_kernel, dim3((mesh->nv + NT - 1) / NT), dim3(NT), 0, c->stream, P, D));
+    CU(c, launch_pdl(vertex_kernel, dim3((mesh->nv + NT * VERTEX_PER_THREAD - 1) / (NT * VERTEX_PER_THREAD)), dim3(NT), 0, c->stream, P, D,
+                     (uint4 *)nullptr, 0u));
     c->launches++;
     std::vector<float> tmp((size_t)mesh->nv * 8);
     CU(c, cudaMemcpyAsync(tmp.data(), c->d_vtx, tmp.size() * 4, cudaMemcpyDeviceToHost, c->stream));

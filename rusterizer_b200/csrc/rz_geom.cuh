@@ -189,146 +189,9 @@ __device__ __forceinline__ uint32_t clip_code(const float *c) {
     return code;
 }
 
-// Stage 1a -- vertex stage (render.rs:104-108): one thread per mesh vertex.  The vertex shader
-// (main.rs:147-152) is ((P*V)*W) * (x,y,z,1); the matrix product is hoisted to the host in the same
-// operation order (SURVEY.md App. D-3).  Besides the clip-space position it stores what every
-// triangle using the vertex would recompute: the perspective divide + viewport transform and the
-// 12 trivial-accept/reject comparisons.
-__global__ void __launch_bounds__(NT) vertex_kernel(FrameParams P, DrawParams D) {
-    pdl_launch();
-    pdl_wait();
-    const uint32_t v = blockIdx.x * NT + threadIdx.x;
-    if (v >= D.nv) return;
-    const float *p = D.pos + 3 * (size_t)v;
-    const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
-    float c[4];
-#pragma unroll
-    for (int r = 0; r < 4; r++) c[r] = dot4z(D.M[4 * r], D.M[4 * r + 1], D.M[4 * r + 2], D.M[4 * r + 3], x, y, z, 1.0f);
-    D.vtx[2 * (size_t)v] = project_vertex(c, (float)P.W, (float)P.H);
-    D.vtx[2 * (size_t)v + 1] = make_float4(c[0], c[1], c[2], __uint_as_float(clip_code(c)));
-}
-
-// Stage 1b/2 -- primitive assembly, clip, setup, binning: one thread per input triangle
-// (render.rs:75-96, rasterizer/mod.rs:425-441).
-__global__ void __launch_bounds__(NT) geom_kernel(FrameParams P, DrawParams D) {
-    __shared__ uint32_t s_part[NT / 32][C_COUNT];
-    __shared__ unsigned long long s_bbox[NT / 32];
-    pdl_launch();
-    pdl_wait();
-
-    GeomLocal lc;
-#pragma unroll
-    for (int k = 0; k < C_COUNT; k++) lc.c[k] = 0;
-    lc.bbox = 0ull;
-
-    const uint32_t t = blockIdx.x * NT + threadIdx.x;
-    {   // CTAs are dispatched roughly in order: pull the indices of the CTA that will run in this slot
-        // ~one wave from now into L2, so its first load is an L2 hit instead of a DRAM round trip
-        const size_t ahead = (size_t)t + (size_t)GEOM_PREFETCH_CTAS * NT;
-        if (ahead < D.nt && (threadIdx.x & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(D.idx + 3 * ahead));
-    }
-    if (t < D.nt) {
-        const uint32_t i0 = __ldg(&D.idx[3 * (size_t)t]), i1 = __ldg(&D.idx[3 * (size_t)t + 1]),
-                       i2 = __ldg(&D.idx[3 * (size_t)t + 2]);
-        if (i0 >= D.nv || i1 >= D.nv || i2 >= D.nv) {
-            atomicOr(&P.fs->err, ERR_INDEX); // the reference panics here (render.rs:83-87)
-        } else {
-            lc.c[C_TRIS_IN]++;
-            const uint32_t vi[3] = {i0, i1, i2};
-            const uint32_t key0 = (D.tri_base + t) * 8u;
-            // Everything a triangle may need from its three vertices is requested up front, so the
-            // independent gathers overlap instead of paying one L2 round trip per decision.
-            const float4 sv0 = __ldg(&D.vtx[2 * (size_t)i0]), cq0 = __ldg(&D.vtx[2 * (size_t)i0 + 1]);
-            const float4 sv1 = __ldg(&D.vtx[2 * (size_t)i1]), cq1 = __ldg(&D.vtx[2 * (size_t)i1 + 1]);
-            const float4 sv2 = __ldg(&D.vtx[2 * (size_t)i2]), cq2 = __ldg(&D.vtx[2 * (size_t)i2 + 1]);
-            const float2 q0 = make_float2(cq0.x, cq0.y), q1 = make_float2(cq1.x, cq1.y), q2 = make_float2(cq2.x, cq2.y);
-            const uint32_t code = __float_as_uint(cq0.w) & __float_as_uint(cq1.w) & __float_as_uint(cq2.w);
-            // clipping::try_clip (rasterizer/clipping.rs:62-195): degenerate test on clip-space xy first
-            const float a2x = cross2(fsub(q1.x, q0.x), fsub(q1.y, q0.y), fsub(q2.x, q0.x), fsub(q2.y, q0.y));
-            if (fabsf(a2x) < 0.000001f) {
-                lc.c[C_DEGENERATE]++;
-            } else {
-                if (code & 0xFC0u) { // all three vertices outside one plane
-                    lc.c[C_OUTSIDE]++;
-                } else if ((code & 0x3Fu) == 0x3Fu) { // all inside all planes
-                    lc.c[C_INSIDE]++;
-                    Setup s;
-                    s.px[0] = sv0.x; s.py[0] = sv0.y; s.z[0] = sv0.z; s.w[0] = sv0.w;
-                    s.px[1] = sv1.x; s.py[1] = sv1.y; s.z[1] = sv1.z; s.w[1] = sv1.w;
-                    s.px[2] = sv2.x; s.py[2] = sv2.y; s.z[2] = sv2.z; s.w[2] = sv2.w;
-                    emit_setup(P, D, s, i0, i1, i2, nullptr, key0, lc);
-                } else {
-                    // Sutherland-Hodgman against LEFT,RIGHT,BOTTOM,TOP,NEAR,FAR (clipping.rs:118-171)
-                    float pv[2][MAX_POLY][4];
-                    float pa[2][MAX_POLY][6];
-                    int n_out = 3, cur = 0;
-                    const float4 cqs[3] = {cq0, cq1, cq2};
-                    const float ws[3] = {sv0.w, sv1.w, sv2.w};
-                    for (int v = 0; v < 3; v++) {
-                        pv[0][v][0] = cqs[v].x; pv[0][v][1] = cqs[v].y; pv[0][v][2] = cqs[v].z; pv[0][v][3] = ws[v];
-                        const float *a = D.attr + 6 * (size_t)vi[v];
-                        for (int k = 0; k < 6; k++) pa[0][v][k] = __ldg(a + k);
-                    }
-                    bool ovf = false;
-                    for (int plane = 0; plane < 6; plane++) {
-                        const int n_in = n_out, in = cur, out = cur ^ 1;
-                        n_out = 0;
-                        for (int i = 0; i < n_in; i++) {
-                            const int prev = (i + n_in - 1) % n_in;
-                            const float *pvv = pv[in][prev], *cvv = pv[in][i];
-                            const float pd = clip_distance(plane, pvv), cd = clip_distance(plane, cvv);
-                            const bool pin = pd >= 0.0f, cin = cd >= 0.0f;
-                            if (!pin && !cin) continue;
-                            if (n_out + 2 > MAX_POLY) {
-                                ovf = true;
-                                break;
-                            }
-                            if (pin != cin) { // crossing: intersection first (clipping.rs:43-51)
-                                const float alpha = fdiv(pd, fsub(pd, cd));
-                                const float om = fsub(1.0f, alpha);
-                                for (int k = 0; k < 4; k++)
-                                    pv[out][n_out][k] = fadd(fmul(pvv[k], om), fmul(cvv[k], alpha));
-                                for (int k = 0; k < 6; k++) // (cur - prev) * alpha + prev (clipping.rs:149,161)
-                                    pa[out][n_out][k] =
-                                        fadd(fmul(fsub(pa[in][i][k], pa[in][prev][k]), alpha), pa[in][prev][k]);
-                                n_out++;
-                            }
-                            if (cin) {
-                                for (int k = 0; k < 4; k++) pv[out][n_out][k] = cvv[k];
-                                for (int k = 0; k < 6; k++) pa[out][n_out][k] = pa[in][i][k];
-                                n_out++;
-                            }
-                        }
-                        cur = out;
-                    }
-                    if (ovf) lc.c[C_CLIP_OVF]++;
-                    if (n_out < 3) {
-                        lc.c[C_OUTSIDE]++; // late outside (clipping.rs:175-177)
-                    } else {
-                        lc.c[C_CLIPPED_IN]++;
-                        const float Wf = (float)P.W, Hf = (float)P.H;
-                        const float4 s0 = project_vertex(pv[cur][0], Wf, Hf);
-                        float4 sb = project_vertex(pv[cur][1], Wf, Hf);
-                        for (int i = 0; i + 2 < n_out; i++) { // fan (0, i+1, i+2) (clipping.rs:185-190)
-                            const float4 sc = project_vertex(pv[cur][i + 2], Wf, Hf);
-                            Setup s;
-                            s.px[0] = s0.x; s.py[0] = s0.y; s.z[0] = s0.z; s.w[0] = s0.w;
-                            s.px[1] = sb.x; s.py[1] = sb.y; s.z[1] = sb.z; s.w[1] = sb.w;
-                            s.px[2] = sc.x; s.py[2] = sc.y; s.z[2] = sc.z; s.w[2] = sc.w;
-                            float ca[3][6];
-                            for (int k = 0; k < 6; k++) {
-                                ca[0][k] = pa[cur][0][k]; ca[1][k] = pa[cur][i + 1][k]; ca[2][k] = pa[cur][i + 2][k];
-                            }
-                            emit_setup(P, D, s, 0u, 0u, 0u, ca, key0 + (uint32_t)min(i, 7), lc);
-                            sb = sc;
-                        }
-                    }
-                }
-            }
-        }
-    }
-
-    // block-level counter reduction: warp reduce -> per-warp partials -> one striped global RED per counter
+// block-level counter reduction: warp reduce -> per-warp partials -> one striped global RED per counter
+__device__ __forceinline__ void flush_geom_counters(const FrameParams &P, const GeomLocal &lc, uint32_t (*s_part)[C_COUNT],
+                                                    unsigned long long *s_bbox) {
     {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -360,6 +223,212 @@ __global__ void __launch_bounds__(NT) geom_kernel(FrameParams P, DrawParams D) {
     }
 }
 
+// Stage 1a -- vertex stage (render.rs:104-108): one thread per mesh vertex.  The vertex shader
+// (main.rs:147-152) is ((P*V)*W) * (x,y,z,1); the matrix product is hoisted to the host in the same
+// operation order (SURVEY.md App. D-3).  Besides the clip-space position it stores what every
+// triangle using the vertex would recompute: the perspective divide + viewport transform and the
+// 12 trivial-accept/reject comparisons.
+// The first vertex kernel of a frame also zeroes the per-frame part of the frame state and the tile
+// counters (zero16/n16 != 0): the previous frame's tile kernel has completed by pdl_wait(), and this
+// frame's geometry kernels start after this kernel.
+__global__ void __launch_bounds__(NT) vertex_kernel(FrameParams P, DrawParams D, uint4 *zero16, uint32_t n16) {
+    pdl_launch();
+    pdl_wait();
+    for (uint32_t i = blockIdx.x * NT + threadIdx.x; i < n16; i += gridDim.x * NT) zero16[i] = make_uint4(0u, 0u, 0u, 0u);
+    // VERTEX_PER_THREAD vertices per thread, a CTA-strided chunk each: all position loads are issued before
+    // the first use, so one wave of CTAs keeps enough bytes in flight to stream the mesh from HBM
+    float x[VERTEX_PER_THREAD], y[VERTEX_PER_THREAD], z[VERTEX_PER_THREAD];
+    const uint32_t v0 = blockIdx.x * (NT * VERTEX_PER_THREAD) + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < VERTEX_PER_THREAD; k++) {
+        const uint32_t v = v0 + k * NT;
+        if (v < D.nv) {
+            const float *p = D.pos + 3 * (size_t)v;
+            x[k] = __ldg(p); y[k] = __ldg(p + 1); z[k] = __ldg(p + 2);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < VERTEX_PER_THREAD; k++) {
+        const uint32_t v = v0 + k * NT;
+        if (v >= D.nv) break;
+        float c[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            c[r] = dot4z(D.M[4 * r], D.M[4 * r + 1], D.M[4 * r + 2], D.M[4 * r + 3], x[k], y[k], z[k], 1.0f);
+        D.vtx[2 * (size_t)v] = project_vertex(c, (float)P.W, (float)P.H);
+        D.vtx[2 * (size_t)v + 1] = make_float4(c[0], c[1], c[2], __uint_as_float(clip_code(c)));
+    }
+}
+
+// Stage 1b/2 -- primitive assembly, clip, setup, binning: one thread per input triangle
+// (render.rs:75-96, rasterizer/mod.rs:425-441).
+#ifndef RZ_GEOM_MIN_CTAS
+#define RZ_GEOM_MIN_CTAS 5 // 48 registers: 40 resident warps per SM (the kernel is latency bound)
+#endif
+__global__ void __launch_bounds__(NT, RZ_GEOM_MIN_CTAS) geom_kernel(FrameParams P, DrawParams D) {
+    __shared__ uint32_t s_part[NT / 32][C_COUNT];
+    __shared__ unsigned long long s_bbox[NT / 32];
+    pdl_launch();
+    pdl_wait();
+
+    GeomLocal lc;
+#pragma unroll
+    for (int k = 0; k < C_COUNT; k++) lc.c[k] = 0;
+    lc.bbox = 0ull;
+
+    // Persistent CTAs: CTA b takes the 256-triangle chunks b, b + grid, b + 2*grid, ...  The index triple of
+    // the next chunk is loaded before the current one is processed (register double buffer), so the DRAM
+    // latency of the index stream never sits on the critical path, the warps of a CTA run free of
+    // each other (no per-chunk barrier), and the counters are flushed once per CTA.
+    const uint32_t n_chunks = (D.nt + NT - 1) / NT;
+    uint32_t n0 = 0, n1 = 0, n2 = 0;
+    {
+        const uint32_t t = blockIdx.x * NT + threadIdx.x;
+        if (t < D.nt) {
+            n0 = __ldg(&D.idx[3 * (size_t)t]); n1 = __ldg(&D.idx[3 * (size_t)t + 1]); n2 = __ldg(&D.idx[3 * (size_t)t + 2]);
+        }
+    }
+    for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const uint32_t t = chunk * NT + threadIdx.x;
+    const uint32_t i0 = n0, i1 = n1, i2 = n2;
+    {
+        const size_t tn = (size_t)t + (size_t)gridDim.x * NT;
+        if (tn < D.nt) {
+            n0 = __ldg(&D.idx[3 * tn]); n1 = __ldg(&D.idx[3 * tn + 1]); n2 = __ldg(&D.idx[3 * tn + 2]);
+        }
+    }
+    if (t < D.nt) {
+        if (i0 >= D.nv || i1 >= D.nv || i2 >= D.nv) {
+            atomicOr(&P.fs->err, ERR_INDEX); // the reference panics here (render.rs:83-87)
+        } else {
+            lc.c[C_TRIS_IN]++;
+            const uint32_t key0 = (D.tri_base + t) * 8u;
+            // Everything a triangle may need from its three vertices is requested up front, so the
+            // independent gathers overlap instead of paying one L2 round trip per decision.
+            const float4 sv0 = __ldg(&D.vtx[2 * (size_t)i0]), cq0 = __ldg(&D.vtx[2 * (size_t)i0 + 1]);
+            const float4 sv1 = __ldg(&D.vtx[2 * (size_t)i1]), cq1 = __ldg(&D.vtx[2 * (size_t)i1 + 1]);
+            const float4 sv2 = __ldg(&D.vtx[2 * (size_t)i2]), cq2 = __ldg(&D.vtx[2 * (size_t)i2 + 1]);
+            const float2 q0 = make_float2(cq0.x, cq0.y), q1 = make_float2(cq1.x, cq1.y), q2 = make_float2(cq2.x, cq2.y);
+            const uint32_t code = __float_as_uint(cq0.w) & __float_as_uint(cq1.w) & __float_as_uint(cq2.w);
+            // clipping::try_clip (rasterizer/clipping.rs:62-195): degenerate test on clip-space xy first
+            const float a2x = cross2(fsub(q1.x, q0.x), fsub(q1.y, q0.y), fsub(q2.x, q0.x), fsub(q2.y, q0.y));
+            if (fabsf(a2x) < 0.000001f) {
+                lc.c[C_DEGENERATE]++;
+            } else {
+                if (code & 0xFC0u) { // all three vertices outside one plane
+                    lc.c[C_OUTSIDE]++;
+                } else if ((code & 0x3Fu) == 0x3Fu) { // all inside all planes
+                    lc.c[C_INSIDE]++;
+                    Setup s;
+                    s.px[0] = sv0.x; s.py[0] = sv0.y; s.z[0] = sv0.z; s.w[0] = sv0.w;
+                    s.px[1] = sv1.x; s.py[1] = sv1.y; s.z[1] = sv1.z; s.w[1] = sv1.w;
+                    s.px[2] = sv2.x; s.py[2] = sv2.y; s.z[2] = sv2.z; s.w[2] = sv2.w;
+                    emit_setup(P, D, s, i0, i1, i2, nullptr, key0, lc);
+                } else {
+                    // straddles a clip plane: queued for clip_kernel (keeps this kernel's register count,
+                    // and with it the number of resident warps, independent of the Sutherland-Hodgman path)
+                    const uint32_t q = alloc_slot(&P.fs->n_clipq);
+                    if (q < P.rec_cap) P.clipq[q] = ((unsigned long long)D.draw << 32) | t;
+                    else atomicOr(&P.fs->err, ERR_REC_OVF);
+                }
+            }
+        }
+    }
+
+    } // persistent chunk loop
+    flush_geom_counters(P, lc, s_part, s_bbox);
+}
+
+// Stage 1c -- triangles that straddle a clip plane (ClipResult::Clipped candidates), all draws of the
+// frame: one thread per queued triangle, persistent grid.  The clip-space vertices are recomputed from
+// the mesh (the same operation sequence as vertex_kernel, hence the same bits), clipped by
+// Sutherland-Hodgman and re-triangulated as a fan (clipping.rs:118-190).
+__global__ void __launch_bounds__(NT) clip_kernel(FrameParams P) {
+    __shared__ uint32_t s_part[NT / 32][C_COUNT];
+    __shared__ unsigned long long s_bbox[NT / 32];
+    pdl_launch();
+    pdl_wait();
+    GeomLocal lc;
+#pragma unroll
+    for (int k = 0; k < C_COUNT; k++) lc.c[k] = 0;
+    lc.bbox = 0ull;
+    const uint32_t nq = min(P.fs->n_clipq, P.rec_cap);
+    for (uint32_t qi = blockIdx.x * NT + threadIdx.x; qi < nq; qi += gridDim.x * NT) {
+        const unsigned long long e = P.clipq[qi];
+        const uint32_t t = (uint32_t)e;
+        const DrawInfo &di = P.draws[(uint32_t)(e >> 32)];
+        DrawParams D; // what emit_setup needs
+        D.attr = di.attr; D.fs = di.fs; D.draw = (uint32_t)(e >> 32);
+        const uint32_t key0 = (di.tri_base + t) * 8u;
+        float pv[2][MAX_POLY][4];
+        float pa[2][MAX_POLY][6];
+        for (int v = 0; v < 3; v++) {
+            const uint32_t vi = __ldg(&di.idx[3 * (size_t)t + v]);
+            const float *p = di.pos + 3 * (size_t)vi;
+            const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+            for (int r = 0; r < 4; r++)
+                pv[0][v][r] = dot4z(di.M[4 * r], di.M[4 * r + 1], di.M[4 * r + 2], di.M[4 * r + 3], x, y, z, 1.0f);
+            const float *a = di.attr + 6 * (size_t)vi;
+            for (int k = 0; k < 6; k++) pa[0][v][k] = __ldg(a + k);
+        }
+        int n_out = 3, cur = 0;
+        bool ovf = false;
+        // Sutherland-Hodgman against LEFT,RIGHT,BOTTOM,TOP,NEAR,FAR (clipping.rs:118-171)
+        for (int plane = 0; plane < 6; plane++) {
+            const int n_in = n_out, in = cur, out = cur ^ 1;
+            n_out = 0;
+            for (int i = 0; i < n_in; i++) {
+                const int prev = (i + n_in - 1) % n_in;
+                const float *pvv = pv[in][prev], *cvv = pv[in][i];
+                const float pd = clip_distance(plane, pvv), cd = clip_distance(plane, cvv);
+                const bool pin = pd >= 0.0f, cin = cd >= 0.0f;
+                if (!pin && !cin) continue;
+                if (n_out + 2 > MAX_POLY) {
+                    ovf = true;
+                    break;
+                }
+                if (pin != cin) { // crossing: intersection first (clipping.rs:43-51)
+                    const float alpha = fdiv(pd, fsub(pd, cd));
+                    const float om = fsub(1.0f, alpha);
+                    for (int k = 0; k < 4; k++) pv[out][n_out][k] = fadd(fmul(pvv[k], om), fmul(cvv[k], alpha));
+                    for (int k = 0; k < 6; k++) // (cur - prev) * alpha + prev (clipping.rs:149,161)
+                        pa[out][n_out][k] = fadd(fmul(fsub(pa[in][i][k], pa[in][prev][k]), alpha), pa[in][prev][k]);
+                    n_out++;
+                }
+                if (cin) {
+                    for (int k = 0; k < 4; k++) pv[out][n_out][k] = cvv[k];
+                    for (int k = 0; k < 6; k++) pa[out][n_out][k] = pa[in][i][k];
+                    n_out++;
+                }
+            }
+            cur = out;
+        }
+        if (ovf) lc.c[C_CLIP_OVF]++;
+        if (n_out < 3) {
+            lc.c[C_OUTSIDE]++; // late outside (clipping.rs:175-177)
+        } else {
+            lc.c[C_CLIPPED_IN]++;
+            const float Wf = (float)P.W, Hf = (float)P.H;
+            const float4 s0 = project_vertex(pv[cur][0], Wf, Hf);
+            float4 sb = project_vertex(pv[cur][1], Wf, Hf);
+            for (int i = 0; i + 2 < n_out; i++) { // fan (0, i+1, i+2) (clipping.rs:185-190)
+                const float4 sc = project_vertex(pv[cur][i + 2], Wf, Hf);
+                Setup s;
+                s.px[0] = s0.x; s.py[0] = s0.y; s.z[0] = s0.z; s.w[0] = s0.w;
+                s.px[1] = sb.x; s.py[1] = sb.y; s.z[1] = sb.z; s.w[1] = sb.w;
+                s.px[2] = sc.x; s.py[2] = sc.y; s.z[2] = sc.z; s.w[2] = sc.w;
+                float ca[3][6];
+                for (int k = 0; k < 6; k++) {
+                    ca[0][k] = pa[cur][0][k]; ca[1][k] = pa[cur][i + 1][k]; ca[2][k] = pa[cur][i + 2][k];
+                }
+                emit_setup(P, D, s, 0u, 0u, 0u, ca, key0 + (uint32_t)min(i, 7), lc);
+                sb = sc;
+            }
+        }
+    }
+    flush_geom_counters(P, lc, s_part, s_bbox);
+}
+
 __device__ __forceinline__ void load_setup(const RasterRec *recs, uint32_t rec, Setup &s, uint32_t &key) {
     const float4 *rr = reinterpret_cast<const float4 *>(&recs[rec]);
     const float4 r0 = __ldg(rr), r1 = __ldg(rr + 1), r2 = __ldg(rr + 2);
@@ -379,6 +448,7 @@ __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
     pdl_launch();
     pdl_wait();
     const uint32_t n = min(P.fs->n_large, P.large_cap);
+    if (n == 0u) return; // nothing queued (meshes of small triangles): skip the round trip of the cursor atomic
     const int lane = threadIdx.x & 31;
     for (;;) { // one warp per (triangle, slab) item, stolen from a global cursor
         uint32_t item = 0;

@@ -245,44 +245,6 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
     pdl_launch();
     pdl_wait();
 
-    // ---- phase 0: tiles nothing was binned into.  The box filter of four clear samples is the clear
-    // colour (buffers.rs:5,111-125): one warp writes such a tile as 64 128-bit stores. ----
-    {
-        const uint32_t shard_tiles = P.tiles_x * (P.ty_end - P.ty_begin);
-        for (uint32_t i = blockIdx.x * (NT / 32) + warp; i < shard_tiles; i += gridDim.x * (NT / 32)) {
-            const uint32_t t = P.ty_begin * P.tiles_x + i;
-            if (P.tile_count[t] != 0u) continue;
-            const int x0 = (int)(t % P.tiles_x) * TW, y0 = (int)(t / P.tiles_x) * TH;
-            if ((P.W & 3u) == 0u) {
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int e = lane + 32 * h, row = e / (TW / 4), q = e % (TW / 4);
-                    const int Yr = y0 + row, Xq = x0 + q * 4;
-                    if (Yr < (int)P.H && Xq < (int)P.W)
-                        *reinterpret_cast<uint4 *>(&P.out[(size_t)Yr * P.W + Xq]) =
-                            make_uint4(CLEAR_COLOR, CLEAR_COLOR, CLEAR_COLOR, CLEAR_COLOR);
-                }
-            } else {
-                for (int e = lane; e < TILE_PX; e += 32) {
-                    const int Yr = y0 + e / TW, Xq = x0 + e % TW;
-                    if (Yr < (int)P.H && Xq < (int)P.W) P.out[(size_t)Yr * P.W + Xq] = CLEAR_COLOR;
-                }
-            }
-            if (DBG) {
-                for (int e = lane; e < TILE_PX; e += 32) {
-                    const int Yr = y0 + e / TW, Xq = x0 + e % TW;
-                    if (Yr >= (int)P.H || Xq >= (int)P.W) continue;
-                    const size_t o = ((size_t)Yr * P.W + Xq) * 4;
-                    for (int k = 0; k < 4; k++) {
-                        if (P.dbg_depth) P.dbg_depth[o + k] = CLEAR_DEPTH;
-                        if (P.dbg_color) P.dbg_color[o + k] = CLEAR_COLOR;
-                        if (P.dbg_owner) P.dbg_owner[o + k] = NO_OWNER;
-                    }
-                }
-            }
-        }
-    }
-
     // ---- phase 1: persistent loop over the tiles that received triangles (dynamic work stealing) ----
     S.lut[tid] = fdiv((float)tid, 255.0f);
     uint32_t bucket_end[ORDER_BUCKETS]; // prefix of the class sizes: work item w belongs to the first class with w < end
@@ -701,6 +663,45 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
         o[6] = 0; o[7] = 0;
     }
     } // persistent tile loop
+
+    // ---- phase 2: tiles nothing was binned into.  The box filter of four clear samples is the clear
+    // colour (buffers.rs:5,111-125): one warp writes such a tile as 64 128-bit stores.  Done after the
+    // persistent loop, so these stores fill the tail of the kernel instead of delaying its start. ----
+    {
+        const uint32_t shard_tiles = P.tiles_x * (P.ty_end - P.ty_begin);
+        for (uint32_t i = blockIdx.x * (NT / 32) + warp; i < shard_tiles; i += gridDim.x * (NT / 32)) {
+            const uint32_t t = P.ty_begin * P.tiles_x + i;
+            if (P.tile_count[t] != 0u) continue;
+            const int x0 = (int)(t % P.tiles_x) * TW, y0 = (int)(t / P.tiles_x) * TH;
+            if ((P.W & 3u) == 0u) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int e = lane + 32 * h, row = e / (TW / 4), q = e % (TW / 4);
+                    const int Yr = y0 + row, Xq = x0 + q * 4;
+                    if (Yr < (int)P.H && Xq < (int)P.W)
+                        *reinterpret_cast<uint4 *>(&P.out[(size_t)Yr * P.W + Xq]) =
+                            make_uint4(CLEAR_COLOR, CLEAR_COLOR, CLEAR_COLOR, CLEAR_COLOR);
+                }
+            } else {
+                for (int e = lane; e < TILE_PX; e += 32) {
+                    const int Yr = y0 + e / TW, Xq = x0 + e % TW;
+                    if (Yr < (int)P.H && Xq < (int)P.W) P.out[(size_t)Yr * P.W + Xq] = CLEAR_COLOR;
+                }
+            }
+            if (DBG) {
+                for (int e = lane; e < TILE_PX; e += 32) {
+                    const int Yr = y0 + e / TW, Xq = x0 + e % TW;
+                    if (Yr >= (int)P.H || Xq >= (int)P.W) continue;
+                    const size_t o = ((size_t)Yr * P.W + Xq) * 4;
+                    for (int k = 0; k < 4; k++) {
+                        if (P.dbg_depth) P.dbg_depth[o + k] = CLEAR_DEPTH;
+                        if (P.dbg_color) P.dbg_color[o + k] = CLEAR_COLOR;
+                        if (P.dbg_owner) P.dbg_owner[o + k] = NO_OWNER;
+                    }
+                }
+            }
+        }
+    }
 
     // ---- counters: warp reduce -> per-warp partials -> one striped global RED per counter ----
     {

@@ -15,7 +15,7 @@ constexpr int SORT_CAP = 2048;      // tile lists up to this length are sorted i
 constexpr int GEOM_SMALL_DIM = 16;  // bbox extent up to which a triangle is binned directly (spans at most 2x2 tiles)
 constexpr int GEOM_THIN_PX = 64;    // bbox area up to which a thin triangle is pre-rasterised exactly
 constexpr float GEOM_THIN_AREA2 = 1.0f; // 2x screen area below which a small triangle is pre-rasterised
-constexpr int GEOM_PREFETCH_CTAS = 592; // index prefetch distance of the geometry stage (~ one wave of CTAs)
+constexpr int VERTEX_PER_THREAD = 4; // vertices per thread of the vertex stage
 constexpr int LARGE_SLAB_ROWS = 8;  // tile rows per large-triangle binning work item
 constexpr int MAX_POLY = 10;        // clipped polygon vertex budget (=> <= 8 fan triangles, 3 key bits)
 
@@ -49,7 +49,7 @@ struct FrameState {
     unsigned long long counters[CNT_STRIPES][16];
     uint32_t err;         // sticky ERR_* flags
     uint32_t pad0[3];
-    uint32_t n_records;   // (unused; kept for layout)                      <- per-frame part starts here
+    uint32_t n_clipq;     // triangles queued for the clip kernel           <- per-frame part starts here
     uint32_t n_large;     // large-triangle binning work items
     uint32_t n_clip_attr; // AttrRec slots handed out to clipped triangles
     uint32_t large_next;  // work-stealing cursor of the large binning kernel
@@ -86,9 +86,13 @@ struct __align__(16) AttrRec {
     float a[20];
 };
 
-// Per-draw data the shading step dereferences
+// Per-draw data the shading step and the clip kernel dereference (one entry per rz_render call)
 struct DrawInfo {
-    const float *attr; // [nv][6]
+    const float *attr;   // [nv][6]
+    const float *pos;    // [nv][3]
+    const uint32_t *idx; // [3*nt]
+    uint32_t nv, tri_base, fs, pad;
+    float M[16];         // (projection * view) * world
 };
 
 // Large-triangle binning work item
@@ -115,6 +119,7 @@ struct FrameParams {
     unsigned long long *bins;    // [tiles][bin_cap]  (key << 32 | rec)
     RasterRec *recs;
     ShadeRec *shade;
+    unsigned long long *clipq;   // [rec_cap] draw << 32 | triangle: triangles that straddle a clip plane
     AttrRec *attrs;              // clipped triangles only
     const DrawInfo *draws;
     uint32_t attr_cap;
