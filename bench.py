@@ -198,6 +198,9 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--inflight", type=int, default=3,
                     help="frames in flight per GPU in the timed region (one renderer context + stream each); frames mode only")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="tiles mode, N>1: 'peer' = tile kernels store their rows straight into rank 0's image over NVLink "
+                         "(CUDA IPC peer memory + flag kernels); 'nccl' = local strips + one all_gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     args = ap.parse_args()
@@ -251,7 +254,13 @@ def main():
         r.set_row_range(r0, r1)
         own_rows = r1 - r0
         strip = torch.empty((rows_per, W), dtype=torch.int32, device="cuda")
-        gather_buf = torch.empty((n_gpus * rows_per, W), dtype=torch.int32, device="cuda") if n_gpus > 1 else None
+        use_peer = n_gpus > 1 and args.gather == "peer"
+        gather_buf = torch.empty((n_gpus * rows_per, W), dtype=torch.int32, device="cuda") if n_gpus > 1 and not use_peer else None
+        pf = None
+        if use_peer:
+            from rusterizer_b200.sharding import PeerFrame
+
+            pf = PeerFrame(r, root=0, n_buffers=2)
         cams = [Camera()] * (K + Wm)
     elif n_gpus > 1:
         sweep = scenes.orbit_cameras(1024)
@@ -265,13 +274,17 @@ def main():
     def frame_async(i):
         blk.view = views[i]
         r.render(dmesh, 0, 0)
-        if tiles_mode:
+        if tiles_mode and pf is not None:
+            last_image[0] = pf.finish_frame()  # rank 0: the complete frame, stream-ordered
+            pf.release()
+        elif tiles_mode:
             r.framebuffer_async(strip.data_ptr())
             if gather_buf is not None:
                 dist.all_gather_into_tensor(gather_buf, strip)
         else:
             r.framebuffer_async()
 
+    last_image = [None]
     # ---- warm-up: the synchronous path sizes the device buffers, then a few async frames ----
     blk.view = views[0]
     r.render(dmesh, 0, 0)
@@ -338,6 +351,10 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+    if world > 1:  # rank 0 slept while the sampler started: line the ranks up again right before the timed frames
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
     launches0 = sum(x[0].launch_count() for x in lanes)
     t_wall0 = time.time()
     if tiles_mode:
@@ -400,6 +417,36 @@ def main():
         for k in stage:
             stage[k].append(t[k])
     stage_avg = {k: sum(v) / len(v) for k, v in stage.items()}
+
+    # ---- tiles mode: the assembled frame on rank 0 must be the frame one GPU renders alone ----
+    assembled_ok = None
+    if tiles_mode and n_gpus > 1:
+        frame_async(0)
+        r.sync()
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            if pf is not None:
+                class _Raw:  # zero-copy torch view of the shared image (device pointer owned by the library)
+                    __cuda_array_interface__ = {"shape": (H, W), "typestr": "<i4", "data": (int(last_image[0]), False), "version": 3}
+
+                got = torch.as_tensor(_Raw(), device="cuda")
+            else:
+                got = gather_buf[:H]
+            solo = Renderer(W, H, device=local)
+            solo.uniforms().bind_texture(0, scene.texture)
+            sb = solo.uniforms().write_block()
+            sb.projection, sb.world, sb.view = scene.projection, scene.draws[0].world, views[0]
+            solo.render(mesh, 0, 0)
+            want = torch.from_numpy(solo.framebuffer().view(np.int32)).cuda()
+            solo.close()
+            assembled_ok = bool(torch.equal(got, want))
+            if not assembled_ok:
+                raise SystemExit("bench.py: the frame assembled from the ranks' tile rows differs from the single-GPU frame")
+        dist.barrier()
+    if pf is not None:
+        pf.close()
+        r.set_row_range(r0, r1)
 
     # ---- e2e: host buffers in, host image out, every step (pinned memory) ----
     pos_h = torch.from_numpy(mesh.vertices).pin_memory()
@@ -511,6 +558,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if tiles_mode else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, scene),
         "gsamples_per_s": gsamples, "ms_per_frame": ms_per_step, "frame_latency_ms": frame_latency_ms,
+        "gather": (args.gather if tiles_mode and n_gpus > 1 else None), "assembled_frame_matches_single_gpu": assembled_ok,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(e2.item()) / e2e_steps * 1e3, "steps": e2e_steps,

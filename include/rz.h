@@ -40,6 +40,7 @@ extern "C" {
 #define RZ_E_CAPACITY -6  /* an async frame outgrew its device buffers; re-issue it through
                              rz_framebuffer(), which grows them and retries                       */
 #define RZ_E_NOMEM -7     /* device or host allocation failed                                     */
+#define RZ_E_PEER -8      /* a peer GPU did not raise its completion flag within the timeout      */
 
 #define RZ_VS_MVP 0     /* projection * view * world * (x,y,z,1)          main.rs:147-152 */
 #define RZ_FS_TEXTURE 0 /* get_texture(0).sample(u, v)                    main.rs:69-71   */
@@ -143,6 +144,23 @@ int rz_sync(rz_ctx *ctx);
  * rows [row_begin, row_end) (rounded outwards to tile rows by the caller via rz_tile_height()).
  * Rows outside are left untouched in the output.  Default: the whole framebuffer. */
 int rz_set_row_range(rz_ctx *ctx, uint32_t row_begin, uint32_t row_end);
+/* Screen-space sharding without a separate gather step (one process per GPU, NVLink peer memory).
+ * The rank that presents the frame allocates the image with rz_shared_alloc and sends the 64-byte
+ * handle to its peers (any transport; the Python mirror uses torch.distributed); they map it with
+ * rz_shared_open and pass `mapped + row_begin*width` to rz_framebuffer_async, so their tile kernels
+ * store the resolved rows straight into the presenting GPU's memory while they rasterise.  Completion
+ * travels the same way: after its frame a rank calls rz_signal({&flags[rank]}, 1, seq) on a mapped flag
+ * array of the presenter, which calls rz_wait_flags(flags, n, stride, seq) -- both are stream-ordered
+ * kernels, nothing blocks the host.  seq must increase from frame to frame (wrap-around safe).
+ * rz_wait_flags gives up after timeout_ms (0 = 2000 ms); the next rz_sync then returns RZ_E_PEER.
+ * No reference counterpart (the reference is a single-threaded CPU program). */
+int rz_shared_alloc(rz_ctx *ctx, uint64_t bytes, void **dev_ptr, uint8_t *handle64);
+int rz_shared_open(rz_ctx *ctx, const uint8_t *handle64, void **dev_ptr);
+int rz_shared_close(rz_ctx *ctx, void *dev_ptr);
+int rz_shared_free(rz_ctx *ctx, void *dev_ptr);
+int rz_signal(rz_ctx *ctx, uint32_t *const *flags, uint32_t n, uint32_t value); /* n <= 16 flags, one kernel */
+int rz_wait_flags(rz_ctx *ctx, const uint32_t *flags, uint32_t n, uint32_t stride_bytes, uint32_t value,
+                  uint32_t timeout_ms);
 uint32_t rz_tile_width(void);
 uint32_t rz_tile_height(void);
 

@@ -684,11 +684,91 @@ int rz_sync(rz_ctx *c) {
     CU(c, cudaMemcpyAsync(c->h_state, dfs, sizeof(FrameState), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaStreamSynchronize(c->down_stream));
+    if (c->h_state->peer_timeout) {
+        CU(c, cudaMemsetAsync(&dfs->peer_timeout, 0, sizeof(uint32_t), c->stream));
+        return fail(c, RZ_E_PEER, "rz_wait_flags: a peer did not signal within the timeout");
+    }
     if (c->h_state->err) {
         const uint32_t flags = c->h_state->err;
         CU(c, cudaMemsetAsync(&dfs->err, 0, sizeof(uint32_t), c->stream));
         return map_err_flags(c, flags);
     }
+    return RZ_OK;
+}
+
+// ---- peer memory (one process per GPU; CUDA IPC over NVLink) ----
+int rz_shared_alloc(rz_ctx *c, uint64_t bytes, void **dev_ptr, uint8_t *handle64) {
+    if (!c || !dev_ptr || !handle64 || bytes == 0) return RZ_E_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    CU(c, cudaSetDevice(c->device));
+    void *p = nullptr;
+    CU(c, cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(c, RZ_E_CUDA, "rz_shared_alloc: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle64, &h, 64);
+    *dev_ptr = p;
+    return RZ_OK;
+}
+
+int rz_shared_open(rz_ctx *c, const uint8_t *handle64, void **dev_ptr) {
+    if (!c || !handle64 || !dev_ptr) return RZ_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(c, RZ_E_CUDA, "rz_shared_open: %s (peer access between the two GPUs is required)", cudaGetErrorString(e));
+    }
+    return RZ_OK;
+}
+
+int rz_shared_close(rz_ctx *c, void *dev_ptr) {
+    if (!c || !dev_ptr) return RZ_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaIpcCloseMemHandle(dev_ptr));
+    return RZ_OK;
+}
+
+int rz_shared_free(rz_ctx *c, void *dev_ptr) {
+    if (!c || !dev_ptr) return RZ_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaFree(dev_ptr));
+    return RZ_OK;
+}
+
+int rz_signal(rz_ctx *c, uint32_t *const *flags, uint32_t n, uint32_t value) {
+    if (!c || !flags || n == 0 || n > 16) return RZ_E_INVALID;
+    if (c->sticky != RZ_OK) return c->sticky;
+    CU(c, cudaSetDevice(c->device));
+    FlagList fl;
+    memset(&fl, 0, sizeof fl);
+    for (uint32_t i = 0; i < n; i++) {
+        if (!flags[i]) return RZ_E_INVALID;
+        fl.p[i] = flags[i];
+    }
+    signal_kernel<<<1, 32, 0, c->stream>>>(fl, n, value);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return RZ_OK;
+}
+
+int rz_wait_flags(rz_ctx *c, const uint32_t *flags, uint32_t n, uint32_t stride_bytes, uint32_t value, uint32_t timeout_ms) {
+    if (!c || !flags || n == 0 || stride_bytes % 4 != 0) return RZ_E_INVALID;
+    if (c->sticky != RZ_OK) return c->sticky;
+    CU(c, cudaSetDevice(c->device));
+    FrameState *dfs = reinterpret_cast<FrameState *>(c->d_state);
+    wait_flags_kernel<<<(n + 31) / 32, 32, 0, c->stream>>>(flags, n, stride_bytes / 4, value,
+                                                           (unsigned long long)(timeout_ms ? timeout_ms : 2000u) * 1000000ull, &dfs->peer_timeout);
+    c->launches++;
+    CU(c, cudaGetLastError());
     return RZ_OK;
 }
 

@@ -507,6 +507,39 @@ __global__ void __launch_bounds__(NT) order_kernel(FrameParams P) {
     P.busy[(size_t)b * P.tiles_x * P.tiles_y + base + __popc(peers & lanemask_lt())] = tile;
 }
 
+// ---- completion flags over peer memory (screen-space sharding, one process per GPU) ----
+// A rank whose tile kernel stored its rows straight into another GPU's image (NVLink peer stores) raises
+// flag[rank] there; the owner of the image spins until every flag has reached the frame's sequence number.
+// Launched WITHOUT programmatic serialization: the stream order guarantees the tile kernel has completed.
+struct FlagList {
+    uint32_t *p[16];
+};
+__global__ void signal_kernel(FlagList flags, uint32_t n, uint32_t value) {
+    if (threadIdx.x >= n) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.p[threadIdx.x]), "r"(value) : "memory");
+}
+// *timed_out is set (and the kernel returns) if a flag does not arrive within timeout_ns: a dead peer must
+// not hang the GPU.
+__global__ void wait_flags_kernel(const uint32_t *flags, uint32_t n, uint32_t stride_words, uint32_t value, unsigned long long timeout_ns,
+                                  uint32_t *timed_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + (size_t)i * stride_words) : "memory");
+        if ((int32_t)(v - value) >= 0) break;
+        __nanosleep(200);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeout_ns) {
+            atomicOr(timed_out, 1u);
+            break;
+        }
+    }
+}
+
 // First kernel of a frame: zero the per-frame part of the frame state and the tile counters.
 __global__ void __launch_bounds__(NT) frame_begin_kernel(uint4 *p, uint32_t n16) {
     pdl_launch();

@@ -48,7 +48,8 @@ constexpr int CNT_STRIPES = 32; // counters are striped over CTAs to spread the 
 struct FrameState {
     unsigned long long counters[CNT_STRIPES][16];
     uint32_t err;         // sticky ERR_* flags
-    uint32_t pad0[3];
+    uint32_t peer_timeout; // set by wait_flags_kernel when a peer's flag did not arrive
+    uint32_t pad0[2];
     uint32_t n_clipq;     // triangles queued for the clip kernel           <- per-frame part starts here
     uint32_t n_large;     // large-triangle binning work items
     uint32_t n_clip_attr; // AttrRec slots handed out to clipped triangles

@@ -34,13 +34,14 @@ COUNTER_FIELDS = (
 ABI_SYMBOLS = (
     "rz_create", "rz_destroy", "rz_set_stream", "rz_bind_texture", "rz_write_block", "rz_read_block",
     "rz_mesh_create", "rz_mesh_destroy", "rz_render", "rz_render_host", "rz_framebuffer",
-    "rz_framebuffer_async", "rz_framebuffer_host_async", "rz_sync", "rz_set_row_range", "rz_tile_width", "rz_tile_height",
+    "rz_framebuffer_async", "rz_framebuffer_host_async", "rz_sync", "rz_shared_alloc", "rz_shared_open",
+    "rz_shared_close", "rz_shared_free", "rz_signal", "rz_wait_flags", "rz_set_row_range", "rz_tile_width", "rz_tile_height",
     "rz_counters", "rz_reset_counters", "rz_timings", "rz_launch_count", "rz_debug_capture",
     "rz_debug_read", "rz_debug_tile_times", "rz_debug_vertex_stage", "rz_last_error", "rz_version",
 )
 
 ERROR_NAMES = {0: "RZ_OK", -1: "RZ_E_INVALID", -2: "RZ_E_CUDA", -3: "RZ_E_NO_DEVICE", -4: "RZ_E_TEXTURE",
-               -5: "RZ_E_INDEX", -6: "RZ_E_CAPACITY", -7: "RZ_E_NOMEM"}
+               -5: "RZ_E_INDEX", -6: "RZ_E_CAPACITY", -7: "RZ_E_NOMEM", -8: "RZ_E_PEER"}
 
 
 class RzError(RuntimeError):
@@ -93,6 +94,12 @@ def load_library() -> C.CDLL:
     L.rz_framebuffer_async.argtypes = [vp, vp, C.POINTER(vp)]
     L.rz_framebuffer_host_async.argtypes = [vp, vp]
     L.rz_sync.argtypes = [vp]
+    L.rz_shared_alloc.argtypes = [vp, C.c_uint64, C.POINTER(vp), u8p]
+    L.rz_shared_open.argtypes = [vp, u8p, C.POINTER(vp)]
+    L.rz_shared_close.argtypes = [vp, vp]
+    L.rz_shared_free.argtypes = [vp, vp]
+    L.rz_signal.argtypes = [vp, C.POINTER(vp), C.c_uint32, C.c_uint32]
+    L.rz_wait_flags.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     L.rz_set_row_range.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.rz_tile_width.restype = C.c_uint32
     L.rz_tile_height.restype = C.c_uint32
@@ -281,6 +288,32 @@ class Renderer:
     def sync(self):
         self._check(self._L.rz_sync(self._ctx))
         self._keepalive.clear()
+
+    # ---- peer memory (screen-space sharding over NVLink, see include/rz.h) ----
+    def shared_alloc(self, nbytes: int) -> tuple[int, bytes]:
+        p, h = C.c_void_p(), (C.c_uint8 * 64)()
+        self._check(self._L.rz_shared_alloc(self._ctx, nbytes, C.byref(p), h))
+        return p.value, bytes(h)
+
+    def shared_open(self, handle: bytes) -> int:
+        p, h = C.c_void_p(), (C.c_uint8 * 64).from_buffer_copy(handle)
+        self._check(self._L.rz_shared_open(self._ctx, h, C.byref(p)))
+        return p.value
+
+    def shared_close(self, ptr: int):
+        self._check(self._L.rz_shared_close(self._ctx, ptr))
+
+    def shared_free(self, ptr: int):
+        self._check(self._L.rz_shared_free(self._ctx, ptr))
+
+    def signal(self, flag_ptrs, value: int):
+        """Raise up to 16 (local or peer-mapped) flags to `value` once all earlier work of the stream is done."""
+        ptrs = [flag_ptrs] if isinstance(flag_ptrs, int) else list(flag_ptrs)
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        self._check(self._L.rz_signal(self._ctx, arr, len(ptrs), value & 0xFFFFFFFF))
+
+    def wait_flags(self, flags_ptr: int, n: int, stride_bytes: int, value: int, timeout_ms: int = 0):
+        self._check(self._L.rz_wait_flags(self._ctx, flags_ptr, n, stride_bytes, value & 0xFFFFFFFF, timeout_ms))
 
     # ---- extras ----
     def set_stream(self, cuda_stream: int | None):

@@ -41,3 +41,100 @@ def gather_strips(strip, height: int, group=None):
     full = torch.empty((world * strip.shape[0],) + tuple(strip.shape[1:]), dtype=strip.dtype, device=strip.device)
     dist.all_gather_into_tensor(full, strip.contiguous(), group=group)
     return full[:height]
+
+
+FLAG_STRIDE = 128  # bytes between two ranks' flags (one cache line each)
+
+
+class PeerFrame:
+    """Tile-row sharding of ONE frame without a gather step: every rank's tile kernel stores its resolved rows
+    straight into the presenting rank's image over NVLink (CUDA IPC peer memory, include/rz.h), and completion
+    flags travel the same way.  `n_buffers` images alternate so a rank may start frame f+1 while the presenter
+    still consumes frame f.
+
+        pf = PeerFrame(renderer, group=None, root=0)       # collective: exchanges the IPC handles
+        for f in range(n): ... renderer.render(...); ptr = pf.finish_frame()   # presenter: device pointer of the
+                                                           # complete image (stream-ordered), others: None
+                           pf.release()                    # presenter: image consumed, peers may overwrite it
+    """
+
+    def __init__(self, renderer, group=None, root: int = 0, n_buffers: int = 2, timeout_ms: int = 2000):
+        import torch.distributed as dist
+
+        self.r, self.group, self.root, self.nbuf, self.timeout_ms = renderer, group, root, n_buffers, timeout_ms
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 16:
+            raise ValueError("PeerFrame supports up to 16 ranks (one node)")
+        W, H = renderer.width, renderer.height
+        from .render import tile_size
+
+        self.rows = row_range(self.rank, self.world, H, tile_size()[1])
+        self.image_bytes = W * H * 4
+        mine = {}
+        self._owned = []
+        if self.rank == root:
+            self.images = []
+            for _ in range(n_buffers):
+                p, h = renderer.shared_alloc(self.image_bytes)
+                self.images.append(p)
+                self._owned.append(p)
+                mine.setdefault("images", []).append(h)
+            self.flags, mine["flags"] = renderer.shared_alloc(FLAG_STRIDE * self.world)
+            self._owned.append(self.flags)
+        self.ack, mine["ack"] = renderer.shared_alloc(FLAG_STRIDE)  # the presenter raises it: "frame consumed"
+        self._owned.append(self.ack)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        self._mapped = []
+        if self.rank == root:
+            self.peer_acks = []
+            for q in range(self.world):
+                if q != root:
+                    p = renderer.shared_open(everyone[q]["ack"])
+                    self.peer_acks.append(p)
+                    self._mapped.append(p)
+        else:
+            self.images = [renderer.shared_open(h) for h in everyone[root]["images"]]
+            self.flags = renderer.shared_open(everyone[root]["flags"])
+            self._mapped += self.images + [self.flags]
+        self.frame = 0
+        if self.rows[0] < self.rows[1]:
+            renderer.set_row_range(*self.rows)
+
+    def finish_frame(self):
+        """Run the recorded draws for this rank's rows, storing them into the presenter's image."""
+        f, r = self.frame, self.r
+        img = self.images[f % self.nbuf]
+        seq = f + 1
+        if self.rank != self.root and f >= self.nbuf:
+            r.wait_flags(self.ack, 1, FLAG_STRIDE, f - self.nbuf + 1, self.timeout_ms)  # image buffer is free again
+        if self.rows[0] < self.rows[1]:
+            r.framebuffer_async(img + self.rows[0] * r.width * 4)
+        self.frame += 1
+        if self.rank != self.root:
+            r.signal(self.flags + self.rank * FLAG_STRIDE, seq)
+            return None
+        others = [q for q in range(self.world) if q != self.root]
+        if others and self.root == 0:  # flags[1..world) are contiguous: one wait kernel
+            r.wait_flags(self.flags + FLAG_STRIDE, self.world - 1, FLAG_STRIDE, seq, self.timeout_ms)
+        else:
+            for q in others:
+                r.wait_flags(self.flags + q * FLAG_STRIDE, 1, FLAG_STRIDE, seq, self.timeout_ms)
+        return img
+
+    def release(self):
+        """Presenter: the image returned by the last finish_frame() has been consumed (stream-ordered)."""
+        if self.rank == self.root and self.peer_acks:
+            self.r.signal(self.peer_acks, self.frame)
+
+    def close(self):
+        self.r.sync()
+        import torch.distributed as dist
+
+        dist.barrier(group=self.group)  # nobody unmaps / frees memory a peer may still be writing
+        for p in self._mapped:
+            self.r.shared_close(p)
+        dist.barrier(group=self.group)
+        for p in self._owned:
+            self.r.shared_free(p)
+        self._mapped, self._owned = [], []

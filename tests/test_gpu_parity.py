@@ -315,3 +315,68 @@ def test_cpp_host_demo_runs():
     o = oracle_render(scenes.default_scene(1.0))
     # libm vs Python trig may differ in the last bit of a matrix entry, so compare loosely
     assert abs(int(m.group(2)) - o["counters"]["n_samples_written"]) < 0.01 * o["counters"]["n_samples_written"]
+
+
+def test_peer_store_primitives_two_contexts_one_gpu():
+    """The screen-space sharding protocol of sharding.PeerFrame on ONE GPU: two contexts (two 'ranks', two
+    streams) store their tile rows into one shared image; completion and back-pressure travel through the
+    flag kernels (rz_signal / rz_wait_flags).  The assembled frames equal the oracle's frames."""
+    import torch
+
+    from rusterizer_b200.render import Renderer
+
+    cams = scenes.orbit_cameras(8)
+    s = scenes.sphere_scene(97, 49, width=320, height=192)
+    mesh = s.draws[0].mesh
+    want = [oracle_render(scenes.sphere_scene(97, 49, width=320, height=192, camera=c))["fb"] for c in cams[:4]]
+    ctx = []
+    for q in range(2):
+        r = Renderer(s.width, s.height)
+        r.uniforms().bind_texture(0, s.texture)
+        b = r.uniforms().write_block()
+        b.projection, b.world = s.projection, s.draws[0].world
+        r.set_row_range(*( (0, 96) if q == 0 else (96, 192) ))
+        ctx.append((r, b))
+    root = ctx[0][0]
+    img, handle = root.shared_alloc(s.width * s.height * 4)
+    assert len(handle) == 64
+    flags, _ = root.shared_alloc(256)
+    ack, _ = ctx[1][0].shared_alloc(128)
+
+    class _Raw:
+        __cuda_array_interface__ = {"shape": (s.height, s.width), "typestr": "<i4", "data": (img, False), "version": 3}
+
+    view = torch.as_tensor(_Raw(), device="cuda")
+    outs = []
+    for f in range(4):
+        seq = f + 1
+        for q, (r, b) in enumerate(ctx):
+            b.view = cams[f].get_view_matrix()
+            r.render(mesh, 0, 0)
+        # "rank 1": wait until the presenter has consumed the previous frame, store rows, raise its flag
+        r1 = ctx[1][0]
+        if f >= 1:
+            r1.wait_flags(ack, 1, 128, f)
+        r1.framebuffer_async(img + 96 * s.width * 4)
+        r1.signal(flags + 128, seq)
+        # presenter: own rows, wait for rank 1, consume (copy out on its stream), acknowledge
+        root.framebuffer_async(img)
+        root.wait_flags(flags + 128, 1, 128, seq)
+        root.sync()
+        outs.append(view.cpu().numpy().view(np.uint32).copy())
+        root.signal([ack], seq)
+    for r, _ in ctx:
+        r.sync()
+    for f in range(4):
+        assert np.array_equal(outs[f], want[f]), f"frame {f}"
+    # a flag that never arrives: the wait kernel gives up and rz_sync reports RZ_E_PEER
+    from rusterizer_b200.render import RzError
+
+    root.wait_flags(flags + 128, 1, 128, 1000, timeout_ms=50)
+    with pytest.raises(RzError) as ei:
+        root.sync()
+    assert ei.value.code == -8
+    root.sync()  # the condition is cleared once reported
+    root.shared_free(img); root.shared_free(flags); ctx[1][0].shared_free(ack)
+    for r, _ in ctx:
+        r.close()
