@@ -245,7 +245,7 @@ def main():
     blk.world = scene.draws[0].world
 
     tiles_mode = args.mode == "tiles"
-    gather_buf = None
+    gather_buf, pf = None, None
     own_rows = H
     if tiles_mode:
         th = 16
@@ -256,7 +256,6 @@ def main():
         strip = torch.empty((rows_per, W), dtype=torch.int32, device="cuda")
         use_peer = n_gpus > 1 and args.gather == "peer"
         gather_buf = torch.empty((n_gpus * rows_per, W), dtype=torch.int32, device="cuda") if n_gpus > 1 and not use_peer else None
-        pf = None
         if use_peer:
             from rusterizer_b200.sharding import PeerFrame
 
@@ -550,7 +549,7 @@ def main():
                         "peak": fp32_peak, "unit": "TFLOP/s (non-FMA f32)", "frac": f_alg / (ms_per_step / 1e3) / 1e12 / fp32_peak,
                         "formula": "28*Nv + 40*Nt_in + 60*Nt_setup + 72*N_bbox_px + 30*N_samples + 180*N_shaded_px (texture FS)"}
     cb = None
-    if not args.no_cpu_baseline and not tiles_mode:
+    if not args.no_cpu_baseline and not tiles_mode and n_gpus == 1:  # rank 0 at N=1 only (bounded sample)
         cb = cpu_baseline(scene, budget_s=args.cpu_budget)
 
     line = {

@@ -73,7 +73,6 @@ struct rz_ctx {
     ShadeRec *d_shade = nullptr;
     AttrRec *d_attrs = nullptr;
     DrawInfo *d_draws = nullptr;
-    std::vector<DrawInfo> h_draws;
     uint32_t draw_cap = 0, attr_cap = 0;
     LargeItem *d_large = nullptr;
     uint32_t *d_out = nullptr;
@@ -480,19 +479,6 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
             CU(c, cudaMalloc(&c->d_draws, (size_t)cap * sizeof(DrawInfo)));
             c->draw_cap = cap;
         }
-        c->h_draws.resize(c->draws.size());
-        uint32_t base = 0;
-        for (size_t i = 0; i < c->draws.size(); i++) {
-            DrawInfo &di = c->h_draws[i];
-            const rz_mesh *m = c->draws[i].mesh;
-            di.attr = m->d_attr; di.pos = m->d_pos; di.idx = m->d_idx;
-            di.nv = m->nv; di.tri_base = base; di.fs = c->draws[i].fs; di.pad = 0;
-            memcpy(di.M, c->draws[i].M, 64);
-            base += (uint32_t)(m->n_idx / 3);
-        }
-        if (!c->h_draws.empty())
-            CU(c, cudaMemcpyAsync(c->d_draws, c->h_draws.data(), c->h_draws.size() * sizeof(DrawInfo),
-                                  cudaMemcpyHostToDevice, c->stream));
     }
     FrameParams P = make_params(c, out_base);
     cudaStream_t st = c->stream;
@@ -859,6 +845,7 @@ int rz_debug_vertex_stage(rz_ctx *c, const rz_mesh *mesh, float *out_clip) {
     FrameParams P = make_params(c, c->d_out);
     DrawParams D;
     memset(&D, 0, sizeof D);
+    D.draw = 0xFFFFFFFFu; // no per-draw table entry
     float pv[16];
     mat4_mul(c->proj, c->view, pv);
     mat4_mul(pv, c->world, D.M);

@@ -235,6 +235,15 @@ __global__ void __launch_bounds__(NT) vertex_kernel(FrameParams P, DrawParams D,
     pdl_launch();
     pdl_wait();
     for (uint32_t i = blockIdx.x * NT + threadIdx.x; i < n16; i += gridDim.x * NT) zero16[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && D.draw != 0xFFFFFFFFu) {
+        // per-draw table entry for the clip and tile kernels, written on the device: a host-side copy of the
+        // table would cost a host-stream synchronisation per frame (pageable cudaMemcpyAsync)
+        DrawInfo *di = const_cast<DrawInfo *>(P.draws) + D.draw;
+        di->attr = D.attr; di->pos = D.pos; di->idx = D.idx;
+        di->nv = D.nv; di->tri_base = D.tri_base; di->fs = D.fs; di->pad = 0u;
+#pragma unroll
+        for (int k = 0; k < 16; k++) di->M[k] = D.M[k];
+    }
     // VERTEX_PER_THREAD vertices per thread, a CTA-strided chunk each: all position loads are issued before
     // the first use, so one wave of CTAs keeps enough bytes in flight to stream the mesh from HBM
     float x[VERTEX_PER_THREAD], y[VERTEX_PER_THREAD], z[VERTEX_PER_THREAD];
