@@ -201,6 +201,8 @@ def main():
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="tiles mode, N>1: 'peer' = tile kernels store their rows straight into rank 0's image over NVLink "
                          "(CUDA IPC peer memory + flag kernels); 'nccl' = local strips + one all_gather")
+    ap.add_argument("--band", type=int, default=4,
+                    help="tiles mode with --gather peer: tile rows per interleaved band (0 = contiguous row ranges)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     args = ap.parse_args()
@@ -259,7 +261,8 @@ def main():
         if use_peer:
             from rusterizer_b200.sharding import PeerFrame
 
-            pf = PeerFrame(r, root=0, n_buffers=2)
+            pf = PeerFrame(r, root=0, n_buffers=2, interleave_band=args.band)
+            own_rows = rows_per  # interleaved bands: the same number of rows per rank
         cams = [Camera()] * (K + Wm)
     elif n_gpus > 1:
         sweep = scenes.orbit_cameras(1024)
@@ -445,7 +448,7 @@ def main():
         dist.barrier()
     if pf is not None:
         pf.close()
-        r.set_row_range(r0, r1)
+        r.set_row_range(r0, r1)  # the e2e leg below runs each rank's contiguous strip
 
     # ---- e2e: host buffers in, host image out, every step (pinned memory) ----
     pos_h = torch.from_numpy(mesh.vertices).pin_memory()
@@ -557,7 +560,8 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if tiles_mode else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, scene),
         "gsamples_per_s": gsamples, "ms_per_frame": ms_per_step, "frame_latency_ms": frame_latency_ms,
-        "gather": (args.gather if tiles_mode and n_gpus > 1 else None), "assembled_frame_matches_single_gpu": assembled_ok,
+        "gather": (args.gather if tiles_mode and n_gpus > 1 else None),
+        "interleave_band_tile_rows": (args.band if tiles_mode and n_gpus > 1 and args.gather == "peer" else None), "assembled_frame_matches_single_gpu": assembled_ok,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(e2.item()) / e2e_steps * 1e3, "steps": e2e_steps,

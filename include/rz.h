@@ -161,6 +161,12 @@ int rz_shared_free(rz_ctx *ctx, void *dev_ptr);
 int rz_signal(rz_ctx *ctx, uint32_t *const *flags, uint32_t n, uint32_t value); /* n <= 16 flags, one kernel */
 int rz_wait_flags(rz_ctx *ctx, const uint32_t *flags, uint32_t n, uint32_t stride_bytes, uint32_t value,
                   uint32_t timeout_ms);
+/* Interleaved screen-space sharding: this ctx owns the bands k of `band_tile_rows` tile rows with
+ * k % world == rank (inside its row range, normally the whole frame), which balances a centred object
+ * across the GPUs; only owned tiles are rasterised, resolved and written, so with rz_framebuffer_async
+ * every rank passes the FULL image (e.g. the peer-mapped one) as device_dst.  band_tile_rows = 0 or
+ * world <= 1 switches interleaving off. */
+int rz_set_row_interleave(rz_ctx *ctx, uint32_t band_tile_rows, uint32_t rank, uint32_t world);
 uint32_t rz_tile_width(void);
 uint32_t rz_tile_height(void);
 

@@ -48,6 +48,7 @@ struct rz_ctx {
     int device = 0;
     uint32_t W = 0, H = 0, tiles_x = 0, tiles_y = 0;
     uint32_t row_begin = 0, row_end = 0;
+    uint32_t il_band = 0, il_rank = 0, il_world = 1;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     float world[16], view[16], proj[16];
     std::vector<Texture> textures;
@@ -430,6 +431,7 @@ static FrameParams make_params(rz_ctx *c, uint32_t *out_base) {
     P.W = c->W; P.H = c->H;
     P.tiles_x = c->tiles_x; P.tiles_y = c->tiles_y;
     P.row_begin = c->row_begin; P.row_end = c->row_end;
+    P.il_band = c->il_band; P.il_rank = c->il_rank; P.il_world = c->il_world;
     P.ty_begin = c->row_begin / TH;
     P.ty_end = (c->row_end + TH - 1) / TH;
     P.rec_cap = c->rec_cap; P.bin_cap = c->bin_cap; P.large_cap = c->large_cap;
@@ -633,6 +635,7 @@ int rz_framebuffer_async(rz_ctx *c, uint32_t *device_dst, const uint32_t **out_d
     if (c->sticky != RZ_OK) return c->sticky;
     CU(c, cudaSetDevice(c->device));
     // an external destination holds only this ctx's rows [row_begin,row_end), starting at device_dst
+    // (with interleaved bands the row range is the whole frame, so device_dst is the full image)
     uint32_t *base = device_dst ? device_dst - (size_t)c->row_begin * c->W : c->d_out;
     int rc = enqueue_frame(c, base, false);
     end_frame(c);
@@ -764,6 +767,17 @@ int rz_set_row_range(rz_ctx *c, uint32_t row_begin, uint32_t row_end) {
         return fail(c, RZ_E_INVALID, "rz_set_row_range: rows must be tile-aligned (%d) and inside the framebuffer", TH);
     c->row_begin = row_begin;
     c->row_end = row_end;
+    return RZ_OK;
+}
+
+int rz_set_row_interleave(rz_ctx *c, uint32_t band_tile_rows, uint32_t rank, uint32_t world) {
+    if (!c) return RZ_E_INVALID;
+    if (band_tile_rows == 0 || world <= 1) {
+        c->il_band = 0; c->il_rank = 0; c->il_world = 1;
+        return RZ_OK;
+    }
+    if (rank >= world) return fail(c, RZ_E_INVALID, "rz_set_row_interleave: rank %u >= world %u", rank, world);
+    c->il_band = band_tile_rows; c->il_rank = rank; c->il_world = world;
     return RZ_OK;
 }
 

@@ -80,7 +80,11 @@ __device__ __forceinline__ void emit_setup(const FrameParams &P, const DrawParam
     b.y1 = min(b.y1, P.row_end);
     if (b.x0 >= b.x1 || b.y0 >= b.y1) return;
     const uint32_t bw = b.x1 - b.x0, bh = b.y1 - b.y0;
-    lc.bbox += (unsigned long long)bw * bh;
+    {
+        const uint32_t rows = owned_rows(P, b.y0, b.y1);
+        if (rows == 0u) return; // touches none of this ctx's interleaved bands
+        lc.bbox += (unsigned long long)bw * rows;
+    }
 
     // ---- exact culls (results identical to walking the bbox) ----
     // (1) Back-facing with a rigorous margin.  The three edge functions of any sample sum to the
@@ -107,11 +111,16 @@ __device__ __forceinline__ void emit_setup(const FrameParams &P, const DrawParam
             // (2) thin / tiny triangles usually touch no sample at all: rasterise them exactly right
             // here so they never reach a tile list (pole slivers of a UV-sphere, distant meshes)
             for (uint32_t Y = b.y0; Y < b.y1; Y++)
-                for (uint32_t X = b.x0; X < b.x1; X++)
+                for (uint32_t X = b.x0; X < b.x1 && owns_tile_row(P, Y / TH); X++)
                     if (coverage_mask(s, (int)X, (int)Y)) tmask |= 1u << (((Y / TH - ty0) << 1) | (X / TW - tx0));
             if (!tmask) return; // contributes nothing (its bbox pixels are already counted)
         } else {
             tmask = 1u | (tx1 > tx0 ? 2u : 0u) | (ty1 > ty0 ? 4u : 0u) | ((tx1 > tx0 && ty1 > ty0) ? 8u : 0u);
+            if (P.il_band) {
+                if (!owns_tile_row(P, ty0)) tmask &= ~3u;
+                if (!owns_tile_row(P, ty0 + 1)) tmask &= ~12u;
+                if (!tmask) return;
+            }
         }
     }
 
@@ -477,7 +486,7 @@ __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
             const uint32_t tx = tx0 + t % ntx, ty = li.ty0 + t / ntx;
             const uint32_t X0 = max(b.x0, tx * TW), X1 = min(b.x1, tx * TW + TW);
             const uint32_t Y0 = max(b.y0, ty * TH), Y1 = min(b.y1, ty * TH + TH);
-            if (X0 >= X1 || Y0 >= Y1) continue;
+            if (X0 >= X1 || Y0 >= Y1 || !owns_tile_row(P, ty)) continue;
             const float sx_lo = fadd((float)X0, 0.125f), sx_hi = fadd((float)(X1 - 1), 0.875f);
             const float sy_lo = fadd((float)Y0, 0.125f), sy_hi = fadd((float)(Y1 - 1), 0.875f);
             bool keep = true;

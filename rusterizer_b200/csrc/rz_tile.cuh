@@ -671,7 +671,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
         const uint32_t shard_tiles = P.tiles_x * (P.ty_end - P.ty_begin);
         for (uint32_t i = blockIdx.x * (NT / 32) + warp; i < shard_tiles; i += gridDim.x * (NT / 32)) {
             const uint32_t t = P.ty_begin * P.tiles_x + i;
-            if (P.tile_count[t] != 0u) continue;
+            if (P.tile_count[t] != 0u || !owns_tile_row(P, t / P.tiles_x)) continue;
             const int x0 = (int)(t % P.tiles_x) * TW, y0 = (int)(t / P.tiles_x) * TH;
             if ((P.W & 3u) == 0u) {
 #pragma unroll

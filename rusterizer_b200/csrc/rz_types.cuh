@@ -113,6 +113,7 @@ struct FrameParams {
     uint32_t tiles_x, tiles_y;   // tile grid of the whole framebuffer
     uint32_t ty_begin, ty_end;   // tile rows owned by this ctx (screen-space shard)
     uint32_t row_begin, row_end; // same in pixel rows
+    uint32_t il_band, il_rank, il_world; // interleaved ownership of tile-row bands (il_band == 0: off), see owns_tile_row()
     uint32_t rec_cap, bin_cap, large_cap;
     FrameState *fs;
     uint32_t *tile_count;        // [tiles_x * tiles_y]
@@ -132,6 +133,22 @@ struct FrameParams {
     unsigned long long *dbg_tile_time; // optional [tiles][4]: tile id | n << 32, start ns, end ns, SM id
     TexInfo tex0;
 };
+
+// Screen-space sharding: besides the contiguous row range a ctx may own every il_world-th band of il_band
+// tile rows (band k belongs to rank k % il_world), which balances a centred object across the GPUs.
+__host__ __device__ inline bool owns_tile_row(const FrameParams &P, uint32_t ty) {
+    return P.il_band == 0u || (ty / P.il_band) % P.il_world == P.il_rank;
+}
+// number of owned pixel rows in [y0, y1) (rows inside the ctx's row range)
+__host__ __device__ inline uint32_t owned_rows(const FrameParams &P, uint32_t y0, uint32_t y1) {
+    if (P.il_band == 0u) return y1 - y0;
+    const uint32_t band_px = P.il_band * TH, period = band_px * P.il_world, lo = P.il_rank * band_px;
+    // f(y) = owned rows in [0, y)
+    const uint32_t r1 = y1 % period, r0 = y0 % period;
+    const uint32_t f1 = (y1 / period) * band_px + (r1 > lo ? (r1 - lo < band_px ? r1 - lo : band_px) : 0u);
+    const uint32_t f0 = (y0 / period) * band_px + (r0 > lo ? (r0 - lo < band_px ? r0 - lo : band_px) : 0u);
+    return f1 - f0;
+}
 
 // One draw call (Renderer::render, render.rs:98-114)
 struct DrawParams {

@@ -58,7 +58,8 @@ class PeerFrame:
                            pf.release()                    # presenter: image consumed, peers may overwrite it
     """
 
-    def __init__(self, renderer, group=None, root: int = 0, n_buffers: int = 2, timeout_ms: int = 2000):
+    def __init__(self, renderer, group=None, root: int = 0, n_buffers: int = 2, timeout_ms: int = 2000,
+                 interleave_band: int = 0):
         import torch.distributed as dist
 
         self.r, self.group, self.root, self.nbuf, self.timeout_ms = renderer, group, root, n_buffers, timeout_ms
@@ -68,7 +69,10 @@ class PeerFrame:
         W, H = renderer.width, renderer.height
         from .render import tile_size
 
-        self.rows = row_range(self.rank, self.world, H, tile_size()[1])
+        # interleave_band > 0: rank q owns the bands k of `interleave_band` tile rows with k % world == q (balanced
+        # for a centred object; peer stores make the strided destination free); 0: contiguous tile-row ranges
+        self.interleave_band = interleave_band if self.world > 1 else 0
+        self.rows = (0, H) if self.interleave_band else row_range(self.rank, self.world, H, tile_size()[1])
         self.image_bytes = W * H * 4
         mine = {}
         self._owned = []
@@ -100,6 +104,7 @@ class PeerFrame:
         self.frame = 0
         if self.rows[0] < self.rows[1]:
             renderer.set_row_range(*self.rows)
+        renderer.set_row_interleave(self.interleave_band, self.rank, self.world)
 
     def finish_frame(self):
         """Run the recorded draws for this rank's rows, storing them into the presenter's image."""
@@ -132,6 +137,7 @@ class PeerFrame:
         import torch.distributed as dist
 
         dist.barrier(group=self.group)  # nobody unmaps / frees memory a peer may still be writing
+        self.r.set_row_interleave(0, 0, 1)
         for p in self._mapped:
             self.r.shared_close(p)
         dist.barrier(group=self.group)
