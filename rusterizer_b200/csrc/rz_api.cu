@@ -441,6 +441,7 @@ static FrameParams make_params(rz_ctx *c, uint32_t *out_base) {
     P.bins = c->d_bins; P.recs = c->d_recs; P.shade = c->d_shade; P.clipq = c->d_clipq; P.attrs = c->d_attrs; P.large = c->d_large;
     P.draws = c->d_draws; P.attr_cap = c->attr_cap;
     P.out = out_base;
+    P.spread_clears = (out_base != c->d_out && out_base != c->d_out_ring[1]) ? 1u : 0u;
     if (c->debug) {
         P.dbg_depth = c->d_dbg_depth; P.dbg_color = c->d_dbg_color; P.dbg_owner = c->d_dbg_owner;
         P.dbg_tile_time = c->d_dbg_time;

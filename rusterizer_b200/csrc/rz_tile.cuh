@@ -215,6 +215,7 @@ struct TileSmemT {
     uint32_t head[TILE_PX];               // per-pixel fragment list heads; reused as resolve staging
     uint32_t scan[NT / 32];
     uint32_t first_big, first_small, nfrag, ovf, cur_tile;
+    uint32_t clr_cursor[NT / 32];         // per-warp cursor of the empty-tile clears
 };
 
 // Sort the tile's list by order key (in shared memory when it fits, else in place in HBM) and
@@ -231,6 +232,49 @@ __device__ __forceinline__ void sort_tile_list(SM &S, unsigned long long *bin, i
         block_sort(bin, n);
     }
     __syncthreads();
+}
+
+// Tiles nothing was binned into: the box filter of four clear samples is the clear colour
+// (buffers.rs:5,111-125).  A warp handles a GROUP of 8 horizontally adjacent tiles (4 lanes per tile, one
+// 128-bit store per lane and row), so a row of empty tiles leaves the SM as 512 contiguous bytes -- full
+// lines for HBM and, when the image lives in a peer GPU's memory, full-size NVLink write packets.  Every warp
+// walks its own strided slice of the shard's groups (cursor g), at most max_visits groups per call.
+constexpr int CLEAR_GROUP = 8;
+template <bool DBG>
+__device__ __forceinline__ void clear_empty_tiles(const FrameParams &P, int lane, uint32_t &g, uint32_t stride, uint32_t max_visits) {
+    const uint32_t groups_x = (P.tiles_x + CLEAR_GROUP - 1) / CLEAR_GROUP;
+    const uint32_t shard_groups = groups_x * (P.ty_end - P.ty_begin);
+    for (uint32_t n = 0; g < shard_groups && n < max_visits; g += stride, n++) {
+        const uint32_t ty = P.ty_begin + g / groups_x, tx = (g % groups_x) * CLEAR_GROUP + (uint32_t)lane / 4u;
+        if (!owns_tile_row(P, ty)) continue;
+        const bool empty = tx < P.tiles_x && P.tile_count[ty * P.tiles_x + tx] == 0u;
+        if (!empty) continue;
+        const int y0 = (int)ty * TH, xq = (int)tx * TW + (lane & 3) * 4;
+        if ((P.W & 3u) == 0u) {
+            if (xq < (int)P.W)
+#pragma unroll 4
+                for (int row = 0; row < TH; row++)
+                    if (y0 + row < (int)P.H)
+                        *reinterpret_cast<uint4 *>(&P.out[(size_t)(y0 + row) * P.W + xq]) =
+                            make_uint4(CLEAR_COLOR, CLEAR_COLOR, CLEAR_COLOR, CLEAR_COLOR);
+        } else {
+            for (int row = 0; row < TH; row++)
+                for (int k = 0; k < 4; k++)
+                    if (y0 + row < (int)P.H && xq + k < (int)P.W) P.out[(size_t)(y0 + row) * P.W + xq + k] = CLEAR_COLOR;
+        }
+        if (DBG) {
+            for (int row = 0; row < TH; row++)
+                for (int k = 0; k < 4; k++) {
+                    if (y0 + row >= (int)P.H || xq + k >= (int)P.W) continue;
+                    const size_t o = ((size_t)(y0 + row) * P.W + xq + k) * 4;
+                    for (int q = 0; q < 4; q++) {
+                        if (P.dbg_depth) P.dbg_depth[o + q] = CLEAR_DEPTH;
+                        if (P.dbg_color) P.dbg_color[o + q] = CLEAR_COLOR;
+                        if (P.dbg_owner) P.dbg_owner[o + q] = NO_OWNER;
+                    }
+                }
+        }
+    }
 }
 
 template <bool DBG>
@@ -257,6 +301,9 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
         }
     }
     const uint32_t n_busy = bucket_end[ORDER_BUCKETS - 1];
+    // empty-tile clears: with a caller-owned destination they are spread over the loop (a few tile groups per
+    // rasterised tile, cursor kept in shared memory), the rest follows after the loop
+    if (lane == 0) S.clr_cursor[warp] = blockIdx.x * (NT / 32) + warp;
     for (;;) {
     __syncthreads(); // previous tile fully retired (also covers S.lut on the first trip)
     if (tid == 0) S.cur_tile = atomicAdd(&P.fs->tile_cursor, 1u);
@@ -662,45 +709,21 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
         o[5] = t_ph[4] > t_start ? t_ph[4] - t_start : 0;
         o[6] = 0; o[7] = 0;
     }
+    if (P.spread_clears) {
+        const uint32_t stride = gridDim.x * (NT / 32), iters = max(1u, (n_busy + gridDim.x - 1) / gridDim.x);
+        const uint32_t groups = ((P.tiles_x + CLEAR_GROUP - 1) / CLEAR_GROUP) * (P.ty_end - P.ty_begin);
+        uint32_t g = S.clr_cursor[warp];
+        clear_empty_tiles<DBG>(P, lane, g, stride, ((groups + stride - 1) / stride + iters) / iters);
+        __syncwarp();
+        if (lane == 0) S.clr_cursor[warp] = g;
+    }
     } // persistent tile loop
 
-    // ---- phase 2: tiles nothing was binned into.  The box filter of four clear samples is the clear
-    // colour (buffers.rs:5,111-125): one warp writes such a tile as 64 128-bit stores.  Done after the
-    // persistent loop, so these stores fill the tail of the kernel instead of delaying its start. ----
+    // ---- the rest of the tiles nothing was binned into ----
     {
-        const uint32_t shard_tiles = P.tiles_x * (P.ty_end - P.ty_begin);
-        for (uint32_t i = blockIdx.x * (NT / 32) + warp; i < shard_tiles; i += gridDim.x * (NT / 32)) {
-            const uint32_t t = P.ty_begin * P.tiles_x + i;
-            if (P.tile_count[t] != 0u || !owns_tile_row(P, t / P.tiles_x)) continue;
-            const int x0 = (int)(t % P.tiles_x) * TW, y0 = (int)(t / P.tiles_x) * TH;
-            if ((P.W & 3u) == 0u) {
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int e = lane + 32 * h, row = e / (TW / 4), q = e % (TW / 4);
-                    const int Yr = y0 + row, Xq = x0 + q * 4;
-                    if (Yr < (int)P.H && Xq < (int)P.W)
-                        *reinterpret_cast<uint4 *>(&P.out[(size_t)Yr * P.W + Xq]) =
-                            make_uint4(CLEAR_COLOR, CLEAR_COLOR, CLEAR_COLOR, CLEAR_COLOR);
-                }
-            } else {
-                for (int e = lane; e < TILE_PX; e += 32) {
-                    const int Yr = y0 + e / TW, Xq = x0 + e % TW;
-                    if (Yr < (int)P.H && Xq < (int)P.W) P.out[(size_t)Yr * P.W + Xq] = CLEAR_COLOR;
-                }
-            }
-            if (DBG) {
-                for (int e = lane; e < TILE_PX; e += 32) {
-                    const int Yr = y0 + e / TW, Xq = x0 + e % TW;
-                    if (Yr >= (int)P.H || Xq >= (int)P.W) continue;
-                    const size_t o = ((size_t)Yr * P.W + Xq) * 4;
-                    for (int k = 0; k < 4; k++) {
-                        if (P.dbg_depth) P.dbg_depth[o + k] = CLEAR_DEPTH;
-                        if (P.dbg_color) P.dbg_color[o + k] = CLEAR_COLOR;
-                        if (P.dbg_owner) P.dbg_owner[o + k] = NO_OWNER;
-                    }
-                }
-            }
-        }
+        __syncwarp();
+        uint32_t g = S.clr_cursor[warp];
+        clear_empty_tiles<DBG>(P, lane, g, gridDim.x * (NT / 32), 0xFFFFFFFFu);
     }
 
     // ---- counters: warp reduce -> per-warp partials -> one striped global RED per counter ----

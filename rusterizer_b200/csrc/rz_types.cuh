@@ -127,6 +127,8 @@ struct FrameParams {
     uint32_t attr_cap;
     LargeItem *large;
     uint32_t *out;               // resolved framebuffer u32[H][W]
+    uint32_t spread_clears;      // caller-owned destination (possibly a peer GPU's memory): empty-tile clears are
+                                 // issued a few per rasterised tile instead of as one burst at the end
     float *dbg_depth;            // optional [H][W][4]
     uint32_t *dbg_color;
     uint32_t *dbg_owner;
