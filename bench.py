@@ -201,7 +201,7 @@ def main():
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="tiles mode, N>1: 'peer' = tile kernels store their rows straight into rank 0's image over NVLink "
                          "(CUDA IPC peer memory + flag kernels); 'nccl' = local strips + one all_gather")
-    ap.add_argument("--band", type=int, default=4,
+    ap.add_argument("--band", type=int, default=16,
                     help="tiles mode with --gather peer: tile rows per interleaved band (0 = contiguous row ranges)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)

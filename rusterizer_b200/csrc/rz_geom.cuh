@@ -366,11 +366,12 @@ __global__ void __launch_bounds__(NT) clip_kernel(FrameParams P) {
     __shared__ unsigned long long s_bbox[NT / 32];
     pdl_launch();
     pdl_wait();
+    const uint32_t nq = min(P.fs->n_clipq, P.rec_cap);
+    if (nq == 0u) return; // nothing straddles a clip plane (the common case for a mesh inside the frustum)
     GeomLocal lc;
 #pragma unroll
     for (int k = 0; k < C_COUNT; k++) lc.c[k] = 0;
     lc.bbox = 0ull;
-    const uint32_t nq = min(P.fs->n_clipq, P.rec_cap);
     for (uint32_t qi = blockIdx.x * NT + threadIdx.x; qi < nq; qi += gridDim.x * NT) {
         const unsigned long long e = P.clipq[qi];
         const uint32_t t = (uint32_t)e;

@@ -248,30 +248,32 @@ __device__ __forceinline__ void clear_empty_tiles(const FrameParams &P, int lane
         const uint32_t ty = P.ty_begin + g / groups_x, tx = (g % groups_x) * CLEAR_GROUP + (uint32_t)lane / 4u;
         if (!owns_tile_row(P, ty)) continue;
         const bool empty = tx < P.tiles_x && P.tile_count[ty * P.tiles_x + tx] == 0u;
-        if (!empty) continue;
+        const unsigned emask = DBG ? __ballot_sync(0xffffffffu, empty) : 0u; // bit 4t: tile t of the group is empty
         const int y0 = (int)ty * TH, xq = (int)tx * TW + (lane & 3) * 4;
-        if ((P.W & 3u) == 0u) {
-            if (xq < (int)P.W)
+        if (empty) {
+            if ((P.W & 3u) == 0u) {
+                if (xq < (int)P.W)
 #pragma unroll 4
+                    for (int row = 0; row < TH; row++)
+                        if (y0 + row < (int)P.H)
+                            *reinterpret_cast<uint4 *>(&P.out[(size_t)(y0 + row) * P.W + xq]) =
+                                make_uint4(CLEAR_COLOR, CLEAR_COLOR, CLEAR_COLOR, CLEAR_COLOR);
+            } else {
                 for (int row = 0; row < TH; row++)
-                    if (y0 + row < (int)P.H)
-                        *reinterpret_cast<uint4 *>(&P.out[(size_t)(y0 + row) * P.W + xq]) =
-                            make_uint4(CLEAR_COLOR, CLEAR_COLOR, CLEAR_COLOR, CLEAR_COLOR);
-        } else {
-            for (int row = 0; row < TH; row++)
-                for (int k = 0; k < 4; k++)
-                    if (y0 + row < (int)P.H && xq + k < (int)P.W) P.out[(size_t)(y0 + row) * P.W + xq + k] = CLEAR_COLOR;
+                    for (int k = 0; k < 4; k++)
+                        if (y0 + row < (int)P.H && xq + k < (int)P.W) P.out[(size_t)(y0 + row) * P.W + xq + k] = CLEAR_COLOR;
+            }
         }
-        if (DBG) {
-            for (int row = 0; row < TH; row++)
-                for (int k = 0; k < 4; k++) {
-                    if (y0 + row >= (int)P.H || xq + k >= (int)P.W) continue;
-                    const size_t o = ((size_t)(y0 + row) * P.W + xq + k) * 4;
-                    for (int q = 0; q < 4; q++) {
-                        if (P.dbg_depth) P.dbg_depth[o + q] = CLEAR_DEPTH;
-                        if (P.dbg_color) P.dbg_color[o + q] = CLEAR_COLOR;
-                        if (P.dbg_owner) P.dbg_owner[o + q] = NO_OWNER;
-                    }
+        if (DBG && emask) { // parity instrumentation: the per-sample state of the empty tiles, coalesced over the group row
+            const int gx0 = (int)((g % groups_x) * CLEAR_GROUP) * TW;
+            for (int row = 0; row < TH && y0 + row < (int)P.H; row++)
+                for (int j = lane; j < CLEAR_GROUP * TW * 4; j += 32) { // sample j of the group row
+                    const int px = gx0 + j / 4;
+                    if (!((emask >> (4 * (j / (TW * 4)))) & 1u) || px >= (int)P.W) continue;
+                    const size_t o = ((size_t)(y0 + row) * P.W + px) * 4 + (j & 3);
+                    if (P.dbg_depth) P.dbg_depth[o] = CLEAR_DEPTH;
+                    if (P.dbg_color) P.dbg_color[o] = CLEAR_COLOR;
+                    if (P.dbg_owner) P.dbg_owner[o] = NO_OWNER;
                 }
         }
     }

@@ -1,0 +1,17 @@
+#!/bin/bash
+# tools/profile_round.sh TAG: the round's profiling passes on one B200 (run under gpurun).  Writes to gpurun_out/:
+#   launches_TAG.csv      ncu launch list (gpu__time_duration.sum, --clock-control none) of a short bench run
+#   prof_TAG.ncu-rep      one `--set full` capture of every kernel of one frame (source imported)
+#   bench_TAG.json/.err   the unprofiled bench line (with cpu_baseline), ref_TAG.json the --impl reference line
+tag=${1:-r01}
+mkdir -p gpurun_out
+python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
+python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/ref_$tag.json 2>> gpurun_out/bench_$tag.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_$tag.csv \
+    python bench.py --steps 5 --warmup 3 --no-cpu-baseline --inflight 1 > gpurun_out/ncu_launch_bench_$tag.log 2>&1
+# full capture: skip the warm-up frames (7 kernels per frame: vertex, geom, clip, large_bin, order, tile)
+ncu --set full --clock-control none --import-source on -k regex:'vertex_kernel|geom_kernel|clip_kernel|large_bin_kernel|order_kernel|tile_kernel' \
+    --launch-skip 30 --launch-count 6 -f -o gpurun_out/prof_$tag python bench.py --steps 3 --warmup 3 --no-cpu-baseline --inflight 1 \
+    > gpurun_out/ncu_full_$tag.log 2>&1
+python tools/tile_times.py > gpurun_out/tile_times_$tag.txt 2>&1
+ls -la gpurun_out | tail -8
