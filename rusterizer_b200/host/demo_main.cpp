@@ -1,9 +1,10 @@
 // demo_main.cpp -- the reference's `Mode::Demo` frame (main.rs:93-105,129-182) at a fixed `elapsed`,
 // driven through the C++ mirror of the crate API; writes the image the reference would hand to
-// minifb as a PPM instead of opening a window.
+// minifb as a PNG/PPM instead of opening a window.   usage: rz_demo [elapsed [out.png|out.ppm [texture.png]]]
 //   g++ -std=c++17 -O2 -ffp-contract=off demo_main.cpp -o rz_demo -L.. -lrz_b200 -Wl,-rpath,'$ORIGIN/..'
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 #include "rusterizer.hpp"
 
@@ -18,17 +19,8 @@ int main(int argc, char **argv) {
         block.view = camera.get_view_matrix();
         block.projection = rz::project(1.0f, 200.0f, (float)H / (float)W, 1.57079637050628662f); // main.rs:137-142
 
-        rz::Texture tex; // images/checkerboard.png decoded: 400x400 RGBA, 4x4 squares, top-left black
-        tex.width = tex.height = 400;
-        tex.texel_width = 4;
-        tex.buf.resize(400 * 400 * 4);
-        for (uint32_t y = 0; y < 400; y++)
-            for (uint32_t x = 0; x < 400; x++) {
-                const uint8_t v = ((x / 100 + y / 100) & 1) ? 255 : 0;
-                uint8_t *p = &tex.buf[(y * 400 + x) * 4];
-                p[0] = p[1] = p[2] = v;
-                p[3] = 255;
-            }
+        // images/checkerboard.png (main.rs:144): decoded from a file when given, else regenerated procedurally
+        const rz::Texture tex = argc > 3 ? rz::Texture::from_png_file(argv[3]) : rz::Texture::checkerboard();
         renderer.uniforms().bind_texture(0, tex);
 
         const rz::Mesh meshes[2] = {rz::cube(1.0f), rz::sphere(0.5f)};
@@ -50,19 +42,17 @@ int main(int argc, char **argv) {
         std::printf("rz_demo: %zux%zu elapsed=%.3f tris_in=%llu samples_written=%llu touched_px=%zu checksum=%016llx\n", W, H,
                     elapsed, (unsigned long long)c.n_tris_in, (unsigned long long)c.n_samples_written, touched,
                     (unsigned long long)sum);
-        if (out) {
-            FILE *f = std::fopen(out, "wb");
-            if (!f) return 2;
-            std::fprintf(f, "P6\n%zu %zu\n255\n", W, H);
-            for (uint32_t px : fb) {
-                const unsigned char rgb[3] = {(unsigned char)(px >> 16), (unsigned char)(px >> 8), (unsigned char)px};
-                std::fwrite(rgb, 1, 3, f);
-            }
-            std::fclose(f);
+        if (out) { // .png or .ppm by extension
+            const std::string path(out);
+            if (path.size() > 4 && path.substr(path.size() - 4) == ".png") renderer.save_png(path);
+            else renderer.save_ppm(path);
         }
         return touched > 1000 ? 0 : 3;
     } catch (const rz::Error &e) {
         std::fprintf(stderr, "rz_demo: error %d: %s\n", e.code, e.what());
+        return 1;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "rz_demo: %s\n", e.what());
         return 1;
     }
 }

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/rz.h"
+#include "rz_image.hpp"
 
 namespace rz {
 
@@ -124,10 +125,44 @@ inline Mesh sphere(float radius, uint32_t n_phi = 17, uint32_t n_theta = 9) { //
 struct Texture { // texture.rs:8-13: row-major u8[h][w][texel_width], origin top-left
     std::vector<uint8_t> buf;
     uint32_t width = 0, height = 0, texel_width = 4;
+
+    // Texture::from_png_file (texture.rs:26-45).  The reference hard-codes texel_width = 4 whatever the file
+    // holds (texture.rs:41), which is only right for RGBA files like images/checkerboard.png; here the width
+    // follows the decoded layout (3 for RGB, 4 for RGBA), the two layouts read_texel handles (texture.rs:47-63).
+    static Texture from_png_file(const std::string &path) {
+        image::Image img = image::read_png(path);
+        Texture t;
+        t.buf = std::move(img.pixels);
+        t.width = img.width; t.height = img.height; t.texel_width = img.channels;
+        return t;
+    }
+    // The decoded content of images/checkerboard.png: 400x400 RGBA, 4x4 squares of 100 px, top-left black.
+    static Texture checkerboard() {
+        Texture t;
+        t.width = t.height = 400;
+        t.texel_width = 4;
+        t.buf.resize(400 * 400 * 4);
+        for (uint32_t y = 0; y < 400; y++)
+            for (uint32_t x = 0; x < 400; x++) {
+                const uint8_t v = ((x / 100 + y / 100) & 1) ? 255 : 0;
+                uint8_t *p = &t.buf[(y * 400 + x) * 4];
+                p[0] = p[1] = p[2] = v;
+                p[3] = 255;
+            }
+        return t;
+    }
 };
 
 struct Camera { // camera.rs:3-54
     std::array<float, 3> pos{0, 0, -5}, up{0, 1, 0}, dir{0, 0, 1};
+    // Orbit constructor for camera sweeps (not in the reference, which only has Default): on a circle of
+    // `radius` in the xz-plane at `angle`, looking at the origin, up +y.  angle 0 is Camera::default().
+    static Camera orbit(float angle, float radius = 5.0f, float height = 0.0f) {
+        Camera c;
+        c.pos = {radius * std::sin(angle), height, -radius * std::cos(angle)};
+        c.dir = {-c.pos[0], -c.pos[1], -c.pos[2]};
+        return c;
+    }
     Mat4 get_view_matrix() const { // camera.rs:10-43
         auto norm = [](std::array<float, 3> v) {
             float acc = 0.0f;
@@ -199,6 +234,10 @@ class Renderer { // render.rs:38-127 without the minifb window
         check(rz_framebuffer(ctx_, fb_.data(), nullptr));
         return fb_;
     }
+
+    // Headless replacement of Renderer::display (render.rs:116-127): the last framebuffer() as a file
+    void save_png(const std::string &path) const { image::write_png(path, fb_.data(), width_, height_); }
+    void save_ppm(const std::string &path) const { image::write_ppm(path, fb_.data(), width_, height_); }
 
     rz_counters_t counters() {
         rz_counters_t c;

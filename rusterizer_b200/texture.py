@@ -33,10 +33,12 @@ class Texture:
 
     @classmethod
     def from_png_file(cls, path) -> "Texture":
-        """texture.rs:26-45 (decodes to RGBA8; the reference hard-codes texel_width = 4)."""
-        from PIL import Image  # host-side I/O only
+        """texture.rs:26-45.  The reference hard-codes texel_width = 4 whatever the file holds (texture.rs:41),
+        which is only right for RGBA files such as images/checkerboard.png; here the width follows the decoded
+        layout (RGB8 -> 3, RGBA8 -> 4), the two layouts read_texel handles (texture.rs:47-63)."""
+        from .image import read_png  # host-side I/O only
 
-        return cls(np.asarray(Image.open(path).convert("RGBA"), dtype=np.uint8))
+        return cls(read_png(path))
 
     @classmethod
     def checkerboard(cls) -> "Texture":

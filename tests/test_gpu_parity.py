@@ -301,15 +301,24 @@ def test_capacity_growth_dense_tile():
     check(s)
 
 
-def test_cpp_host_demo_runs():
-    """The C++ mirror of the crate API renders the Mode::Demo frame on the GPU (main.rs:93-105)."""
+def test_cpp_host_demo_runs(tmp_path):
+    """The C++ mirror of the crate API renders the Mode::Demo frame on the GPU (main.rs:93-105): texture loaded
+    from a PNG file (Texture::from_png_file, texture.rs:26-45), image written as PNG instead of a window."""
     import re
     import subprocess
     from pathlib import Path
 
+    from rusterizer_b200 import image
+    from rusterizer_b200.texture import Texture
+
     demo = Path(__file__).resolve().parent.parent / "rusterizer_b200" / "host" / "rz_demo"
-    p = subprocess.run([str(demo), "1.0"], capture_output=True, text=True)
+    tex_png, out_png = tmp_path / "checkerboard.png", tmp_path / "frame.png"
+    tex_png.write_bytes(image.encode_png(Texture.checkerboard().texels))
+    p = subprocess.run([str(demo), "1.0", str(out_png), str(tex_png)], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
+    frame = image.read_png(out_png)
+    m = re.search(r"touched_px=(\d+)", p.stdout)
+    assert frame.shape == (720, 1280, 3) and int((frame != 0x19).any(axis=2).sum()) == int(m.group(1))
     m = re.search(r"tris_in=(\d+) samples_written=(\d+) touched_px=(\d+)", p.stdout)
     assert m and int(m.group(1)) == 268
     o = oracle_render(scenes.default_scene(1.0))
