@@ -46,6 +46,14 @@ extern "C" {
 #define RZ_FS_TEXTURE 0 /* get_texture(0).sample(u, v)                    main.rs:69-71   */
 #define RZ_FS_COLOR 1   /* attr.color                                     main.rs:72      */
 #define RZ_FS_DEBUG 2   /* Color::grayscale(frag_coords.depths[0])        main.rs:73-75   */
+/* Shader registry beyond the crate's three closures.  The reference lets a fragment
+ * shader closure read any bound texture (Uniforms::get_texture(index), uniform.rs:35-37) and combine Colors
+ * with the operators of color.rs:75-123; as identifiers that becomes:
+ *   - a texture index in bits 8..15 of fs_id for the shaders that sample:  RZ_FS_WITH_TEXTURE(fs, index)
+ *   - RZ_FS_TEXTURE_BLEND: (get_texture(index).sample(u, v) + attr.color) / 2.0   (Color Add, Div<f32>) */
+#define RZ_FS_TEXTURE_BLEND 3
+#define RZ_FS_WITH_TEXTURE(fs, index) ((uint32_t)(fs) | ((uint32_t)(index) << 8))
+#define RZ_MAX_TEXTURES 32
 
 typedef struct rz_ctx rz_ctx;   /* Renderer + Rasterizer + Uniforms state (render.rs:38-45)  */
 typedef struct rz_mesh rz_mesh; /* a device-resident Mesh<WorldSpace>     (mesh.rs:5-12)     */

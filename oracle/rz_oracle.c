@@ -517,12 +517,16 @@ void orc_write_block(orc_ctx *c, const float *world, const float *view, const fl
     if (proj) memcpy(c->proj, proj, 64);
 }
 
-/* main.rs:67-77 : FS ids follow `enum FS` (main.rs:23-27): 0 Texture, 1 Color, 2 Debug */
+/* main.rs:67-77 : FS ids follow `enum FS` (main.rs:23-27): 0 Texture, 1 Color, 2 Debug.
+ * Registry extension (include/rz.h): bits 8..15 of fs_id = texture index for the sampling shaders
+ * (Uniforms::get_texture(index), uniform.rs:35-37); 3 = TextureBlend = (sample + attr.color) / 2.0 with the
+ * component-wise Color Add and Div<f32> of color.rs:88-111. */
 static int fragment_shader(orc_ctx *c, uint32_t fs_id, const float *fc_depths, const attr_t *a, float *rgba) {
-    switch (fs_id) {
+    const uint32_t shader = fs_id & 0xFFu, ti = (fs_id >> 8) & 0xFFu;
+    switch (shader) {
     case 0:
-        if (c->n_tex == 0) return -1;
-        tex_sample(c, &c->tex[0], a->v[4], a->v[5], rgba);
+        if (ti >= c->n_tex) return -1;
+        tex_sample(c, &c->tex[ti], a->v[4], a->v[5], rgba);
         return 0;
     case 1:
         rgba[0] = a->v[0]; rgba[1] = a->v[1]; rgba[2] = a->v[2]; rgba[3] = a->v[3];
@@ -531,6 +535,16 @@ static int fragment_shader(orc_ctx *c, uint32_t fs_id, const float *fc_depths, c
         rgba[0] = rgba[1] = rgba[2] = fc_depths[0];
         rgba[3] = 1.0f;
         return 0;
+    case 3: {
+        if (ti >= c->n_tex) return -1;
+        float t[4];
+        tex_sample(c, &c->tex[ti], a->v[4], a->v[5], t);
+        for (int k = 0; k < 4; k++) {
+            volatile float sum = t[k] + a->v[k]; /* Color + Color, color.rs:99-109 */
+            rgba[k] = sum / 2.0f;                /* Color / f32,   color.rs:88-97  */
+        }
+        return 0;
+    }
     default:
         return -1;
     }
@@ -614,8 +628,9 @@ static int rasterize_one(orc_ctx *c, const tri_t *raw, uint32_t fs_id, uint32_t 
  */
 int orc_render(orc_ctx *c, const float *pos, const float *attrs, uint32_t nv, const uint32_t *idx, uint64_t n_idx,
                uint32_t vs_id, uint32_t fs_id) {
-    if (vs_id != 0 || fs_id > 2) return -3;
-    if (fs_id == 0 && c->n_tex == 0) return -4;
+    if (vs_id != 0 || (fs_id & 0xFFu) > 3 || (fs_id >> 16) != 0) return -3;
+    if (((fs_id & 0xFFu) == 0 || (fs_id & 0xFFu) == 3) && ((fs_id >> 8) & 0xFFu) >= c->n_tex) return -4;
+    if (((fs_id & 0xFFu) == 1 || (fs_id & 0xFFu) == 2) && (fs_id >> 8) != 0) return -3;
     if (c->vs_cap < nv) {
         free(c->vs_out);
         c->vs_out = (float *)malloc((size_t)(nv ? nv : 1) * 16);

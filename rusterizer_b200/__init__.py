@@ -17,6 +17,7 @@ from .mesh import Mesh, centered_quad, cube, sphere, triangle  # noqa: F401
 from .texture import Texture  # noqa: F401
 
 FS_TEXTURE, FS_COLOR, FS_DEBUG = 0, 1, 2  # `enum FS`, main.rs:23-27
+FS_TEXTURE_BLEND = 3  # registry extension, see include/rz.h (RZ_FS_WITH_TEXTURE adds a texture index)
 VS_MVP = 0  # the crate's only vertex shader, main.rs:147-152
 
 

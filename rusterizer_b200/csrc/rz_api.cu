@@ -77,6 +77,7 @@ struct rz_ctx {
     uint32_t draw_cap = 0, attr_cap = 0;
     LargeItem *d_large = nullptr;
     uint32_t *d_out = nullptr;
+    TexInfo *d_textab = nullptr; // [RZ_MAX_TEXTURES]
     unsigned long long *d_cnt_backup = nullptr;
     float *d_dbg_depth = nullptr;
     uint32_t *d_dbg_color = nullptr, *d_dbg_owner = nullptr;
@@ -261,8 +262,10 @@ int rz_create(int device, uint32_t width, uint32_t height, rz_ctx **out) {
         CU_NEW(cudaEventCreateWithFlags(&c->ev_d2h_done[i], cudaEventDisableTiming));
     }
     c->d_out_ring[0] = c->d_out;
-    CU_NEW(cudaFuncSetAttribute(tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemT<false>)));
-    CU_NEW(cudaFuncSetAttribute(tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemT<true>)));
+    CU_NEW(cudaFuncSetAttribute(tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemT<false>)));
+    CU_NEW(cudaFuncSetAttribute(tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemT<false>)));
+    CU_NEW(cudaFuncSetAttribute(tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemT<true>)));
+    CU_NEW(cudaFuncSetAttribute(tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemT<true>)));
 #undef CU_NEW
     *out = c;
     return RZ_OK;
@@ -278,6 +281,7 @@ void rz_destroy(rz_ctx *c) {
     cudaFree(c->d_state); cudaFree(c->d_out); cudaFree(c->d_out_ring[1]); cudaFree(c->d_cnt_backup);
     cudaFree(c->d_dbg_depth); cudaFree(c->d_dbg_color); cudaFree(c->d_dbg_owner); cudaFree(c->d_dbg_time);
     for (auto &t : c->textures) cudaFree(t.d_data);
+    cudaFree(c->d_textab);
     for (int p = 0; p < 2; p++)
         for (auto *m : c->staging[p]) rz_mesh_destroy(m);
     if (c->h_state) cudaFreeHost(c->h_state);
@@ -316,7 +320,13 @@ int rz_bind_texture(rz_ctx *c, uint32_t index, const uint8_t *texels, uint32_t w
     t.w = width; t.h = height; t.tw = texel_width;
     t.len = (size_t)width * height * texel_width;
     CU(c, cudaMalloc(&t.d_data, t.len));
+    if (c->textures.size() >= RZ_MAX_TEXTURES)
+        return fail(c, RZ_E_TEXTURE, "rz_bind_texture: at most %d textures can be bound", RZ_MAX_TEXTURES);
     CU(c, cudaMemcpyAsync(t.d_data, texels, t.len, cudaMemcpyHostToDevice, c->stream));
+    TexInfo ti;
+    ti.data = t.d_data; ti.len = t.len; ti.w = t.w; ti.h = t.h; ti.tw = t.tw; ti.bound = 1;
+    if (!c->d_textab) CU(c, cudaMalloc(&c->d_textab, sizeof(TexInfo) * RZ_MAX_TEXTURES));
+    CU(c, cudaMemcpyAsync(c->d_textab + c->textures.size(), &ti, sizeof ti, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     c->textures.push_back(t);
     return RZ_OK;
@@ -382,9 +392,15 @@ void rz_mesh_destroy(rz_mesh *m) {
 
 static int record_draw(rz_ctx *c, const rz_mesh *mesh, uint32_t vs_id, uint32_t fs_id) {
     if (vs_id != RZ_VS_MVP) return fail(c, RZ_E_INVALID, "rz_render: unknown vertex shader id %u", vs_id);
-    if (fs_id > RZ_FS_DEBUG) return fail(c, RZ_E_INVALID, "rz_render: unknown fragment shader id %u", fs_id);
-    if (fs_id == RZ_FS_TEXTURE && c->textures.empty())
-        return fail(c, RZ_E_TEXTURE, "rz_render: FS Texture needs texture 0 bound (uniform.rs:36)");
+    const uint32_t shader = fs_id & 0xFFu, tex = (fs_id >> 8) & 0xFFu;
+    if (shader > RZ_FS_TEXTURE_BLEND || (fs_id >> 16) != 0)
+        return fail(c, RZ_E_INVALID, "rz_render: unknown fragment shader id 0x%x", fs_id);
+    const bool textured = shader == RZ_FS_TEXTURE || shader == RZ_FS_TEXTURE_BLEND;
+    if (tex != 0 && !textured) return fail(c, RZ_E_INVALID, "rz_render: fragment shader %u takes no texture index", shader);
+    if (textured && tex >= c->textures.size())
+        return fail(c, RZ_E_TEXTURE, "rz_render: the fragment shader reads texture %u but %zu are bound (uniform.rs:36)", tex,
+                    c->textures.size());
+    if (c->draws.size() >= (1u << 24)) return fail(c, RZ_E_INVALID, "rz_render: more than 2^24 draws in one frame");
     DrawCmd d;
     d.mesh = mesh;
     d.fs = fs_id;
@@ -448,6 +464,7 @@ static FrameParams make_params(rz_ctx *c, uint32_t *out_base) {
     }
     if (!c->textures.empty()) {
         const Texture &t = c->textures[0];
+        P.tex_table = c->d_textab;
         P.tex0.data = t.d_data; P.tex0.len = t.len; P.tex0.w = t.w; P.tex0.h = t.h; P.tex0.tw = t.tw; P.tex0.bound = 1;
     }
     return P;
@@ -535,10 +552,16 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     if (timed) CU(c, cudaEventRecord(c->ev[2], st));
     const dim3 tile_grid(std::min<uint32_t>(n_tiles, (uint32_t)c->num_sms * (c->debug ? 3u : 4u))); // persistent CTAs, 4 per SM
     if (n_tiles) {
-        if (c->debug)
-            CU(c, launch_pdl(tile_kernel<true>, tile_grid, dim3(NT), sizeof(TileSmemT<true>), st, P));
+        bool ext = false; // does any draw use the shader-registry extension (texture index != 0, TextureBlend)?
+        for (auto &d : c->draws) ext = ext || (d.fs >> 8) != 0 || (d.fs & 0xFFu) == RZ_FS_TEXTURE_BLEND;
+        if (c->debug && ext)
+            CU(c, launch_pdl(tile_kernel<true, true>, tile_grid, dim3(NT), sizeof(TileSmemT<true>), st, P));
+        else if (c->debug)
+            CU(c, launch_pdl(tile_kernel<true, false>, tile_grid, dim3(NT), sizeof(TileSmemT<true>), st, P));
+        else if (ext)
+            CU(c, launch_pdl(tile_kernel<false, true>, tile_grid, dim3(NT), sizeof(TileSmemT<false>), st, P));
         else
-            CU(c, launch_pdl(tile_kernel<false>, tile_grid, dim3(NT), sizeof(TileSmemT<false>), st, P));
+            CU(c, launch_pdl(tile_kernel<false, false>, tile_grid, dim3(NT), sizeof(TileSmemT<false>), st, P));
         c->launches++;
     }
     if (timed) CU(c, cudaEventRecord(c->ev[3], st));

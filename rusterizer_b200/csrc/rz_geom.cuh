@@ -155,7 +155,7 @@ __device__ __forceinline__ void emit_setup(const FrameParams &P, const DrawParam
     rr[1] = make_float4(s.px[2], s.py[2], s.z[0], s.z[1]);
     rr[2] = make_float4(s.z[2], __uint_as_float(key), 0.0f, 0.0f);
     float4 *sr = reinterpret_cast<float4 *>(&P.shade[rec]);
-    sr[0] = make_float4(s.w[0], s.w[1], s.w[2], __uint_as_float(D.fs | (ca ? 4u : 0u) | (D.draw << 3)));
+    sr[0] = make_float4(s.w[0], s.w[1], s.w[2], __uint_as_float((D.fs & 3u) | (ca ? 4u : 0u) | (((D.fs >> 8) & 31u) << 3) | (D.draw << 8)));
     sr[1] = make_float4(__uint_as_float(i0), __uint_as_float(i1), __uint_as_float(i2), __uint_as_float(clip_attr));
 
     if (small) {

@@ -65,8 +65,7 @@ __device__ __forceinline__ void read_texel(const TexInfo &t, const float *lut, u
 // and the resolve forces those bits to 0xFF (buffers.rs:121-124), so the image is identical; the
 // parity instrumentation keeps it to compare the per-sample colours bit for bit.
 template <bool ALPHA>
-__device__ __forceinline__ uint32_t sample_texture_argb(const TexInfo &t, const float *lut, float u, float v,
-                                                        uint32_t &oob) {
+__device__ __forceinline__ void sample_texture(const TexInfo &t, const float *lut, float u, float v, uint32_t &oob, float *o) {
     const float x = fmul(u, (float)(t.w - 1)), y = fmul(v, (float)(t.h - 1));
     const uint32_t x0 = sat_u32(floorf(x)), x1 = sat_u32(ceilf(x));
     const uint32_t y0 = sat_u32(floorf(y)), y1 = sat_u32(ceilf(y));
@@ -93,13 +92,16 @@ __device__ __forceinline__ uint32_t sample_texture_argb(const TexInfo &t, const 
         read_texel(t, lut, x0, y1, bl, oob);
         read_texel(t, lut, x1, y1, br, oob);
     }
-    float o[4];
 #pragma unroll
     for (int k = 0; k < (ALPHA ? 4 : 3); k++) {
         const float q0 = fadd(fmul(tl[k], omx), fmul(tr[k], xf));
         const float q1 = fadd(fmul(bl[k], omx), fmul(br[k], xf));
         o[k] = fadd(fmul(q0, omy), fmul(q1, yf));
     }
+    if (!ALPHA) o[3] = 0.0f;
+}
+template <bool ALPHA>
+__device__ __forceinline__ uint32_t pack_argb(const float *o) {
     if (!ALPHA) return 0xFF000000u | to_argb(o[0], o[1], o[2], 0.0f);
     return to_argb(o[0], o[1], o[2], o[3]);
 }
@@ -109,12 +111,14 @@ __device__ __forceinline__ uint32_t sample_texture_argb(const TexInfo &t, const 
 // sampled depth of sample 0 (0.0 when uncovered), as FragCoords.depths[0] (mod.rs:458-463).
 // `s` needs the screen points and edge normals only; depths_camera_space, the shader id and the
 // attribute locations come from the triangle's ShadeRec.
-template <bool ALPHA>
+// EXT = false compiles the reference's three shaders on texture 0 only (the registry extension costs registers in
+// the hottest loop of the frame; frames that do not use it run the lean instantiation).
+template <bool ALPHA, bool EXT>
 __device__ __forceinline__ uint32_t shade(const FrameParams &P, const Setup &s, uint32_t rec, const float *lut, int X,
                                           int Y, uint32_t mpost, float depth0, uint32_t &oob) {
     const float4 *sr = reinterpret_cast<const float4 *>(&P.shade[rec]);
     const float4 s0 = __ldg(sr);
-    const uint32_t info = __float_as_uint(s0.w), fs = info & 3u;
+    const uint32_t info = __float_as_uint(s0.w), fs = info & 3u, texidx = EXT ? (info >> 3) & 31u : 0u;
     if (fs == 2u) return to_argb(depth0, depth0, depth0, 1.0f); // Color::grayscale(depths[0])
     const float4 s1 = __ldg(sr + 1);
     const float *a0, *a1, *a2;
@@ -123,7 +127,7 @@ __device__ __forceinline__ uint32_t shade(const FrameParams &P, const Setup &s, 
         a1 = a0 + 6;
         a2 = a0 + 12;
     } else {         // unclipped: straight from the mesh
-        const float *attr = P.draws[info >> 3].attr;
+        const float *attr = P.draws[info >> 8].attr;
         a0 = attr + 6 * (size_t)__float_as_uint(s1.x);
         a1 = attr + 6 * (size_t)__float_as_uint(s1.y);
         a2 = attr + 6 * (size_t)__float_as_uint(s1.z);
@@ -146,8 +150,19 @@ __device__ __forceinline__ uint32_t shade(const FrameParams &P, const Setup &s, 
 #define RZ_INTERP(c) fadd(fadd(fmul(__ldg(a0 + (c)), u), fmul(__ldg(a1 + (c)), v)), fmul(__ldg(a2 + (c)), w))
     if (fs == 1u) return to_argb(RZ_INTERP(0), RZ_INTERP(1), RZ_INTERP(2), RZ_INTERP(3));
     const float tu = RZ_INTERP(4), tv = RZ_INTERP(5);
+    float o[4];
+    if (!EXT || texidx == 0u) {
+        sample_texture<ALPHA>(P.tex0, lut, tu, tv, oob, o);
+    } else {
+        const TexInfo t = P.tex_table[texidx];
+        sample_texture<ALPHA>(t, lut, tu, tv, oob, o);
+    }
+    if (EXT && fs == 3u) { // FS TextureBlend: (texture.sample(u, v) + attr.color) / 2.0   (Color Add + Div<f32>, color.rs:88-111)
+#pragma unroll
+        for (int k = 0; k < (ALPHA ? 4 : 3); k++) o[k] = fdiv(fadd(o[k], RZ_INTERP(k)), 2.0f);
+    }
 #undef RZ_INTERP
-    return sample_texture_argb<ALPHA>(P.tex0, lut, tu, tv, oob);
+    return pack_argb<ALPHA>(o);
 }
 
 // Bitonic network in its "flip then halve" form: every compare-exchange puts the smaller key at
@@ -279,7 +294,7 @@ __device__ __forceinline__ void clear_empty_tiles(const FrameParams &P, int lane
     }
 }
 
-template <bool DBG>
+template <bool DBG, bool EXT>
 __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef TileSmemT<DBG> SM;
@@ -433,7 +448,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                     if (!mp) continue;
                     c_shaded++;
                     c_samples += __popc(mp);
-                    const uint32_t argb = shade<true>(P, q, B[it].rec, S.lut, X, Y, mp, zs[0], c_oob);
+                    const uint32_t argb = shade<true, EXT>(P, q, B[it].rec, S.lut, X, Y, mp, zs[0], c_oob);
 #pragma unroll
                     for (int k = 0; k < 4; k++)
                         if ((mp >> k) & 1u) {
@@ -653,7 +668,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 q.py[1] = S.it_f[3][it]; q.px[2] = S.it_f[4][it]; q.py[2] = S.it_f[5][it];
                 setup_normals(q);
                 const float4 z = S.u.fr.z[f];
-                const uint32_t argb = shade<DBG>(P, q, S.it_rec[it], S.lut, tileX0 + (int)(p % TW), tileY0 + (int)(p / TW),
+                const uint32_t argb = shade<DBG, EXT>(P, q, S.it_rec[it], S.lut, tileX0 + (int)(p % TW), tileY0 + (int)(p / TW),
                                             fin & 0xFu, z.x, c_oob);
 #pragma unroll
                 for (int k = 0; k < 4; k++)

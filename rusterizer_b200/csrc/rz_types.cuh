@@ -76,7 +76,7 @@ struct __align__(16) RasterRec {
 // array through their vertex indices (nothing is copied); clipped ones at an AttrRec.  32 B.
 struct __align__(16) ShadeRec {
     float w0, w1, w2;
-    uint32_t info;        // fs | clipped << 2 | draw << 3
+    uint32_t info;        // fs (2 bits) | clipped << 2 | texture index << 3 (5 bits) | draw << 8
     uint32_t i0, i1, i2;  // vertex indices into the draw's attribute array (unclipped)
     uint32_t clip_attr;   // index into FrameParams::attrs (clipped)
 };
@@ -133,7 +133,8 @@ struct FrameParams {
     uint32_t *dbg_color;
     uint32_t *dbg_owner;
     unsigned long long *dbg_tile_time; // optional [tiles][4]: tile id | n << 32, start ns, end ns, SM id
-    TexInfo tex0;
+    TexInfo tex0;                // texture 0 by value (the built-in FS Texture, main.rs:69-71)
+    const TexInfo *tex_table;    // every bound texture (fragment shaders with a texture index != 0)
 };
 
 // Screen-space sharding: besides the contiguous row range a ctx may own every il_world-th band of il_band
@@ -162,7 +163,7 @@ struct DrawParams {
                            //   [1] = clip x, y, z, bits(the 12 trivial accept/reject comparisons)
     uint32_t nv, nt;
     uint32_t tri_base;     // triangle number of this draw's first triangle inside the frame
-    uint32_t fs;
+    uint32_t fs;           // shader id | texture index << 8
     uint32_t draw;         // index into FrameParams::draws
     float M[16];           // (projection * view) * world, row-major (main.rs:147-152)
 };

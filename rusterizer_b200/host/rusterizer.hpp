@@ -25,7 +25,8 @@ namespace rz {
 using Mat4 = std::array<float, 16>; // row-major [[f32;4];4]  (math/matrix.rs:13)
 
 enum class VS : uint32_t { MVP = RZ_VS_MVP };                                            // main.rs:147-152
-enum class FS : uint32_t { Texture = RZ_FS_TEXTURE, Color = RZ_FS_COLOR, Debug = RZ_FS_DEBUG }; // main.rs:23-27
+enum class FS : uint32_t { Texture = RZ_FS_TEXTURE, Color = RZ_FS_COLOR, Debug = RZ_FS_DEBUG, // main.rs:23-27
+                           TextureBlend = RZ_FS_TEXTURE_BLEND };                               // registry extension (rz.h)
 
 struct Error : std::runtime_error {
     int code;
@@ -219,14 +220,15 @@ class Renderer { // render.rs:38-127 without the minifb window
     Uniforms &uniforms() { return uniforms_; } // render.rs:71
 
     // Renderer::render(&mesh, vertex_shader, fragment_shader), render.rs:98-114
-    void render(const Mesh &mesh, VS vs, FS fs) {
+    // texture_index: which bound texture a sampling shader reads (Uniforms::get_texture(index), uniform.rs:35-37)
+    void render(const Mesh &mesh, VS vs, FS fs, uint32_t texture_index = 0) {
         if (mesh.vertices.size() != mesh.attributes.size())
             throw Error(RZ_E_INVALID, "Mesh: vertices and attributes must have the same length");
         const UniformBlock &b = uniforms_.block_;
         check(rz_write_block(ctx_, b.world.data(), b.view.data(), b.projection.data()));
         check(rz_render_host(ctx_, mesh.vertices.empty() ? nullptr : mesh.vertices[0].data(),
                              mesh.attributes.empty() ? nullptr : &mesh.attributes[0].r, (uint32_t)mesh.vertices.size(),
-                             mesh.indices.data(), mesh.indices.size(), (uint32_t)vs, (uint32_t)fs));
+                             mesh.indices.data(), mesh.indices.size(), (uint32_t)vs, RZ_FS_WITH_TEXTURE((uint32_t)fs, texture_index)));
     }
 
     // Rasterizer::framebuffer(), rasterizer/mod.rs:520-522 (what Renderer::display hands to minifb)

@@ -21,13 +21,19 @@ from .texture import Texture
 
 F = np.float32
 FS_TEXTURE, FS_COLOR, FS_DEBUG = 0, 1, 2
+FS_TEXTURE_BLEND = 3  # registry extension (include/rz.h): (texture.sample(u, v) + attr.color) / 2.0
+
+
+def fs_with_texture(fs: int, index: int) -> int:
+    """RZ_FS_WITH_TEXTURE: the sampling shaders read Uniforms::get_texture(index) (uniform.rs:35-37)."""
+    return fs | (index << 8)
 
 
 @dataclass
 class Draw:
     mesh: Mesh
     world: np.ndarray
-    fs: int = FS_TEXTURE
+    fs: int = FS_TEXTURE  # shader id, optionally combined with a texture index: fs_with_texture(fs, index)
 
 
 @dataclass
@@ -38,7 +44,8 @@ class Scene:
     view: np.ndarray
     projection: np.ndarray
     draws: list = field(default_factory=list)
-    texture: Texture | None = None
+    texture: Texture | None = None          # texture 0
+    extra_textures: list = field(default_factory=list)  # textures 1.. (bind order, uniform.rs:29-33)
 
     @property
     def n_triangles(self) -> int:

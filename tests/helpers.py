@@ -11,6 +11,8 @@ def oracle_render(scene, fast=False):
     r = OracleRenderer(scene.width, scene.height, get_lib(fast=fast))
     if scene.texture is not None:
         r.bind_texture(0, scene.texture.texels)
+        for k, t in enumerate(getattr(scene, "extra_textures", [])):
+            r.bind_texture(k + 1, t.texels)
     r.write_block(view=scene.view, projection=scene.projection)
     for d in scene.draws:
         r.write_block(world=d.world)
@@ -29,6 +31,8 @@ def gpu_render(scene, debug=True, device_resident=False, renderer=None):
     r = renderer or Renderer(scene.width, scene.height)
     if renderer is None and scene.texture is not None:
         r.uniforms().bind_texture(0, scene.texture)
+        for k, t in enumerate(getattr(scene, "extra_textures", [])):
+            r.uniforms().bind_texture(k + 1, t)
     if debug:
         r.debug_capture(True)
     r.reset_counters()

@@ -389,3 +389,80 @@ def test_peer_store_primitives_two_contexts_one_gpu():
     root.shared_free(img); root.shared_free(flags); ctx[1][0].shared_free(ack)
     for r, _ in ctx:
         r.close()
+
+
+def test_rgb_texture_non_square_and_out_of_range_uvs():
+    """Texture::read_texel with texel_width 3 (texture.rs:51-61), a non-square non-power-of-two texture, and UVs
+    outside [0,1]: the reference neither wraps nor clamps (texture.rs:65-83) -- coordinates past the buffer are a
+    panic there, a clamped read counted in n_tex_oob here and in the oracle; everything else must match bit for bit."""
+    rng = np.random.default_rng(11)
+    tex = scenes.Texture(rng.integers(0, 256, (37, 61, 3), dtype=np.uint8))
+    base = scenes.default_scene(1.0, width=320, height=180)
+    s = scenes.Scene("rgb_tex", base.width, base.height, base.view, base.projection, base.draws, tex)
+    check(s)
+    # UVs scaled to [-0.25, 1.5]: part of the samples fall outside the texture
+    draws = []
+    for d in base.draws:
+        a = d.mesh.attributes.copy()
+        a[:, 4:6] = a[:, 4:6] * 1.75 - 0.25
+        draws.append(scenes.Draw(Mesh(d.mesh.vertices, d.mesh.indices, a), d.world, d.fs))
+    s2 = scenes.Scene("rgb_tex_oob", base.width, base.height, base.view, base.projection, draws, tex)
+    o = oracle_render(s2)
+    g = gpu_render(s2, debug=True)
+    assert o["counters"]["n_tex_oob"] > 0
+    msgs = compare(o, g)
+    assert not msgs, "; ".join(msgs)
+
+
+def test_many_draws_in_one_frame():
+    """150 draws accumulate into one frame in submission order (main.rs:170-173): more draws than the per-draw
+    table's first allocation, alternating fragment shaders, overlapping in depth."""
+    rng = np.random.default_rng(5)
+    base = scenes.default_scene(0.5, width=256, height=144)
+    quad, tri = scenes.centered_quad(1.0), scenes.triangle()
+    draws = []
+    for k in range(150):
+        world = mathx.matmul(mathx.translate(float(rng.uniform(-3, 3)), float(rng.uniform(-2, 2)), float(rng.uniform(-1, 6))),
+                             mathx.rotate(float(rng.uniform(0, 6)), float(rng.uniform(0, 6)), float(rng.uniform(0, 6))))
+        draws.append(scenes.Draw(quad if k % 2 else tri, world, k % 3))
+    s = scenes.Scene("many_draws", base.width, base.height, base.view, base.projection, draws, base.texture)
+    check(s)
+    check(s, device_resident=True)
+
+
+def test_shader_registry_texture_index_and_blend():
+    """Registry extension (include/rz.h): sampling shaders take a texture index
+    (Uniforms::get_texture(index), uniform.rs:35-37) and FS TextureBlend = (sample + attr.color) / 2.0 with the
+    Color operators of color.rs:88-111 -- three textures (RGBA and RGB), five draws, against the oracle."""
+    from rusterizer_b200.render import Renderer, RzError
+
+    rng = np.random.default_rng(23)
+    base = scenes.default_scene(1.0, width=320, height=180)
+    cube, sph = base.draws[0], base.draws[1]
+    t1 = scenes.Texture(rng.integers(0, 256, (64, 48, 4), dtype=np.uint8))
+    t2 = scenes.Texture(rng.integers(0, 256, (33, 77, 3), dtype=np.uint8))
+    W = scenes.fs_with_texture
+    draws = [scenes.Draw(cube.mesh, cube.world, W(scenes.FS_TEXTURE, 1)),
+             scenes.Draw(sph.mesh, sph.world, W(scenes.FS_TEXTURE_BLEND, 2)),
+             scenes.Draw(scenes.centered_quad(3.0), mathx.translate(-2.0, 0.5, 1.0), W(scenes.FS_TEXTURE_BLEND, 0)),
+             scenes.Draw(scenes.triangle(), mathx.translate(2.0, -1.0, -1.0), scenes.FS_COLOR),
+             scenes.Draw(scenes.centered_quad(1.5), mathx.matmul(mathx.translate(2.5, 1.5, 0.0), mathx.rotate(0.4, 0.2, 0.1)),
+                         scenes.FS_TEXTURE)]
+    s = scenes.Scene("registry", base.width, base.height, base.view, base.projection, draws, base.texture, [t1, t2])
+    check(s)
+    check(s, device_resident=True)
+    # a near-clipped triangle through the blend shader (interpolated attributes live in an AttrRec)
+    c = scenes.clip_test_scene(0.4, width=320, height=180)
+    c.draws[0].fs = W(scenes.FS_TEXTURE_BLEND, 1)
+    c.extra_textures = [t1]
+    check(c)
+    # failure points: unbound texture index (uniform.rs:36 index panic), index on a non-sampling shader
+    r = Renderer(64, 64)
+    r.uniforms().bind_texture(0, base.texture)
+    with pytest.raises(RzError) as e:
+        r.render(scenes.triangle(), 0, W(scenes.FS_TEXTURE, 1))
+    assert e.value.code == -4
+    with pytest.raises(RzError) as e:
+        r.render(scenes.triangle(), 0, W(scenes.FS_COLOR, 1))
+    assert e.value.code == -1
+    r.close()

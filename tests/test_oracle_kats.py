@@ -401,3 +401,28 @@ def test_vector_len_normalized_arith():
     for i in range(3):
         for j in range(3):
             eq(v[i] + v[j], expected[i * 3 + j])
+
+
+def test_registry_blend_shader_arithmetic():
+    """FS TextureBlend (registry extension, include/rz.h) = (texture.sample(u, v) + attr.color) / 2.0 with one
+    IEEE rounding per Color operator (color.rs:88-111).  A full-screen quad with constant colour and constant uv:
+    every pixel is pack((texel/255 + colour) / 2)."""
+    from oracle.oracle import OracleRenderer
+
+    tex = np.zeros((2, 2, 4), np.uint8)
+    tex[...] = (200, 100, 50, 255)
+    r = OracleRenderer(16, 16)
+    r.bind_texture(0, np.zeros((4, 4, 4), np.uint8))
+    r.bind_texture(1, tex)
+    pos = np.array([[-1, -1, 0.5], [1, -1, 0.5], [1, 1, 0.5], [-1, 1, 0.5]], np.float32) * np.float32([0.9, 0.9, 1])
+    col = np.float32([0.25, 0.5, 0.75, 1.0])
+    attrs = np.tile(np.concatenate([col, np.float32([0.5, 0.5])]), (4, 1)).astype(np.float32)
+    idx = np.array([0, 2, 1, 0, 3, 2], np.uint32)
+    r.render(pos, attrs, idx, 0, 3 | (1 << 8))
+    fb = r.framebuffer()
+    f = np.float32
+    want = [int(f(f(f(f(t) / f(255.0)) + c) / f(2.0)) * f(255.0)) for t, c in zip((200, 100, 50), col[:3])]
+    assert fb[8, 8] == (0xFF000000 | (want[0] << 16) | (want[1] << 8) | want[2])
+    with pytest.raises(Exception):
+        r.render(pos, attrs, idx, 0, 3 | (2 << 8))  # texture 2 is not bound
+    r.close()
