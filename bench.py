@@ -50,48 +50,87 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread every few
+    milliseconds (the timed region of the default run lasts tens of milliseconds); `nvidia-smi -lms` as fallback."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index: int, period_s: float = 0.004):
+        self.index, self.period, self.rows, self.proc, self.thread, self.stop_flag = index, period_s, [], None, None, False
+        self.mode = None
+
+    def _reasons(self, mask):
+        import pynvml as N
+
+        bits = {"hw_slowdown": N.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": N.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": N.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": N.nvmlClocksEventReasonSwPowerCap}
+        return [n for n, b in bits.items() if mask & b]
+
+    def _poll(self):
+        import pynvml as N
+
+        while not self.stop_flag:
+            try:
+                sm = N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)
+                mask = N.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.rows.append((time.time(), float(sm), float(self.max_sm), self._reasons(mask)))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+            import pynvml as N
+
+            N.nvmlInit()
+            # NVML enumerates all GPUs of the box: honour CUDA_VISIBLE_DEVICES when it lists ordinals
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.index
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                phys = int(vis.split(",")[self.index])
+            self.h = N.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM)
+            self.mode = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.mode = None
+        try:
+            q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.mode = "nvidia-smi"
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return None
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.rows:
-            if ts < t0 - 0.05 or ts > t1 + 0.15:
-                continue
             f = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                self.rows.append((time.time(), float(f[1]), float(f[2]),
+                                  [n for n, v in zip(self.NAMES, f[5:9]) if v.lower().startswith("active")]))
             except Exception:
                 continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self, t0, t1):
+        if self.mode is None:
+            return None
+        if self.mode == "nvml":
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            margin0, margin1 = 0.0, 0.0
+        else:
+            time.sleep(0.15)
+            self.proc.terminate()
+            margin0, margin1 = 0.05, 0.15
+        rows = [r for r in self.rows if t0 - margin0 <= r[0] <= t1 + margin1]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.mode}
+        reasons = sorted({n for r in rows for n in r[3]})
+        return {"sm_mhz": statistics.median(r[1] for r in rows), "sm_max_mhz": max(r[2] for r in rows), "reasons": reasons,
+                "samples": len(rows), "source": self.mode}
 
 
 def build_scene(args):
@@ -188,7 +227,7 @@ def workload_config(args, scene):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="frames", choices=["frames", "tiles"])
@@ -309,7 +348,7 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        time.sleep(0.02 if sampler.mode == "nvml" else 0.3)
     L = 1 if tiles_mode else max(1, args.inflight)
     lanes = [(r, stream, blk, [dmesh])]
     frame_latency_ms = None
