@@ -590,6 +590,18 @@ def main():
     roofline["fp32"] = {"algorithmic_gflop_per_frame": f_alg / 1e9, "achieved": f_alg / (ms_per_step / 1e3) / 1e12,
                         "peak": fp32_peak, "unit": "TFLOP/s (non-FMA f32)", "frac": f_alg / (ms_per_step / 1e3) / 1e12 / fp32_peak,
                         "formula": "28*Nv + 40*Nt_in + 60*Nt_setup + 72*N_bbox_px + 30*N_samples + 180*N_shaded_px (texture FS)"}
+    # third reading: the issue-slot roofline.  ncu counted the warp instructions one C2 frame executes (all kernels,
+    # profiles/traffic.json); a B200 issues at most 148 SMs x 4 schedulers x clock of them per second.
+    try:
+        det = json.loads(tp.read_text()).get("_detail", {}) if (tp.exists() and not tiles_mode and args.n_phi == 1001 and args.n_theta == 501) else {}
+        winst = sum(float(v.get("warp_inst", 0.0)) for v in det.values())
+        if winst > 0:
+            issue_peak = 148 * 4 * sm_mhz * 1e6
+            roofline["issue"] = {"warp_instructions_per_frame": winst, "achieved_ginst_per_s": winst / (ms_per_step / 1e3) / 1e9,
+                                 "peak_ginst_per_s": issue_peak / 1e9, "frac": winst / (ms_per_step / 1e3) / issue_peak,
+                                 "source": "smsp__inst_executed.sum per kernel from profiles/traffic.json (ncu --set full, same workload)"}
+    except Exception:
+        pass
     cb = None
     if not args.no_cpu_baseline and not tiles_mode and n_gpus == 1:  # rank 0 at N=1 only (bounded sample)
         cb = cpu_baseline(scene, budget_s=args.cpu_budget)
