@@ -203,6 +203,17 @@ static_assert(sizeof(BigSetup) == 80, "BigSetup must be 20 words");
 
 constexpr uint32_t FR_NONE = 0xFFFFu;
 
+__device__ __forceinline__ uint32_t smem_atom_add(uint32_t *p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ uint32_t smem_atom_exch(uint32_t *p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+    return old;
+}
+
 struct FragPool {
     float4 z[POOL];        // the 4 sample depths (0.0 where uncovered, like Fragment.sampled_depths)
     uint32_t meta[POOL];   // item | pixel << 8 | coverage << 16
@@ -219,7 +230,7 @@ struct TileSmemT {
     float it_f[10][NT];                   // items of the current chunk: px,py x3 | z x3 | inv
     uint32_t it_key[NT], it_rec[NT];
     uint32_t it_rcp[NT];                  // ceil(65536 / bw): j / bw == (j * rcp) >> 16 for j < 256, bw <= 16
-    uint32_t it_box[NT];                  // lx0 | ly0 << 8 | bw << 16
+    uint32_t it_box[NT];                  // lx0 | ly0 << 8 | bw << 16 | tie-break bits << 24
     uint32_t pre[NT + 1];                 // exclusive prefix of the in-tile bbox areas (work units)
     uint8_t unit_item[UNIT_CAP];          // work unit -> item
     union {
@@ -479,7 +490,10 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 S.it_f[9][tid] = s.inv;
                 S.it_key[tid] = key; S.it_rec[tid] = rec;
                 S.it_rcp[tid] = (65536u + (uint32_t)bw - 1u) / (uint32_t)max(bw, 1);
-                S.it_box[tid] = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bw << 16);
+                float thr0[3];
+                edge_thresholds(s, thr0); // tie-break constants, once per item: bit 24+k set <=> edge k does NOT own its ties
+                S.it_box[tid] = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bw << 16) | (__float_as_uint(thr0[0]) << 24) |
+                                (__float_as_uint(thr0[1]) << 25) | (__float_as_uint(thr0[2]) << 26);
             }
             uint32_t incl = area;
 #pragma unroll
@@ -541,20 +555,22 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                         q.px[0] = S.it_f[0][it]; q.py[0] = S.it_f[1][it]; q.px[1] = S.it_f[2][it];
                         q.py[1] = S.it_f[3][it]; q.px[2] = S.it_f[4][it]; q.py[2] = S.it_f[5][it];
                         setup_normals(q);
-                        float thr[3];
-                        edge_thresholds(q, thr);
+                        float thr[3]; // 0.0 or the smallest subnormal (bit pattern 1), see edge_thresholds()
+#pragma unroll
+                        for (int k = 0; k < 3; k++) thr[k] = __uint_as_float((box >> (24 + k)) & 1u);
                         m = coverage_mask_fast(q, thr, tileX0 + lpx, tileY0 + lpy);
                     }
                     const uint32_t bal = __ballot_sync(0xffffffffu, m != 0u);
                     if (bal) { // warp-aggregated fragment allocation (ballot + popc prefix)
                         uint32_t slot = 0;
-                        if (lane == 0) slot = atomicAdd(&S.nfrag, (uint32_t)__popc(bal));
+                        // plain PTX atomics: the compiler would wrap atomicAdd/atomicExch in its own leader election
+                        if (lane == 0) slot = smem_atom_add(&S.nfrag, (uint32_t)__popc(bal));
                         slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(bal & lanemask_lt());
                         if (m) {
                             cov_try++;
                             if (slot < POOL) {
                                 S.u.fr.meta[slot] = it | (p << 8) | (m << 16);
-                                S.u.fr.next[slot] = (uint16_t)atomicExch(&S.head[p], slot);
+                                S.u.fr.next[slot] = (uint16_t)smem_atom_exch(&S.head[p], slot);
                             } else {
                                 S.ovf = 1u;
                             }
