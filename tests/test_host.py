@@ -183,3 +183,91 @@ def test_sharding_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+_PEER_WORKER = r"""
+import os, sys, time
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+import numpy as np, torch.distributed as dist
+from multiprocessing import shared_memory
+from rusterizer_b200 import sharding
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+W, H, TH = 64, 112, 16
+
+
+class FakeRenderer:
+    # The peer-memory surface of render.Renderer (include/rz.h) on host shared memory: 'device pointers' are
+    # (block << 40 | offset), handles are shm names, frames are copied synchronously from `self.next_frame`.
+    def __init__(self):
+        self.width, self.height, self.blocks, self.rows, self.il = W, H, {{}}, (0, H), (0, 0, 1)
+        self.next_frame = None
+    def _view(self, ptr, n):
+        return np.ndarray((n,), np.uint32, self.blocks[ptr >> 40].buf, offset=ptr & ((1 << 40) - 1))
+    def shared_alloc(self, nbytes):
+        shm = shared_memory.SharedMemory(create=True, size=nbytes)
+        np.ndarray((nbytes // 4,), np.uint32, shm.buf)[:] = 0
+        bid = len(self.blocks) + 1 + 100 * rank
+        self.blocks[bid] = shm
+        return bid << 40, shm.name.encode().ljust(64, b"\0")
+    def shared_open(self, handle):
+        shm = shared_memory.SharedMemory(name=handle.rstrip(b"\0").decode())
+        bid = len(self.blocks) + 1 + 100 * rank
+        self.blocks[bid] = shm
+        return bid << 40
+    def shared_close(self, ptr):
+        self.blocks.pop(ptr >> 40).close()
+    def shared_free(self, ptr):
+        shm = self.blocks.pop(ptr >> 40); shm.close(); shm.unlink()
+    def set_row_range(self, a, b): self.rows = (a, b)
+    def set_row_interleave(self, band, r, w): self.il = (band, r, w)
+    def owns(self, y):
+        band, r, w = self.il
+        return self.rows[0] <= y < self.rows[1] and (band == 0 or (y // TH // band) % w == r)
+    def framebuffer_async(self, dst):
+        img = self._view(dst - self.rows[0] * W * 4, W * H).reshape(H, W)
+        for y in range(H):
+            if self.owns(y): img[y] = self.next_frame[y]
+    def signal(self, ptrs, value):
+        for p in ([ptrs] if isinstance(ptrs, int) else ptrs): self._view(p, 1)[0] = value
+    def wait_flags(self, ptr, n, stride, value, timeout_ms=0):
+        t0 = time.time()
+        for i in range(n):
+            while int(self._view(ptr + i * stride, 1)[0]) < value:
+                assert time.time() - t0 < 20, "peer flag never arrived"
+                time.sleep(0.0005)
+    def sync(self): pass
+
+
+for band in (0, 1, 2):
+    r = FakeRenderer()
+    pf = sharding.PeerFrame(r, root=0, n_buffers=2, interleave_band=band)
+    rng = np.random.default_rng(99)
+    frames = [rng.integers(0, 2 ** 32, (H, W), dtype=np.uint64).astype(np.uint32) for _ in range(7)]  # same on every rank
+    for f, frame in enumerate(frames):
+        r.next_frame = frame
+        img = pf.finish_frame()
+        if rank == 0:
+            got = r._view(img, W * H).reshape(H, W)
+            assert np.array_equal(got, frame), (band, f)   # complete and not stale: every rank's rows have arrived
+            pf.release()
+        else:
+            assert img is None
+    pf.close()
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_peer_frame_protocol_world_size_3_gloo(tmp_path):
+    """The N>1 host logic of sharding.PeerFrame on CPU: 3 ranks over gloo with a fake renderer whose 'peer memory'
+    is host shared memory -- handle exchange, contiguous and interleaved row ownership, completion flags, the two
+    alternating images and the acknowledgement back-pressure deliver every frame complete to the presenter."""
+    script = tmp_path / "peer_worker.py"
+    script.write_text(_PEER_WORKER.format(root=str(ROOT)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="3")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(3)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
