@@ -203,15 +203,11 @@ static_assert(sizeof(BigSetup) == 80, "BigSetup must be 20 words");
 
 constexpr uint32_t FR_NONE = 0xFFFFu;
 
-__device__ __forceinline__ uint32_t smem_atom_add(uint32_t *p, uint32_t v) {
-    uint32_t old;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
-    return old;
-}
-__device__ __forceinline__ uint32_t smem_atom_exch(uint32_t *p, uint32_t v) {
-    uint32_t old;
-    asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
-    return old;
+#ifndef RZ_BUDGET_TRIG
+#define RZ_BUDGET_TRIG 3u // a chunk is cut beforehand when its predicted fragments exceed 7/8 * (1 + TRIG/8) of the pool
+#endif
+__device__ __forceinline__ uint32_t fit_units(uint32_t units, uint32_t nfrag) {
+    return nfrag > 32u ? max(256u, units * (uint32_t)(POOL * 7 / 8) / nfrag) : (uint32_t)UNIT_CAP;
 }
 
 struct FragPool {
@@ -230,7 +226,7 @@ struct TileSmemT {
     float it_f[10][NT];                   // items of the current chunk: px,py x3 | z x3 | inv
     uint32_t it_key[NT], it_rec[NT];
     uint32_t it_rcp[NT];                  // ceil(65536 / bw): j / bw == (j * rcp) >> 16 for j < 256, bw <= 16
-    uint32_t it_box[NT];                  // lx0 | ly0 << 8 | bw << 16 | tie-break bits << 24
+    uint32_t it_box[NT];                  // lx0 | ly0 << 8 | bw << 16
     uint32_t pre[NT + 1];                 // exclusive prefix of the in-tile bbox areas (work units)
     uint8_t unit_item[UNIT_CAP];          // work unit -> item
     union {
@@ -242,6 +238,7 @@ struct TileSmemT {
     uint32_t scan[NT / 32];
     uint32_t first_big, first_small, nfrag, ovf, cur_tile;
     uint32_t clr_cursor[NT / 32];         // per-warp cursor of the empty-tile clears
+    uint32_t unit_budget;                 // adaptive work-unit budget of a chunk (fragment pool occupancy predictor)
 };
 
 // Sort the tile's list by order key (in shared memory when it fits, else in place in HBM) and
@@ -332,6 +329,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
     // empty-tile clears: with a caller-owned destination they are spread over the loop (a few tile groups per
     // rasterised tile, cursor kept in shared memory), the rest follows after the loop
     if (lane == 0) S.clr_cursor[warp] = blockIdx.x * (NT / 32) + warp;
+    if (tid == 0) S.unit_budget = UNIT_CAP;
     for (;;) {
     __syncthreads(); // previous tile fully retired (also covers S.lut on the first trip)
     if (tid == 0) S.cur_tile = atomicAdd(&P.fs->tile_cursor, 1u);
@@ -490,10 +488,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 S.it_f[9][tid] = s.inv;
                 S.it_key[tid] = key; S.it_rec[tid] = rec;
                 S.it_rcp[tid] = (65536u + (uint32_t)bw - 1u) / (uint32_t)max(bw, 1);
-                float thr0[3];
-                edge_thresholds(s, thr0); // tie-break constants, once per item: bit 24+k set <=> edge k does NOT own its ties
-                S.it_box[tid] = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bw << 16) | (__float_as_uint(thr0[0]) << 24) |
-                                (__float_as_uint(thr0[1]) << 25) | (__float_as_uint(thr0[2]) << 26);
+                S.it_box[tid] = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bw << 16);
             }
             uint32_t incl = area;
 #pragma unroll
@@ -518,18 +513,24 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 for (uint32_t k = 0; k < area && first + k < (uint32_t)UNIT_CAP; k++) S.unit_item[first + k] = (uint8_t)tid;
             }
             __syncthreads();
-            if (S.pre[cnt] > (uint32_t)UNIT_CAP) {
-                // more work units than the chunk can index: keep the longest prefix of items that fits
+            // unit budget of this chunk: what the unit table can index, and what the fragment pool is expected to
+            // hold given the fragments-per-unit ratio the last chunks of this CTA saw (a chunk whose fragments
+            // overflow the pool has to redo its whole coverage pass, so it is cheaper to cut it beforehand)
+            // S.unit_budget aims at 7/8 of the pool; a chunk is only cut when the prediction exceeds the pool by
+            // a clear margin (~1.2x), borderline chunks are simply tried
+            const uint32_t budget = min((uint32_t)UNIT_CAP, S.unit_budget);
+            if (S.pre[cnt] > min((uint32_t)UNIT_CAP, budget + budget * RZ_BUDGET_TRIG / 8u)) {
+                // keep the longest prefix of items that fits
                 // (chunks must follow submission order, so an unsorted list is sorted first)
                 if (!sorted) {
                     sort_tile_list(S, bin, n);
                     sorted = true;
                     continue;
                 }
-                int lo = 1, hi = cnt; // largest c with pre[c] <= UNIT_CAP (pre[1] <= 256 always fits)
+                int lo = 1, hi = cnt; // largest c with pre[c] <= budget (pre[1] <= 256 always fits)
                 while (hi - lo > 0) {
                     const int mid = (lo + hi + 1) >> 1;
-                    if (S.pre[mid] <= (uint32_t)UNIT_CAP) lo = mid; else hi = mid - 1;
+                    if (S.pre[mid] <= budget) lo = mid; else hi = mid - 1;
                 }
                 cnt = lo;
             }
@@ -555,22 +556,20 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                         q.px[0] = S.it_f[0][it]; q.py[0] = S.it_f[1][it]; q.px[1] = S.it_f[2][it];
                         q.py[1] = S.it_f[3][it]; q.px[2] = S.it_f[4][it]; q.py[2] = S.it_f[5][it];
                         setup_normals(q);
-                        float thr[3]; // 0.0 or the smallest subnormal (bit pattern 1), see edge_thresholds()
-#pragma unroll
-                        for (int k = 0; k < 3; k++) thr[k] = __uint_as_float((box >> (24 + k)) & 1u);
+                        float thr[3];
+                        edge_thresholds(q, thr);
                         m = coverage_mask_fast(q, thr, tileX0 + lpx, tileY0 + lpy);
                     }
                     const uint32_t bal = __ballot_sync(0xffffffffu, m != 0u);
                     if (bal) { // warp-aggregated fragment allocation (ballot + popc prefix)
                         uint32_t slot = 0;
-                        // plain PTX atomics: the compiler would wrap atomicAdd/atomicExch in its own leader election
-                        if (lane == 0) slot = smem_atom_add(&S.nfrag, (uint32_t)__popc(bal));
+                        if (lane == 0) slot = atomicAdd(&S.nfrag, (uint32_t)__popc(bal));
                         slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(bal & lanemask_lt());
                         if (m) {
                             cov_try++;
                             if (slot < POOL) {
                                 S.u.fr.meta[slot] = it | (p << 8) | (m << 16);
-                                S.u.fr.next[slot] = (uint16_t)smem_atom_exch(&S.head[p], slot);
+                                S.u.fr.next[slot] = (uint16_t)atomicExch(&S.head[p], slot);
                             } else {
                                 S.ovf = 1u;
                             }
@@ -578,24 +577,36 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                     }
                 }
                 __syncthreads();
+                // S.nfrag keeps counting past the pool: the chunk's true fragment count.  fit_units() = the units that
+                // would have filled 7/8 of the pool at this chunk's fragments-per-unit ratio (units <= 6144: 32-bit)
                 if (!S.ovf) {
                     c_cov += cov_try;
+                    if (tid == 0) S.unit_budget = min((uint32_t)UNIT_CAP, (3u * S.unit_budget + fit_units((uint32_t)units, S.nfrag)) / 4u + 64u);
                     break;
                 }
-                // The chunk's fragments do not fit the pool.  Nothing has touched the tile state yet:
-                // drop them and retry with half the items.  Chunks must follow submission order, so an
-                // unsorted list is sorted first.
+                const uint32_t fit = fit_units((uint32_t)units, S.nfrag);
+                // The chunk's fragments do not fit the pool.  Nothing has touched the tile state yet: drop them
+                // and retry with the prefix of items the measured ratio says will fit.  Chunks must follow
+                // submission order, so an unsorted list is sorted first.
                 __syncthreads();
                 S.head[tid] = FR_NONE;
                 if (tid == 0) {
                     S.nfrag = 0;
                     S.ovf = 0;
+                    S.unit_budget = fit;
                 }
                 if (!sorted) {
                     need_sort = true;
                     break;
                 }
-                cnt = max(1, cnt >> 1);
+                {
+                    int lo = 1, hi = max(1, cnt - 1); // largest c < cnt with pre[c] <= fit (fit < units, so it shrinks)
+                    while (hi - lo > 0) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (S.pre[mid] <= fit) lo = mid; else hi = mid - 1;
+                    }
+                    cnt = lo;
+                }
                 __syncthreads();
             }
             if (need_sort) {

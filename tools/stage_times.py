@@ -7,16 +7,18 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     import torch
     from rusterizer_b200 import scenes
     from rusterizer_b200.render import Renderer
-    sc = scenes.sphere_scene(1001, 501)
+    which = os.environ.get("RZ_SCENE", "c2")  # c2 | overdraw | c4i | c4ii | c3 | c1
+    sc = {"c2": lambda: scenes.sphere_scene(1001, 501), "overdraw": lambda: scenes.overdraw_scene(),
+          "c4i": lambda: scenes.sphere_scene(1001, 501, width=8192, height=8192), "c4ii": lambda: scenes.fullscreen_quad_scene(),
+          "c3": lambda: scenes.near_clip_scene(), "c1": lambda: scenes.default_scene(1.0)}[which]()
     r = Renderer(sc.width, sc.height)
     r.uniforms().bind_texture(0, sc.texture)
-    m = r.upload(sc.draws[0].mesh)
-    b = r.uniforms().write_block(); b.projection = sc.projection; b.view = sc.view; b.world = sc.draws[0].world
+    ms = [r.upload(d.mesh) for d in sc.draws]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     acc = {}
     for i in range(25):
         flush.zero_(); torch.cuda.synchronize()
-        r.render(m, 0, 0); r.framebuffer_device()
+        scenes.render_scene(r, sc, ms); r.framebuffer_device()
         if i >= 5:
             for k, v in r.timings().items(): acc.setdefault(k, []).append(v)
     print(json.dumps({k: round(1e3 * sorted(v)[len(v) // 2], 1) for k, v in acc.items()}))
@@ -29,4 +31,4 @@ else:
         if lib != "default": env["RZ_B200_LIB"] = os.path.abspath(lib)
         lib = "@".join([lib] + kv)
         out = subprocess.run([sys.executable, __file__, "--child"], env=env, capture_output=True, text=True)
-        print(lib, "median us:", out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:])
+        print(lib, os.environ.get("RZ_SCENE", "c2"), "median us:", out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:])
