@@ -13,9 +13,18 @@ constexpr int UNIT_CAP = 6144;      // (item, pixel) work units per chunk (one b
 constexpr int POOL = 1024;          // per-chunk fragment records held in shared memory
 constexpr int SORT_CAP = 2048;      // tile lists up to this length are sorted in shared memory
 constexpr int GEOM_SMALL_DIM = 16;  // bbox extent up to which a triangle is binned directly (spans at most 2x2 tiles)
-constexpr int GEOM_THIN_PX = 64;    // bbox area up to which a thin triangle is pre-rasterised exactly
-constexpr float GEOM_THIN_AREA2 = 1.0f; // 2x screen area below which a small triangle is pre-rasterised
-constexpr int VERTEX_PER_THREAD = 4; // vertices per thread of the vertex stage
+#ifndef RZ_GEOM_THIN_PX
+#define RZ_GEOM_THIN_PX 64
+#endif
+#ifndef RZ_GEOM_THIN_AREA2
+#define RZ_GEOM_THIN_AREA2 1.0f
+#endif
+constexpr int GEOM_THIN_PX = RZ_GEOM_THIN_PX;    // bbox area up to which a thin triangle is pre-rasterised exactly
+constexpr float GEOM_THIN_AREA2 = RZ_GEOM_THIN_AREA2; // 2x screen area below which a small triangle is pre-rasterised
+#ifndef RZ_VERTEX_PER_THREAD
+#define RZ_VERTEX_PER_THREAD 1 // 1, 2 and 4 measured on one box: 41.0 / 42.0 / 42.8 us for the C2 geometry stage
+#endif
+constexpr int VERTEX_PER_THREAD = RZ_VERTEX_PER_THREAD; // vertices per thread of the vertex stage
 constexpr int LARGE_SLAB_ROWS = 8;  // tile rows per large-triangle binning work item
 constexpr int MAX_POLY = 10;        // clipped polygon vertex budget (=> <= 8 fan triangles, 3 key bits)
 
