@@ -169,6 +169,14 @@ int rz_shared_free(rz_ctx *ctx, void *dev_ptr);
 int rz_signal(rz_ctx *ctx, uint32_t *const *flags, uint32_t n, uint32_t value); /* n <= 16 flags, one kernel */
 int rz_wait_flags(rz_ctx *ctx, const uint32_t *flags, uint32_t n, uint32_t stride_bytes, uint32_t value,
                   uint32_t timeout_ms);
+/* Scissor rectangle, the extension the reference sketches in Rasterizer::bounding_box
+ * (rasterizer/mod.rs:349-350: "the user would supply a scissoring rect that could be used to bound the
+ * triangles"): every triangle's pixel bounding box is intersected with [x0,x1) x [y0,y1) instead of the
+ * viewport, so nothing outside it is rasterised; those pixels resolve to the clear colour.  The rect is
+ * clamped to the viewport; it applies to the draws of the frames executed after the call (one rect per
+ * frame, like the resolution).  Default: the whole viewport. */
+int rz_set_scissor(rz_ctx *ctx, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1);
+
 /* Interleaved screen-space sharding: this ctx owns the bands k of `band_tile_rows` tile rows with
  * k % world == rank (inside its row range, normally the whole frame), which balances a centred object
  * across the GPUs; only owned tiles are rasterised, resolved and written, so with rz_framebuffer_async

@@ -72,6 +72,7 @@ class OracleLib:
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_bind_texture.argtypes = [C.c_void_p, C.c_uint32, u8p, C.c_uint32, C.c_uint32, C.c_uint32]
         L.orc_write_block.argtypes = [C.c_void_p, fp, fp, fp]
+        L.orc_set_scissor.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         L.orc_render.argtypes = [C.c_void_p, fp, fp, C.c_uint32, u32p, C.c_uint64, C.c_uint32, C.c_uint32]
         L.orc_rasterize.argtypes = [C.c_void_p, fp, fp, C.c_uint64, C.c_uint32]
         L.orc_vertex_stage.argtypes = [C.c_void_p, fp, C.c_uint32, fp]
@@ -234,6 +235,9 @@ class OracleRenderer:
         rc = self.L.lib.orc_bind_texture(self.ctx, index, _u8p(t), w, h, tw)
         if rc != 0:
             raise ValueError(f"orc_bind_texture failed: {rc}")
+
+    def set_scissor(self, x0, y0, x1, y1):
+        self.L.lib.orc_set_scissor(self.ctx, x0, y0, x1, y1)
 
     def write_block(self, world=None, view=None, projection=None):
         arrs = [None if m is None else f32(m).reshape(16) for m in (world, view, projection)]

@@ -64,6 +64,7 @@ typedef struct {
 
 typedef struct orc_ctx {
     uint32_t width, height;
+    uint32_t sc_x0, sc_y0, sc_x1, sc_y1; /* scissor rect (extension suggested at mod.rs:349-350); default = viewport */
     uint32_t *color;   /* [w*h][4]  buffers.rs:83-105 */
     float *depth;      /* [w*h][4]  buffers.rs:129-147 */
     uint32_t *owner;   /* [w*h][4]  oracle-only: order key of the last writer */
@@ -468,6 +469,7 @@ orc_ctx *orc_create(uint32_t width, uint32_t height) {
     size_t n = (size_t)width * height;
     c->width = width;
     c->height = height;
+    c->sc_x0 = 0; c->sc_y0 = 0; c->sc_x1 = width; c->sc_y1 = height;
     c->color = (uint32_t *)malloc(n * 4 * sizeof(uint32_t));
     c->depth = (float *)malloc(n * 4 * sizeof(float));
     c->owner = (uint32_t *)malloc(n * 4 * sizeof(uint32_t));
@@ -497,6 +499,13 @@ void orc_destroy(orc_ctx *c) {
     free(c->tile_mask[0]); free(c->tile_mask[1]); free(c->vs_out);
     for (uint32_t i = 0; i < c->n_tex; i++) free(c->tex[i].buf);
     free(c);
+}
+
+/* Scissor rect [x0,x1) x [y0,y1), clamped to the viewport; x0 >= x1 or y0 >= y1 draws nothing. */
+int orc_set_scissor(orc_ctx *c, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1) {
+    c->sc_x0 = x0 < c->width ? x0 : c->width; c->sc_x1 = x1 < c->width ? x1 : c->width;
+    c->sc_y0 = y0 < c->height ? y0 : c->height; c->sc_y1 = y1 < c->height ? y1 : c->height;
+    return 0;
 }
 
 /* uniform.rs:29-33 : index must equal the number of bound textures */
@@ -584,8 +593,10 @@ static int rasterize_one(orc_ctx *c, const tri_t *raw, uint32_t fs_id, uint32_t 
         float xy6[6] = {r.px[0], r.py[0], r.px[1], r.py[1], r.px[2], r.py[2]};
         uint64_t bb[4];
         orc_pixel_bbox(xy6, bb);
-        uint64_t min_x = bb[0], max_x = bb[1] < W ? bb[1] : W;
-        uint64_t min_y = bb[2], max_y = bb[3] < H ? bb[3] : H;
+        /* "the user would supply a scissoring rect that could be used to bound the triangles" (mod.rs:349-350):
+         * the viewport bounds 0..width / 0..height become the scissor rect (default: the viewport itself) */
+        uint64_t min_x = bb[0] > c->sc_x0 ? bb[0] : c->sc_x0, max_x = bb[1] < c->sc_x1 ? bb[1] : c->sc_x1;
+        uint64_t min_y = bb[2] > c->sc_y0 ? bb[2] : c->sc_y0, max_y = bb[3] < c->sc_y1 ? bb[3] : c->sc_y1;
         for (uint64_t i = min_y; i < max_y; i++) {
             for (uint64_t j = min_x; j < max_x; j++) {
                 c->cnt.n_bbox_px++;

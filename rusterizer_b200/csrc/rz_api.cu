@@ -49,6 +49,7 @@ struct rz_ctx {
     uint32_t W = 0, H = 0, tiles_x = 0, tiles_y = 0;
     uint32_t row_begin = 0, row_end = 0;
     uint32_t il_band = 0, il_rank = 0, il_world = 1;
+    uint32_t sc_x0 = 0, sc_y0 = 0, sc_x1 = 0, sc_y1 = 0; // scissor rect (rz_set_scissor), default = viewport
     cudaStream_t own_stream = nullptr, stream = nullptr;
     float world[16], view[16], proj[16];
     std::vector<Texture> textures;
@@ -230,6 +231,7 @@ int rz_create(int device, uint32_t width, uint32_t height, rz_ctx **out) {
     c->tiles_x = (width + TW - 1) / TW;
     c->tiles_y = (height + TH - 1) / TH;
     c->row_begin = 0; c->row_end = height;
+    c->sc_x1 = width; c->sc_y1 = height;
     static const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}; // uniform.rs:18-27
     memcpy(c->world, ident, 64); memcpy(c->view, ident, 64); memcpy(c->proj, ident, 64);
 #define CU_NEW(call)                                                                       \
@@ -448,6 +450,7 @@ static FrameParams make_params(rz_ctx *c, uint32_t *out_base) {
     P.tiles_x = c->tiles_x; P.tiles_y = c->tiles_y;
     P.row_begin = c->row_begin; P.row_end = c->row_end;
     P.il_band = c->il_band; P.il_rank = c->il_rank; P.il_world = c->il_world;
+    P.scissor = make_uint4(c->sc_x0, c->sc_y0, c->sc_x1, c->sc_y1);
     P.ty_begin = c->row_begin / TH;
     P.ty_end = (c->row_end + TH - 1) / TH;
     P.rec_cap = c->rec_cap; P.bin_cap = c->bin_cap; P.large_cap = c->large_cap;
@@ -791,6 +794,13 @@ int rz_set_row_range(rz_ctx *c, uint32_t row_begin, uint32_t row_end) {
         return fail(c, RZ_E_INVALID, "rz_set_row_range: rows must be tile-aligned (%d) and inside the framebuffer", TH);
     c->row_begin = row_begin;
     c->row_end = row_end;
+    return RZ_OK;
+}
+
+int rz_set_scissor(rz_ctx *c, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1) {
+    if (!c) return RZ_E_INVALID;
+    c->sc_x0 = std::min(x0, c->W); c->sc_x1 = std::min(x1, c->W);
+    c->sc_y0 = std::min(y0, c->H); c->sc_y1 = std::min(y1, c->H);
     return RZ_OK;
 }
 

@@ -165,16 +165,17 @@ __device__ __forceinline__ float sample_depth(const Setup &s, int X, int Y, int 
 struct BBox {
     uint32_t x0, x1, y0, y1;
 };
-__device__ __forceinline__ BBox pixel_bbox(const Setup &s, uint32_t W, uint32_t H) {
+// `sc` = {x0, y0, x1, y1}: the viewport, or the scissor rect the reference suggests at mod.rs:349-350.
+__device__ __forceinline__ BBox pixel_bbox(const Setup &s, const uint4 sc) {
     float mnx = fminf(fminf(fminf(3.40282347e+38f, s.px[0]), s.px[1]), s.px[2]);
     float mxx = fmaxf(fmaxf(fmaxf(-3.40282347e+38f, s.px[0]), s.px[1]), s.px[2]);
     float mny = fminf(fminf(fminf(3.40282347e+38f, s.py[0]), s.py[1]), s.py[2]);
     float mxy = fmaxf(fmaxf(fmaxf(-3.40282347e+38f, s.py[0]), s.py[1]), s.py[2]);
     BBox b;
-    b.x0 = sat_u32(floorf(mnx));
-    b.x1 = min(sat_u32(ceilf(mxx)), W);
-    b.y0 = sat_u32(floorf(mny));
-    b.y1 = min(sat_u32(ceilf(mxy)), H);
+    b.x0 = max(sat_u32(floorf(mnx)), sc.x);
+    b.x1 = min(sat_u32(ceilf(mxx)), sc.z);
+    b.y0 = max(sat_u32(floorf(mny)), sc.y);
+    b.y1 = min(sat_u32(ceilf(mxy)), sc.w);
     return b;
 }
 

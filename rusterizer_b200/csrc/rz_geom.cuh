@@ -75,7 +75,7 @@ __device__ __forceinline__ void emit_setup(const FrameParams &P, const DrawParam
     setup_normals(s); // inv_2x_area is recomputed by the tile stage; nothing here needs it
     lc.c[C_TRIS_SETUP]++;
 
-    BBox b = pixel_bbox(s, P.W, P.H);
+    BBox b = pixel_bbox(s, P.scissor);
     b.y0 = max(b.y0, P.row_begin); // screen-space shard owned by this ctx
     b.y1 = min(b.y1, P.row_end);
     if (b.x0 >= b.x1 || b.y0 >= b.y1) return;
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
         Setup s;
         uint32_t key;
         load_setup(P.recs, li.rec, s, key);
-        BBox b = pixel_bbox(s, P.W, P.H);
+        BBox b = pixel_bbox(s, P.scissor);
         b.y0 = max(b.y0, P.row_begin);
         b.y1 = min(b.y1, P.row_end);
         const uint32_t tx0 = b.x0 / TW, tx1 = (b.x1 - 1) / TW + 1, ntx = tx1 - tx0;

@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
             if (valid) {
                 rec = (uint32_t)__ldcg(bin + item);
                 load_setup(P.recs, rec, s, key);
-                BBox b = pixel_bbox(s, P.W, P.H);
+                BBox b = pixel_bbox(s, P.scissor);
                 const int x0 = max((int)b.x0, tileX0), x1 = min((int)b.x1, tileX0 + TW);
                 const int y0 = max((int)b.y0, tileY0), y1 = min((int)b.y1, tileY0 + TH);
                 if (x0 < x1 && y0 < y1) {

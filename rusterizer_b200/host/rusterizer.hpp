@@ -237,6 +237,9 @@ class Renderer { // render.rs:38-127 without the minifb window
         return fb_;
     }
 
+    // Scissor rect [x0,x1) x [y0,y1): the extension sketched in Rasterizer::bounding_box (rasterizer/mod.rs:349-350)
+    void set_scissor(uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1) { check(rz_set_scissor(ctx_, x0, y0, x1, y1)); }
+
     // Headless replacement of Renderer::display (render.rs:116-127): the last framebuffer() as a file
     void save_png(const std::string &path) const { image::write_png(path, fb_.data(), width_, height_); }
     void save_ppm(const std::string &path) const { image::write_ppm(path, fb_.data(), width_, height_); }

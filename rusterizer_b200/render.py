@@ -35,7 +35,7 @@ ABI_SYMBOLS = (
     "rz_create", "rz_destroy", "rz_set_stream", "rz_bind_texture", "rz_write_block", "rz_read_block",
     "rz_mesh_create", "rz_mesh_destroy", "rz_render", "rz_render_host", "rz_framebuffer",
     "rz_framebuffer_async", "rz_framebuffer_host_async", "rz_sync", "rz_shared_alloc", "rz_shared_open",
-    "rz_shared_close", "rz_shared_free", "rz_signal", "rz_wait_flags", "rz_set_row_range", "rz_set_row_interleave", "rz_tile_width", "rz_tile_height",
+    "rz_shared_close", "rz_shared_free", "rz_signal", "rz_wait_flags", "rz_set_row_range", "rz_set_row_interleave", "rz_set_scissor", "rz_tile_width", "rz_tile_height",
     "rz_counters", "rz_reset_counters", "rz_timings", "rz_launch_count", "rz_debug_capture",
     "rz_debug_read", "rz_debug_tile_times", "rz_debug_vertex_stage", "rz_last_error", "rz_version",
 )
@@ -102,6 +102,7 @@ def load_library() -> C.CDLL:
     L.rz_wait_flags.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     L.rz_set_row_range.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.rz_set_row_interleave.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.rz_set_scissor.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     L.rz_tile_width.restype = C.c_uint32
     L.rz_tile_height.restype = C.c_uint32
     L.rz_counters.argtypes = [vp, C.POINTER(CountersT)]
@@ -322,6 +323,10 @@ class Renderer:
 
     def set_row_range(self, row_begin: int, row_end: int):
         self._check(self._L.rz_set_row_range(self._ctx, row_begin, row_end))
+
+    def set_scissor(self, x0: int, y0: int, x1: int, y1: int):
+        """Scissor rect [x0,x1) x [y0,y1) (the extension sketched at rasterizer/mod.rs:349-350)."""
+        self._check(self._L.rz_set_scissor(self._ctx, x0, y0, x1, y1))
 
     def set_row_interleave(self, band_tile_rows: int, rank: int, world: int):
         self._check(self._L.rz_set_row_interleave(self._ctx, band_tile_rows, rank, world))

@@ -46,6 +46,7 @@ class Scene:
     draws: list = field(default_factory=list)
     texture: Texture | None = None          # texture 0
     extra_textures: list = field(default_factory=list)  # textures 1.. (bind order, uniform.rs:29-33)
+    scissor: tuple | None = None            # (x0, y0, x1, y1), the extension sketched at rasterizer/mod.rs:349-350
 
     @property
     def n_triangles(self) -> int:

@@ -14,6 +14,8 @@ def oracle_render(scene, fast=False):
         for k, t in enumerate(getattr(scene, "extra_textures", [])):
             r.bind_texture(k + 1, t.texels)
     r.write_block(view=scene.view, projection=scene.projection)
+    if getattr(scene, "scissor", None):
+        r.set_scissor(*scene.scissor)
     for d in scene.draws:
         r.write_block(world=d.world)
         r.render(d.mesh.vertices, d.mesh.attributes, d.mesh.indices, 0, d.fs)
@@ -35,6 +37,8 @@ def gpu_render(scene, debug=True, device_resident=False, renderer=None):
             r.uniforms().bind_texture(k + 1, t)
     if debug:
         r.debug_capture(True)
+    if getattr(scene, "scissor", None):
+        r.set_scissor(*scene.scissor)
     r.reset_counters()
     meshes = [r.upload(d.mesh) for d in scene.draws] if device_resident else None
     render_scene(r, scene, meshes)

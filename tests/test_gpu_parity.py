@@ -466,3 +466,23 @@ def test_shader_registry_texture_index_and_blend():
         r.render(scenes.triangle(), 0, W(scenes.FS_COLOR, 1))
     assert e.value.code == -1
     r.close()
+
+
+@pytest.mark.parametrize("rect", [(37, 21, 251, 163), (0, 0, 320, 180), (100, 50, 101, 51), (64, 48, 64, 120), (300, 170, 9999, 9999)])
+def test_scissor_rect(rect):
+    """rz_set_scissor (the extension the reference sketches at rasterizer/mod.rs:349-350): the triangles' pixel bounding
+    boxes are intersected with the rect instead of the viewport -- small and large triangles, a near-clipped one,
+    rects that cut through tiles, a one-pixel rect, an empty rect and one that is clamped to the viewport."""
+    base = scenes.default_scene(1.0, width=320, height=180)
+    clip = scenes.clip_test_scene(0.4, width=320, height=180)
+    sph = scenes.sphere_scene(65, 33, width=320, height=180)
+    draws = base.draws + [scenes.Draw(clip.draws[0].mesh, clip.draws[0].world, scenes.FS_COLOR),
+                          scenes.Draw(sph.draws[0].mesh, mathx.translate(1.5, -1.0, 2.0), scenes.FS_TEXTURE)]
+    s = scenes.Scene("scissor", 320, 180, base.view, base.projection, draws, base.texture, scissor=rect)
+    o, g = check(s)
+    x0, y0, x1, y1 = (min(rect[0], 320), min(rect[1], 180), min(rect[2], 320), min(rect[3], 180))
+    outside = np.ones((180, 320), bool)
+    outside[y0:y1, x0:x1] = False
+    assert (g["fb"][outside] == 0xFF191919).all()
+    full = oracle_render(scenes.Scene("noscissor", 320, 180, base.view, base.projection, draws, base.texture))
+    assert np.array_equal(g["fb"][~outside], full["fb"][~outside])  # inside the rect nothing changes

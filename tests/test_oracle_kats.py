@@ -426,3 +426,23 @@ def test_registry_blend_shader_arithmetic():
     with pytest.raises(Exception):
         r.render(pos, attrs, idx, 0, 3 | (2 << 8))  # texture 2 is not bound
     r.close()
+
+
+def test_scissor_bounds_the_bbox_walk():
+    """Scissor extension (rasterizer/mod.rs:349-350): the bbox walk is bounded by the rect instead of the viewport,
+    so n_bbox_px is exactly the rect's share and pixels outside keep the clear colour."""
+    from oracle.oracle import OracleRenderer
+
+    r = OracleRenderer(32, 32)
+    pos = np.array([[-1, -1, 0.5], [1, -1, 0.5], [1, 1, 0.5], [-1, 1, 0.5]], np.float32)
+    attrs = np.tile(np.float32([1, 0, 0, 1, 0, 0]), (4, 1))
+    idx = np.array([0, 2, 1, 0, 3, 2], np.uint32)
+    r.set_scissor(5, 7, 20, 9)
+    r.render(pos, attrs, idx, 0, 1)
+    c = r.counters()
+    fb = r.framebuffer()
+    assert c["n_bbox_px"] == 2 * (20 - 5) * (9 - 7)      # both triangles' boxes cover the viewport
+    inside = np.zeros((32, 32), bool)
+    inside[7:9, 5:20] = True
+    assert (fb[~inside] == 0xFF191919).all() and (fb[inside] == 0xFFFF0000).all()
+    r.close()
