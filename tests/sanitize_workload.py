@@ -1,13 +1,13 @@
 #!/usr/bin/env python
-"""tools/sanitize.py: a few small frames through every kernel path (small + large + clipped triangles, all fragment
+"""tests/sanitize_workload.py: a few small frames through every kernel path (small + large + clipped triangles, all fragment
 shaders, registry extension, scissor, streaming host path, interleaved bands), compared with the oracle.  Meant to be
 run under compute-sanitizer:
-    compute-sanitizer --tool memcheck  python tools/sanitize.py
-    compute-sanitizer --tool racecheck python tools/sanitize.py
-    compute-sanitizer --tool initcheck python tools/sanitize.py
+    compute-sanitizer --tool memcheck  python tests/sanitize_workload.py
+    compute-sanitizer --tool racecheck python tests/sanitize_workload.py
+    compute-sanitizer --tool initcheck python tests/sanitize_workload.py
 """
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/ may use the oracle; tools/ may not
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from helpers import compare, gpu_render, oracle_render
