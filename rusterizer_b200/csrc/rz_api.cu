@@ -87,6 +87,7 @@ struct rz_ctx {
     uint32_t vert_cap = 0;
     uint32_t rec_cap = 0, bin_cap = 0, large_cap = 0;
     bool debug = false;
+    bool use_direct = true; // tile-kernel instantiation with the large-item path (see enqueue_frame)
 
     FrameState *h_state = nullptr; // pinned
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -264,10 +265,14 @@ int rz_create(int device, uint32_t width, uint32_t height, rz_ctx **out) {
         CU_NEW(cudaEventCreateWithFlags(&c->ev_d2h_done[i], cudaEventDisableTiming));
     }
     c->d_out_ring[0] = c->d_out;
-    CU_NEW(cudaFuncSetAttribute(tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemT<false>)));
-    CU_NEW(cudaFuncSetAttribute(tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemT<false>)));
-    CU_NEW(cudaFuncSetAttribute(tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemT<true>)));
-    CU_NEW(cudaFuncSetAttribute(tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmemT<true>)));
+    {
+        struct { const void *f; size_t smem; } k[] = {
+            {(const void *)tile_kernel<false, false, false>, sizeof(TileSmemT<false>)}, {(const void *)tile_kernel<false, false, true>, sizeof(TileSmemT<false>)},
+            {(const void *)tile_kernel<false, true, false>, sizeof(TileSmemT<false>)},  {(const void *)tile_kernel<false, true, true>, sizeof(TileSmemT<false>)},
+            {(const void *)tile_kernel<true, false, false>, sizeof(TileSmemT<true>)},   {(const void *)tile_kernel<true, false, true>, sizeof(TileSmemT<true>)},
+            {(const void *)tile_kernel<true, true, false>, sizeof(TileSmemT<true>)},    {(const void *)tile_kernel<true, true, true>, sizeof(TileSmemT<true>)}};
+        for (auto &e : k) CU_NEW(cudaFuncSetAttribute(e.f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem));
+    }
 #undef CU_NEW
     *out = c;
     return RZ_OK;
@@ -557,14 +562,18 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     if (n_tiles) {
         bool ext = false; // does any draw use the shader-registry extension (texture index != 0, TextureBlend)?
         for (auto &d : c->draws) ext = ext || (d.fs >> 8) != 0 || (d.fs & 0xFFu) == RZ_FS_TEXTURE_BLEND;
-        if (c->debug && ext)
-            CU(c, launch_pdl(tile_kernel<true, true>, tile_grid, dim3(NT), sizeof(TileSmemT<true>), st, P));
-        else if (c->debug)
-            CU(c, launch_pdl(tile_kernel<true, false>, tile_grid, dim3(NT), sizeof(TileSmemT<true>), st, P));
-        else if (ext)
-            CU(c, launch_pdl(tile_kernel<false, true>, tile_grid, dim3(NT), sizeof(TileSmemT<false>), st, P));
-        else
-            CU(c, launch_pdl(tile_kernel<false, false>, tile_grid, dim3(NT), sizeof(TileSmemT<false>), st, P));
+        // DIRECT: the pixel-parallel path for chunks of large items is only compiled into the instantiations used
+        // when the last frame whose state the host has seen queued large triangles (a stale guess costs speed only)
+        const bool dir = c->use_direct;
+#define RZ_TILE_LAUNCH(D, E, R) CU(c, launch_pdl(tile_kernel<D, E, R>, tile_grid, dim3(NT), sizeof(TileSmemT<D>), st, P))
+        if (c->debug) {
+            if (ext) { if (dir) RZ_TILE_LAUNCH(true, true, true); else RZ_TILE_LAUNCH(true, true, false); }
+            else     { if (dir) RZ_TILE_LAUNCH(true, false, true); else RZ_TILE_LAUNCH(true, false, false); }
+        } else {
+            if (ext) { if (dir) RZ_TILE_LAUNCH(false, true, true); else RZ_TILE_LAUNCH(false, true, false); }
+            else     { if (dir) RZ_TILE_LAUNCH(false, false, true); else RZ_TILE_LAUNCH(false, false, false); }
+        }
+#undef RZ_TILE_LAUNCH
         c->launches++;
     }
     if (timed) CU(c, cudaEventRecord(c->ev[3], st));
@@ -609,6 +618,7 @@ int rz_framebuffer(rz_ctx *c, uint32_t *out_host, const uint32_t **out_device) {
         CU(c, cudaMemcpyAsync(c->h_state, dfs, sizeof(FrameState), cudaMemcpyDeviceToHost, st));
         CU(c, cudaStreamSynchronize(st));
         const uint32_t flags = c->h_state->err;
+        c->use_direct = c->h_state->n_large > 0;
         if (!flags) break;
         CU(c, cudaMemsetAsync(&dfs->err, 0, sizeof(uint32_t), st));
         if (flags & ERR_INDEX) {
@@ -700,6 +710,7 @@ int rz_sync(rz_ctx *c) {
     CU(c, cudaMemcpyAsync(c->h_state, dfs, sizeof(FrameState), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaStreamSynchronize(c->down_stream));
+    c->use_direct = c->h_state->n_large > 0;
     if (c->h_state->peer_timeout) {
         CU(c, cudaMemsetAsync(&dfs->peer_timeout, 0, sizeof(uint32_t), c->stream));
         return fail(c, RZ_E_PEER, "rz_wait_flags: a peer did not signal within the timeout");

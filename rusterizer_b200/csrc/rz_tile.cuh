@@ -257,6 +257,91 @@ __device__ __forceinline__ void sort_tile_list(SM &S, unsigned long long *bin, i
     __syncthreads();
 }
 
+// Chunk dominated by large items: pixel-parallel walk with deferred shading (see the call site).  Only compiled
+// into the DIRECT instantiations of the tile kernel: its register needs perturb the allocation of the fragment
+// path that small-triangle workloads live in (C2 tile stage 90 -> 92 us on the same box), so frames without
+// large triangles run an instantiation that does not contain it.
+template <bool DBG, bool EXT>
+__device__ __forceinline__ uint4 direct_chunk(const FrameParams &P, TileSmemT<DBG> &S, int cnt, bool sorted, int X, int Y) {
+    const int tid = threadIdx.x, lx = tid % TW, ly = tid / TW;
+    uint32_t c_cov = 0, c_shaded = 0, c_samples = 0, c_oob = 0;
+    // the walk needs submission order: an unsorted chunk (it is the whole tile list then) is ranked by
+    // order key right in the item table instead of being sorted and reloaded
+    if (tid < cnt) {
+        uint32_t rank = (uint32_t)tid;
+        if (!sorted) {
+            rank = 0;
+            const uint32_t mykey = S.it_key[tid];
+            for (int j = 0; j < cnt; j++) rank += S.it_key[j] < mykey ? 1u : 0u;
+        }
+        S.unit_item[rank] = (uint8_t)tid; // the unit table is free in this path
+    }
+    __syncthreads();
+    float4 d = *reinterpret_cast<const float4 *>(&S.depth[tid * 4]);
+    uint32_t own = 0xFFFFFFFFu; // 4 x u8: chunk item that owns sample k (0xFF: untouched in this chunk)
+    uint32_t omp = 0u;          // 4 x 5 bits: that fragment's post-depth mask | (sample 0 covered) << 4
+    for (int r = 0; r < cnt; r++) {
+        const int it = (int)S.unit_item[r];
+        const uint32_t box = S.it_box[it];
+        const uint32_t rx = (uint32_t)lx - (box & 0xFFu), ry = (uint32_t)ly - ((box >> 8) & 0xFFu);
+        const uint32_t ibw = (box >> 16) & 0x1Fu;
+        if (rx >= ibw || ry * ibw >= S.pre[it + 1] - S.pre[it]) continue; // outside the in-tile bbox
+        Setup q;
+        q.px[0] = S.it_f[0][it]; q.py[0] = S.it_f[1][it]; q.px[1] = S.it_f[2][it];
+        q.py[1] = S.it_f[3][it]; q.px[2] = S.it_f[4][it]; q.py[2] = S.it_f[5][it];
+        setup_normals(q);
+        float thr[3];
+        edge_thresholds(q, thr);
+        const uint32_t m = coverage_mask_fast(q, thr, X, Y);
+        if (!m) continue;
+        c_cov++;
+        q.z[0] = S.it_f[6][it]; q.z[1] = S.it_f[7][it]; q.z[2] = S.it_f[8][it];
+        q.inv = S.it_f[9][it];
+        uint32_t mp = 0;
+        if (m & 1u) { const float z = sample_depth(q, X, Y, 0); if (z < d.x) { d.x = z; mp |= 1u; } } // strict < (mod.rs:374)
+        if (m & 2u) { const float z = sample_depth(q, X, Y, 1); if (z < d.y) { d.y = z; mp |= 2u; } }
+        if (m & 4u) { const float z = sample_depth(q, X, Y, 2); if (z < d.z) { d.z = z; mp |= 4u; } }
+        if (m & 8u) { const float z = sample_depth(q, X, Y, 3); if (z < d.w) { d.w = z; mp |= 8u; } }
+        if (!mp) continue;
+        c_shaded++;
+        c_samples += __popc(mp);
+        const uint32_t tag = mp | ((m & 1u) << 4);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if ((mp >> k) & 1u) {
+                own = (own & ~(0xFFu << (8 * k))) | ((uint32_t)it << (8 * k));
+                omp = (omp & ~(0x1Fu << (5 * k))) | (tag << (5 * k));
+            }
+    }
+    *reinterpret_cast<float4 *>(&S.depth[tid * 4]) = d;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t it = (own >> (8 * k)) & 0xFFu;
+        if (it == 0xFFu) continue;
+        bool first = true; // shade every surviving owner once (MSAA: one shader call per fragment)
+#pragma unroll
+        for (int j = 0; j < k; j++) first = first && ((own >> (8 * j)) & 0xFFu) != it;
+        if (!first) continue;
+        const uint32_t tag = (omp >> (5 * k)) & 0x1Fu;
+        Setup q;
+        q.px[0] = S.it_f[0][it]; q.py[0] = S.it_f[1][it]; q.px[1] = S.it_f[2][it];
+        q.py[1] = S.it_f[3][it]; q.px[2] = S.it_f[4][it]; q.py[2] = S.it_f[5][it];
+        q.z[0] = S.it_f[6][it]; q.z[1] = S.it_f[7][it]; q.z[2] = S.it_f[8][it];
+        q.inv = S.it_f[9][it];
+        setup_normals(q);
+        const float depth0 = (tag & 16u) ? sample_depth(q, X, Y, 0) : 0.0f; // FragCoords.depths[0] (mod.rs:458-463)
+        const uint32_t argb = shade<DBG, EXT>(P, q, S.it_rec[it], S.lut, X, Y, tag & 0xFu, depth0, c_oob);
+#pragma unroll
+        for (int j = k; j < 4; j++)
+            if (((own >> (8 * j)) & 0xFFu) == it) {
+                S.color[tid * 4 + j] = argb;
+                if (DBG) S.okey[tid * 4 + j] = S.it_key[it];
+            }
+    }
+    __syncthreads();
+    return make_uint4(c_cov, c_shaded, c_samples, c_oob);
+}
+
 // Tiles nothing was binned into: the box filter of four clear samples is the clear colour
 // (buffers.rs:5,111-125).  A warp handles a GROUP of 8 horizontally adjacent tiles (4 lanes per tile, one
 // 128-bit store per lane and row), so a row of empty tiles leaves the SM as 512 contiguous bytes -- full
@@ -302,7 +387,7 @@ __device__ __forceinline__ void clear_empty_tiles(const FrameParams &P, int lane
     }
 }
 
-template <bool DBG, bool EXT>
+template <bool DBG, bool EXT, bool DIRECT>
 __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef TileSmemT<DBG> SM;
@@ -513,6 +598,19 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 for (uint32_t k = 0; k < area && first + k < (uint32_t)UNIT_CAP; k++) S.unit_item[first + k] = (uint8_t)tid;
             }
             __syncthreads();
+            // ================= chunk dominated by large items: pixel-parallel, deferred shading =================
+            // When the items of the chunk cover the tile broadly (average in-tile bbox >= DIRECT_MIN_AREA pixels) the
+            // fragment machinery below only adds barriers: every thread keeps its pixel, walks the chunk's items in
+            // submission order (exact coverage, sample depths, strict-< depth test: the literal sequence of
+            // rasterizer/mod.rs:443-473), remembers per sample which item wrote it last together with that fragment's
+            // post-depth mask, and shades each surviving owner once at the end.  No fragment pool, three barriers.
+            if (DIRECT && cnt > 0 && S.pre[cnt] >= (uint32_t)DIRECT_MIN_AREA * (uint32_t)cnt) {
+                const uint4 dc = direct_chunk<DBG, EXT>(P, S, cnt, sorted, X, Y);
+                c_cov += dc.x; c_shaded += dc.y; c_samples += dc.z; c_oob += dc.w;
+                pos += cnt;
+                continue;
+            }
+
             // unit budget of this chunk: what the unit table can index, and what the fragment pool is expected to
             // hold given the fragments-per-unit ratio the last chunks of this CTA saw (a chunk whose fragments
             // overflow the pool has to redo its whole coverage pass, so it is cheaper to cut it beforehand)

@@ -11,6 +11,10 @@ constexpr int NT = 256;             // threads per CTA in every kernel
 constexpr int CHUNK = 255;          // items per triangle-parallel chunk (item id fits u8, 0xFF = none)
 constexpr int UNIT_CAP = 6144;      // (item, pixel) work units per chunk (one byte each in shared memory)
 constexpr int POOL = 1024;          // per-chunk fragment records held in shared memory
+#ifndef RZ_DIRECT_MIN_AREA
+#define RZ_DIRECT_MIN_AREA 192
+#endif
+constexpr int DIRECT_MIN_AREA = RZ_DIRECT_MIN_AREA; // average in-tile bbox (pixels) from which a chunk is walked pixel-parallel
 constexpr int SORT_CAP = 2048;      // tile lists up to this length are sorted in shared memory
 constexpr int GEOM_SMALL_DIM = 16;  // bbox extent up to which a triangle is binned directly (spans at most 2x2 tiles)
 #ifndef RZ_GEOM_THIN_PX
