@@ -235,7 +235,7 @@ def main():
     ap.add_argument("--n-theta", type=int, default=501)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--inflight", type=int, default=3,
+    ap.add_argument("--inflight", type=int, default=6,
                     help="frames in flight per GPU in the timed region (one renderer context + stream each); frames mode only")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="tiles mode, N>1: 'peer' = tile kernels store their rows straight into rank 0's image over NVLink "

@@ -523,7 +523,8 @@ __global__ void __launch_bounds__(NT) order_kernel(FrameParams P) {
     uint32_t base = 0;
     if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&P.fs->bucket_n[b], (uint32_t)__popc(peers));
     base = __shfl_sync(peers, base, leader);
-    P.busy[(size_t)b * P.tiles_x * P.tiles_y + base + __popc(peers & lanemask_lt())] = tile;
+    // the entry carries the list length too: the tile stage learns both with one load
+    P.busy[(size_t)b * P.tiles_x * P.tiles_y + base + __popc(peers & lanemask_lt())] = (unsigned long long)tile | ((unsigned long long)n << 32);
 }
 
 // ---- completion flags over peer memory (screen-space sharding, one process per GPU) ----

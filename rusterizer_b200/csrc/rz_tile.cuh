@@ -203,6 +203,9 @@ static_assert(sizeof(BigSetup) == 80, "BigSetup must be 20 words");
 
 constexpr uint32_t FR_NONE = 0xFFFFu;
 
+#ifndef RZ_B_REG_MAXFRAG
+#define RZ_B_REG_MAXFRAG 640 // chunks with more fragments (> 2.5 per pixel: overdraw) replay their pixel lists by re-walking
+#endif
 #ifndef RZ_BUDGET_TRIG
 #define RZ_BUDGET_TRIG 3u // a chunk is cut beforehand when its predicted fragments exceed 7/8 * (1 + TRIG/8) of the pool
 #endif
@@ -237,6 +240,7 @@ struct TileSmemT {
     uint32_t head[TILE_PX];               // per-pixel fragment list heads; reused as resolve staging
     uint32_t scan[NT / 32];
     uint32_t first_big, first_small, nfrag, ovf, cur_tile;
+    uint32_t bucket_end[ORDER_BUCKETS];   // prefix of the list-length class sizes (busy-list work order)
     uint32_t clr_cursor[NT / 32];         // per-warp cursor of the empty-tile clears
     uint32_t unit_budget;                 // adaptive work-unit budget of a chunk (fragment pool occupancy predictor)
 };
@@ -401,41 +405,45 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
 
     // ---- phase 1: persistent loop over the tiles that received triangles (dynamic work stealing) ----
     S.lut[tid] = fdiv((float)tid, 255.0f);
-    uint32_t bucket_end[ORDER_BUCKETS]; // prefix of the class sizes: work item w belongs to the first class with w < end
-    {
+    // prefix of the class sizes: work item w belongs to the first class with w < end
+    // (kept in shared memory: eight registers held over the whole tile loop were spilled instead)
+    if (tid == 0) {
         uint32_t acc = 0;
 #pragma unroll
         for (int b = 0; b < ORDER_BUCKETS; b++) {
             acc += P.fs->bucket_n[b];
-            bucket_end[b] = acc;
+            S.bucket_end[b] = acc;
         }
     }
-    const uint32_t n_busy = bucket_end[ORDER_BUCKETS - 1];
     // empty-tile clears: with a caller-owned destination they are spread over the loop (a few tile groups per
     // rasterised tile, cursor kept in shared memory), the rest follows after the loop
     if (lane == 0) S.clr_cursor[warp] = blockIdx.x * (NT / 32) + warp;
     if (tid == 0) S.unit_budget = UNIT_CAP;
     for (;;) {
-    __syncthreads(); // previous tile fully retired (also covers S.lut on the first trip)
+    __syncthreads(); // previous tile fully retired (also covers S.lut and S.bucket_end on the first trip)
     if (tid == 0) S.cur_tile = atomicAdd(&P.fs->tile_cursor, 1u);
     __syncthreads();
+    const uint32_t n_busy = S.bucket_end[ORDER_BUCKETS - 1];
     const uint32_t work = S.cur_tile;
     if (work >= n_busy) break;
     uint32_t tile;
+    int n;
     {
         uint32_t b = 0, start = 0;
 #pragma unroll
         for (int k = 0; k < ORDER_BUCKETS - 1; k++)
-            if (work >= bucket_end[k]) {
+            if (work >= S.bucket_end[k]) {
                 b = k + 1;
-                start = bucket_end[k];
+                start = S.bucket_end[k];
             }
-        tile = P.busy[(size_t)b * P.tiles_x * P.tiles_y + (work - start)];
+        // the entry carries the tile id and its list length (order_kernel): one load instead of two dependent ones
+        const unsigned long long e = __ldcg(P.busy + (size_t)b * P.tiles_x * P.tiles_y + (work - start));
+        tile = (uint32_t)e;
+        n = (int)min((uint32_t)(e >> 32), P.bin_cap);
     }
     const uint32_t tx = tile % P.tiles_x, ty = tile / P.tiles_x;
     const int tileX0 = tx * TW, tileY0 = ty * TH;
     const int X = tileX0 + lx, Y = tileY0 + ly;
-    const int n = (int)min(P.tile_count[tile], P.bin_cap);
     unsigned long long t_start = 0, t_ph[5] = {0, 0, 0, 0, 0};
 #define RZ_STAMP(k)                                                                                  \
     if (DBG && P.dbg_tile_time && tid == 0 && t_ph[k] == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[k]));
@@ -482,11 +490,11 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 S.first_big = CHUNK + 1;
                 S.first_small = CHUNK + 1;
             }
+            const int nvalid = min(CHUNK, n - pos);
             __syncthreads();
             if (valid && big) atomicMin(&S.first_big, (uint32_t)tid);
             if (valid && !big) atomicMin(&S.first_small, (uint32_t)tid);
             __syncthreads();
-            const int nvalid = min(CHUNK, n - pos);
             const int first_big = (int)S.first_big, first_small = (int)S.first_small;
 
             if (!sorted && first_big <= CHUNK) { // large items need the ordered walk
@@ -735,40 +743,106 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
             __syncthreads();
             RZ_STAMP(2) // A2 done
             // ---- phase B: thread = pixel; replay this pixel's fragments in submission order ----
-            // (depth test exactly as Rasterizer::depth_coverage + write_pixel, mod.rs:363-397).  A pixel
-            // holds 2-3 fragments on average, so the next one in key order is found by re-walking its
-            // list; the last writer of every sample is the fragment that stays visible.
+            // (depth test exactly as Rasterizer::depth_coverage + write_pixel, mod.rs:363-397); the last writer
+            // of every sample is the fragment that stays visible.  A pixel holds 2-3 fragments on average.
             {
                 const uint32_t h = S.head[tid];
+                const bool reg_lists = nfrag <= RZ_B_REG_MAXFRAG; // dense chunks: most lists exceed the register path
                 if (h != FR_NONE) {
                     float4 d = *reinterpret_cast<const float4 *>(&S.depth[tid * 4]);
                     uint32_t own0 = FR_NONE, own1 = FR_NONE, own2 = FR_NONE, own3 = FR_NONE;
-                    uint32_t last_key = 0;
-                    bool first = true;
-                    for (;;) {
-                        uint32_t best = FR_NONE, best_key = 0xFFFFFFFFu;
-                        for (uint32_t g = h; g != FR_NONE; g = S.u.fr.next[g]) {
-                            const uint32_t k = S.it_key[S.u.fr.meta[g] & 0xFFu];
-                            if ((first || k > last_key) && k < best_key) {
-                                best = g;
-                                best_key = k;
-                            }
-                        }
-                        if (best == FR_NONE) break;
-                        const uint32_t m = (S.u.fr.meta[best] >> 16) & 0xFu;
-                        const float4 z = S.u.fr.z[best];
+                    // one fragment of the replay: Rasterizer::depth_coverage + the depth half of write_pixel
+                    auto replay = [&](uint32_t g) {
+                        const uint32_t m = (S.u.fr.meta[g] >> 16) & 0xFu;
+                        const float4 z = S.u.fr.z[g];
                         uint32_t mp = 0;
-                        if ((m & 1u) && z.x < d.x) { mp |= 1u; d.x = z.x; own0 = best; } // strict < (mod.rs:374)
-                        if ((m & 2u) && z.y < d.y) { mp |= 2u; d.y = z.y; own1 = best; }
-                        if ((m & 4u) && z.z < d.z) { mp |= 4u; d.z = z.z; own2 = best; }
-                        if ((m & 8u) && z.w < d.w) { mp |= 8u; d.w = z.w; own3 = best; }
-                        S.u.fr.fin[best] = (uint8_t)mp; // post-depth mask; the visible bits are added below
+                        if ((m & 1u) && z.x < d.x) { mp |= 1u; d.x = z.x; own0 = g; } // strict < (mod.rs:374)
+                        if ((m & 2u) && z.y < d.y) { mp |= 2u; d.y = z.y; own1 = g; }
+                        if ((m & 4u) && z.z < d.z) { mp |= 4u; d.z = z.z; own2 = g; }
+                        if ((m & 8u) && z.w < d.w) { mp |= 8u; d.w = z.w; own3 = g; }
+                        S.u.fr.fin[g] = (uint8_t)mp; // post-depth mask; the visible bits are added below
                         if (mp) {
                             c_shaded++;
                             c_samples += __popc(mp);
                         }
-                        last_key = best_key;
-                        first = false;
+                    };
+                    // Lists of up to four fragments (nearly all of them) are walked ONCE: every fragment goes into
+                    // a register as key << 32 | coverage << 16 | fragment, a 5-exchange network orders them by key,
+                    // absent slots carry the key 0xFFFFFFFF (no triangle has it: a frame holds < 2^29 triangles,
+                    // key = 8 * number + fan index) and sort to the end.  Keys within a pixel list are distinct (one
+                    // fragment per item).  The masks stay in registers: one byte store per fragment at the end.
+                    const unsigned long long ABSENT = 0xFFFFFFFF00000000ull | FR_NONE;
+                    unsigned long long e0 = ABSENT, e1 = ABSENT, e2 = ABSENT, e3 = ABSENT;
+                    uint32_t g = h;
+#define RZ_ENTRY(e)                                                                                          \
+    {                                                                                                        \
+        const uint32_t meta_ = S.u.fr.meta[g];                                                               \
+        e = ((unsigned long long)S.it_key[meta_ & 0xFFu] << 32) | (meta_ & 0xF0000u) | g;                    \
+        g = S.u.fr.next[g];                                                                                  \
+    }
+                    if (reg_lists) RZ_ENTRY(e0)
+                    if (reg_lists && g != FR_NONE) {
+                        RZ_ENTRY(e1)
+                        if (g != FR_NONE) {
+                            RZ_ENTRY(e2)
+                            if (g != FR_NONE) RZ_ENTRY(e3)
+                        }
+                    }
+#undef RZ_ENTRY
+                    bool replayed = false;
+                    if (reg_lists && g == FR_NONE) {
+                        replayed = true;
+#define RZ_CX(a, b) { const unsigned long long lo_ = min(a, b), hi_ = max(a, b); a = lo_; b = hi_; }
+                        RZ_CX(e0, e1) RZ_CX(e2, e3) RZ_CX(e0, e2) RZ_CX(e1, e3) RZ_CX(e1, e2)
+#undef RZ_CX
+                        uint32_t mpk = 0u;      // post-depth mask of slot i in bits 4i..4i+3
+                        uint32_t ownk = 0xFFFFu; // slot that wrote sample s last in bits 4s..4s+3 (0xF: none)
+#define RZ_SLOT(i, e)                                                                                        \
+    if ((i) == 0 || e != ABSENT) {                                                                           \
+        const uint32_t m = ((uint32_t)e >> 16) & 0xFu;                                                       \
+        const float4 z = S.u.fr.z[(uint32_t)e & 0xFFFFu];                                                    \
+        uint32_t mp = 0;                                                                                     \
+        if ((m & 1u) && z.x < d.x) { mp |= 1u; d.x = z.x; ownk = (ownk & ~0x000Fu) | (uint32_t)(i); }        \
+        if ((m & 2u) && z.y < d.y) { mp |= 2u; d.y = z.y; ownk = (ownk & ~0x00F0u) | ((uint32_t)(i) << 4); } \
+        if ((m & 4u) && z.z < d.z) { mp |= 4u; d.z = z.z; ownk = (ownk & ~0x0F00u) | ((uint32_t)(i) << 8); } \
+        if ((m & 8u) && z.w < d.w) { mp |= 8u; d.w = z.w; ownk = (ownk & ~0xF000u) | ((uint32_t)(i) << 12); }\
+        mpk |= mp << (4 * (i));                                                                              \
+        if (mp) {                                                                                            \
+            c_shaded++;                                                                                      \
+            c_samples += __popc(mp);                                                                         \
+        }                                                                                                    \
+    }
+                        RZ_SLOT(0, e0) RZ_SLOT(1, e1) RZ_SLOT(2, e2) RZ_SLOT(3, e3)
+#undef RZ_SLOT
+                        // fin = post-depth mask | still-visible mask << 4 (the samples this slot wrote last)
+#define RZ_FIN(i, e)                                                                                         \
+    if ((i) == 0 || e != ABSENT) {                                                                           \
+        const uint32_t vis = ((ownk & 0xFu) == (uint32_t)(i) ? 1u : 0u) | (((ownk >> 4) & 0xFu) == (uint32_t)(i) ? 2u : 0u) | \
+                             (((ownk >> 8) & 0xFu) == (uint32_t)(i) ? 4u : 0u) | (((ownk >> 12) & 0xFu) == (uint32_t)(i) ? 8u : 0u); \
+        S.u.fr.fin[(uint32_t)e & 0xFFFFu] = (uint8_t)(((mpk >> (4 * (i))) & 0xFu) | (vis << 4));             \
+    }
+                        RZ_FIN(0, e0) RZ_FIN(1, e1) RZ_FIN(2, e2) RZ_FIN(3, e3)
+#undef RZ_FIN
+                    }
+                    if (!replayed)
+                    {
+                        // longer lists: the next fragment in key order is found by re-walking the list
+                        uint32_t last_key = 0;
+                        bool first = true;
+                        for (;;) {
+                            uint32_t best = FR_NONE, best_key = 0xFFFFFFFFu;
+                            for (uint32_t g2 = h; g2 != FR_NONE; g2 = S.u.fr.next[g2]) {
+                                const uint32_t k = S.it_key[S.u.fr.meta[g2] & 0xFFu];
+                                if ((first || k > last_key) && k < best_key) {
+                                    best = g2;
+                                    best_key = k;
+                                }
+                            }
+                            if (best == FR_NONE) break;
+                            replay(best);
+                            last_key = best_key;
+                            first = false;
+                        }
                     }
                     if (own0 != FR_NONE) S.u.fr.fin[own0] |= 0x10u;
                     if (own1 != FR_NONE) S.u.fr.fin[own1] |= 0x20u;
@@ -808,7 +882,6 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
         }
     }
     __syncthreads();
-
     // ---- resolve (ColorBuffer::box_filter_color, buffers.rs:111-125) and write back ----
     const uint32_t res = box_filter(S.color[tid * 4], S.color[tid * 4 + 1], S.color[tid * 4 + 2], S.color[tid * 4 + 3]);
     if (DBG && X < (int)P.W && Y < (int)P.H) {

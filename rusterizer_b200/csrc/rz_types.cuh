@@ -131,7 +131,7 @@ struct FrameParams {
     uint32_t rec_cap, bin_cap, large_cap;
     FrameState *fs;
     uint32_t *tile_count;        // [tiles_x * tiles_y]
-    uint32_t *busy;              // [ORDER_BUCKETS][tiles_x * tiles_y] ids of the non-empty tiles per class
+    unsigned long long *busy;    // [ORDER_BUCKETS][tiles_x * tiles_y] non-empty tiles per class: tile id | list length << 32
     unsigned long long *bins;    // [tiles][bin_cap]  (key << 32 | rec)
     RasterRec *recs;
     ShadeRec *shade;
