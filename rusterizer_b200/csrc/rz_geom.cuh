@@ -124,6 +124,9 @@ __device__ __forceinline__ void emit_setup(const FrameParams &P, const DrawParam
         }
     }
 
+    // non-finite / absurd coordinates take the literal per-pixel walk of the tile stage; frames without any
+    // (all of them, in practice) skip the detection of such items in every chunk
+    if (!setup_is_tame(s)) atomicOr(&P.fs->has_wild, 1u);
     const uint32_t stripe = blockIdx.x % REC_STRIPES, stripe_cap = P.rec_cap / REC_STRIPES;
     const uint32_t local = alloc_slot(&P.fs->rec_cursor[stripe]);
     if (local >= stripe_cap) {

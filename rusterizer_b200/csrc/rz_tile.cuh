@@ -169,7 +169,16 @@ __device__ __forceinline__ uint32_t shade(const FrameParams &P, const Setup &s, 
 // the lower index, so n need not be a power of two (the missing tail behaves like +inf padding).
 template <typename T>
 __device__ __forceinline__ void block_sort(T *a, int n) {
+    // Thread t owns the elements t, t + NT, ...: an aligned block of 32 elements belongs to one warp, so an
+    // exchange distance below 32 keeps both partners inside the warp and __syncwarp orders the stages; only
+    // the wide stages (and the first narrow one after them) need the CTA barrier -- 14 instead of 45 for 512 keys.
+    bool prev_wide = false;
     for (int k = 2; (k >> 1) < n; k <<= 1) {
+        {
+            const bool wide = k > 32;
+            if (wide || prev_wide) __syncthreads(); else __syncwarp();
+            prev_wide = wide;
+        }
         for (int i = threadIdx.x; i < n; i += NT) {
             const int p = i ^ (k - 1);
             if (p > i && p < n) {
@@ -177,8 +186,10 @@ __device__ __forceinline__ void block_sort(T *a, int n) {
                 if (x > y) { a[i] = y; a[p] = x; }
             }
         }
-        __syncthreads();
         for (int j = k >> 2; j > 0; j >>= 1) {
+            const bool wide = j >= 32;
+            if (wide || prev_wide) __syncthreads(); else __syncwarp();
+            prev_wide = wide;
             for (int i = threadIdx.x; i < n; i += NT) {
                 const int p = i ^ j;
                 if (p > i && p < n) {
@@ -186,9 +197,9 @@ __device__ __forceinline__ void block_sort(T *a, int n) {
                     if (x > y) { a[i] = y; a[p] = x; }
                 }
             }
-            __syncthreads();
         }
     }
+    __syncthreads();
 }
 
 // A large item staged in shared memory for the pixel-parallel walk (24 words).
@@ -237,7 +248,7 @@ struct TileSmemT {
         unsigned long long sorted[SORT_CAP];
         BigSetup big[CHUNK];
     } u;
-    uint32_t head[TILE_PX];               // per-pixel fragment list heads; reused as resolve staging
+    uint32_t head[TILE_PX];               // per-pixel fragment list heads
     uint32_t scan[NT / 32];
     uint32_t first_big, first_small, nfrag, ovf, cur_tile;
     uint32_t bucket_end[ORDER_BUCKETS];   // prefix of the list-length class sizes (busy-list work order)
@@ -405,6 +416,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
 
     // ---- phase 1: persistent loop over the tiles that received triangles (dynamic work stealing) ----
     S.lut[tid] = fdiv((float)tid, 255.0f);
+    const bool wild = P.fs->has_wild != 0u; // the frame holds items for the literal per-pixel walk
     // prefix of the class sizes: work item w belongs to the first class with w < end
     // (kept in shared memory: eight registers held over the whole tile loop were spilled instead)
     if (tid == 0) {
@@ -419,10 +431,12 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
     // rasterised tile, cursor kept in shared memory), the rest follows after the loop
     if (lane == 0) S.clr_cursor[warp] = blockIdx.x * (NT / 32) + warp;
     if (tid == 0) S.unit_budget = UNIT_CAP;
+    // Barriers of a tile trip: ONE at the top.  Every phase of a tile ends with a barrier and the write-back after the
+    // last one touches thread-private shared-memory words only, so thread 0 steals the next work item right there
+    // (the atomic's round trip overlaps the write-back) and the barrier at the top of the next trip publishes it.
+    if (tid == 0) S.cur_tile = atomicAdd(&P.fs->tile_cursor, 1u);
     for (;;) {
     __syncthreads(); // previous tile fully retired (also covers S.lut and S.bucket_end on the first trip)
-    if (tid == 0) S.cur_tile = atomicAdd(&P.fs->tile_cursor, 1u);
-    __syncthreads();
     const uint32_t n_busy = S.bucket_end[ORDER_BUCKETS - 1];
     const uint32_t work = S.cur_tile;
     if (work >= n_busy) break;
@@ -465,7 +479,8 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
             sort_tile_list(S, bin, n);
             sorted = true;
         }
-        __syncthreads();
+        // (no barrier needed here: sort_tile_list ends with one, and the clears above are separated from their
+        // first readers by the barriers of phase A0)
 
         for (int pos = 0; pos < n;) {
             // ---- load this window's items (thread = item) ----
@@ -484,18 +499,23 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 if (x0 < x1 && y0 < y1) {
                     bx0 = x0 - tileX0; by0 = y0 - tileY0; bw = x1 - x0; bh = y1 - y0;
                 }
-                big = bw > 0 && !setup_is_tame(s); // NaN / inf / absurd coordinates: literal per-pixel path
-            }
-            if (tid == 0) {
-                S.first_big = CHUNK + 1;
-                S.first_small = CHUNK + 1;
+                big = wild && bw > 0 && !setup_is_tame(s); // NaN / inf / absurd coordinates: literal per-pixel path
             }
             const int nvalid = min(CHUNK, n - pos);
-            __syncthreads();
-            if (valid && big) atomicMin(&S.first_big, (uint32_t)tid);
-            if (valid && !big) atomicMin(&S.first_small, (uint32_t)tid);
-            __syncthreads();
-            const int first_big = (int)S.first_big, first_small = (int)S.first_small;
+            // items for the literal walk split the window into runs; a frame without any has none to look for
+            int first_big = CHUNK + 1, first_small = 0;
+            if (wild) {
+                if (tid == 0) {
+                    S.first_big = CHUNK + 1;
+                    S.first_small = CHUNK + 1;
+                }
+                __syncthreads();
+                if (valid && big) atomicMin(&S.first_big, (uint32_t)tid);
+                if (valid && !big) atomicMin(&S.first_small, (uint32_t)tid);
+                __syncthreads();
+                first_big = (int)S.first_big;
+                first_small = (int)S.first_small;
+            }
 
             if (!sorted && first_big <= CHUNK) { // large items need the ordered walk
                 sort_tile_list(S, bin, n);
@@ -881,7 +901,9 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
             pos += cnt;
         }
     }
-    __syncthreads();
+    else __syncthreads(); // (a busy tile never has an empty list; keeps the hand-over below safe if it ever did)
+    // every path through the chunk loop ends with a barrier: all threads have read S.cur_tile long ago
+    if (tid == 0) S.cur_tile = atomicAdd(&P.fs->tile_cursor, 1u);
     // ---- resolve (ColorBuffer::box_filter_color, buffers.rs:111-125) and write back ----
     const uint32_t res = box_filter(S.color[tid * 4], S.color[tid * 4 + 1], S.color[tid * 4 + 2], S.color[tid * 4 + 3]);
     if (DBG && X < (int)P.W && Y < (int)P.H) {
@@ -894,15 +916,12 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
         }
     }
     if ((P.W & 3u) == 0u) {
-        S.head[tid] = res; // stage, then 64 threads issue 128-bit row stores
-        __syncthreads();
-        if (tid < TH * (TW / 4)) {
-            const int row = tid / (TW / 4), q = tid % (TW / 4);
-            const int Yr = tileY0 + row, Xq = tileX0 + q * 4;
-            if (Yr < (int)P.H && Xq < (int)P.W)
-                *reinterpret_cast<uint4 *>(&P.out[(size_t)Yr * P.W + Xq]) =
-                    *reinterpret_cast<const uint4 *>(&S.head[row * TW + q * 4]);
-        }
+        // 128-bit row stores without staging: lane L (L % 4 == 0) collects the pixels of lanes L..L+3, which are
+        // four consecutive pixels of one tile row (lane = pixel index mod 32, 16 pixels per row)
+        const uint32_t r1 = __shfl_down_sync(0xffffffffu, res, 1), r2 = __shfl_down_sync(0xffffffffu, res, 2),
+                       r3 = __shfl_down_sync(0xffffffffu, res, 3);
+        if ((lane & 3) == 0 && X < (int)P.W && Y < (int)P.H)
+            *reinterpret_cast<uint4 *>(&P.out[(size_t)Y * P.W + X]) = make_uint4(res, r1, r2, r3);
     } else if (X < (int)P.W && Y < (int)P.H) {
         P.out[(size_t)Y * P.W + X] = res;
     }

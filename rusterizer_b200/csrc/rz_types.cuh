@@ -67,7 +67,7 @@ struct FrameState {
     uint32_t n_large;     // large-triangle binning work items
     uint32_t n_clip_attr; // AttrRec slots handed out to clipped triangles
     uint32_t large_next;  // work-stealing cursor of the large binning kernel
-    uint32_t n_busy;      // (unused; kept for layout)
+    uint32_t has_wild;    // a triangle with NaN / inf / absurd screen coordinates was emitted (tile stage: literal walk)
     uint32_t tile_cursor; // work-stealing cursor of the tile kernel
     uint32_t pad1[2];
     uint32_t rec_cursor[REC_STRIPES]; // emitted (post-clip, post-cull) triangles per stripe
