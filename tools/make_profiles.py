@@ -4,26 +4,31 @@ summaries under profiles/ (r01_launches.csv + summary, r01_ncu_full_summary.txt,
 bench lines)."""
 import collections, csv, json, shutil, subprocess, sys
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01f"
-G, P = "gpurun_out/", "profiles/"
-rows = list(csv.reader(open(f"{G}launches_{tag}.csv", errors="ignore")))
-hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
-H = rows[hi]; kn, mv, mu = H.index("Kernel Name"), H.index("Metric Value"), H.index("Metric Unit")
-d = collections.OrderedDict()
-for r in rows[hi + 1:]:
-    if len(r) <= mv: continue
-    v = float(r[mv].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r[mu], 1.0)
-    d.setdefault(r[kn][:70], []).append(v)
-ours = {k: v for k, v in d.items() if "rz::" in k}
-tot = sum(sum(v) / len(v) for v in ours.values())
-out = ["# ncu launch list summary (round 1, final)  --  source: profiles/r01_launches.csv",
-       "# command: ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --inflight 1",
-       "# per-launch times are cold-cache and serialised: compare SHARES, not absolutes", "",
-       f"{'kernel':70s} {'launches':>8s} {'mean_us':>9s} {'min_us':>9s} {'max_us':>9s}"]
-out += [f"{k:70s} {len(v):8d} {sum(v)/len(v):9.2f} {min(v):9.2f} {max(v):9.2f}" for k, v in d.items()]
-out += ["", "share of one frame (our kernels, mean launch time):"]
-out += [f"  {k:62s} {sum(v)/len(v)/tot*100:5.1f}%" for k, v in ours.items()]
-open(P + "r01_launches_summary.txt", "w").write("\n".join(out) + "\n")
-shutil.copy(f"{G}launches_{tag}.csv", P + "r01_launches.csv")
+TRAFFIC_ONLY = "--traffic-only" in sys.argv  # on the GPU box, between the ncu capture and the bench run: bench.py quotes
+G, P = "gpurun_out/", "profiles/"             # profiles/traffic.json, which has to describe the code being measured
+if not TRAFFIC_ONLY:
+    rows = list(csv.reader(open(f"{G}launches_{tag}.csv", errors="ignore")))
+    hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
+    H = rows[hi]; kn, mv, mu = H.index("Kernel Name"), H.index("Metric Value"), H.index("Metric Unit")
+    d = collections.OrderedDict()
+    for r in rows[hi + 1:]:
+        if len(r) <= mv: continue
+        v = float(r[mv].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r[mu], 1.0)
+        d.setdefault(r[kn][:70], []).append(v)
+    ours = collections.OrderedDict()  # template instantiations of one kernel (tile_kernel<DBG, EXT, DIRECT>) count as one
+    for k, v in d.items():
+        if "rz::" in k:
+            ours.setdefault(k.split("<")[0].split("(")[0].replace("void ", ""), []).extend(v)
+    tot = sum(sum(v) / len(v) for v in ours.values())
+    out = ["# ncu launch list summary (round 1, final)  --  source: profiles/r01_launches.csv",
+           "# command: ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --inflight 1",
+           "# per-launch times are cold-cache and serialised: compare SHARES, not absolutes", "",
+           f"{'kernel':70s} {'launches':>8s} {'mean_us':>9s} {'min_us':>9s} {'max_us':>9s}"]
+    out += [f"{k:70s} {len(v):8d} {sum(v)/len(v):9.2f} {min(v):9.2f} {max(v):9.2f}" for k, v in d.items()]
+    out += ["", "share of one frame (our kernels, mean launch time):"]
+    out += [f"  {k:62s} {sum(v)/len(v)/tot*100:5.1f}%" for k, v in ours.items()]
+    open(P + "r01_launches_summary.txt", "w").write("\n".join(out) + "\n")
+    shutil.copy(f"{G}launches_{tag}.csv", P + "r01_launches.csv")
 open(P + "r01_ncu_full_summary.txt", "w").write(subprocess.run([sys.executable, "tools/ncu_raw_summary.py", f"{G}prof_{tag}.ncu-rep"], capture_output=True, text=True).stdout)
 raw = subprocess.run(["ncu", "-i", f"{G}prof_{tag}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(raw.splitlines())); H, U = rr[0], rr[1]
@@ -41,6 +46,8 @@ for r in rr[2:]:
 json.dump({"tile": det["tile"]["traffic_bytes"], "geometry": det["geom"]["traffic_bytes"] + det["vertex"]["traffic_bytes"],
            "_source": "profiles/r01_ncu_full_summary.txt (ncu --set full --clock-control none --import-source on, one launch of each kernel of one C2 frame; tools/profile_round.sh)",
            "_detail": det}, open(P + "traffic.json", "w"), indent=1)
+if TRAFFIC_ONLY:
+    sys.exit(0)
 shutil.copy(f"{G}tile_times_{tag}.txt", P + "r01_tile_times.txt")
 shutil.copy(f"{G}configs_{tag}.jsonl", P + "r01_configs.jsonl")
 open(P + "r01_bench_n1.json", "w").write(open(f"{G}bench_{tag}.json").read().strip().splitlines()[-1] + "\n")
