@@ -333,7 +333,8 @@ int rz_bind_texture(rz_ctx *c, uint32_t index, const uint8_t *texels, uint32_t w
         return fail(c, RZ_E_TEXTURE, "rz_bind_texture: at most %d textures can be bound", RZ_MAX_TEXTURES);
     CU(c, cudaMemcpyAsync(t.d_data, texels, t.len, cudaMemcpyHostToDevice, c->stream));
     TexInfo ti;
-    ti.data = t.d_data; ti.len = t.len; ti.w = t.w; ti.h = t.h; ti.tw = t.tw; ti.bound = 1;
+    ti.data = t.d_data; ti.len = t.len; ti.w = t.w; ti.h = t.h; ti.tw = t.tw;
+    ti.bound = 1u | ((t.tw == 4 && t.len < (1ull << 32)) ? 2u : 0u); // bit 1: RGBA8 with 32-bit byte offsets (rz_tile.cuh)
     if (!c->d_textab) CU(c, cudaMalloc(&c->d_textab, sizeof(TexInfo) * RZ_MAX_TEXTURES));
     CU(c, cudaMemcpyAsync(c->d_textab + c->textures.size(), &ti, sizeof ti, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
@@ -475,7 +476,8 @@ static FrameParams make_params(rz_ctx *c, uint32_t *out_base) {
     if (!c->textures.empty()) {
         const Texture &t = c->textures[0];
         P.tex_table = c->d_textab;
-        P.tex0.data = t.d_data; P.tex0.len = t.len; P.tex0.w = t.w; P.tex0.h = t.h; P.tex0.tw = t.tw; P.tex0.bound = 1;
+        P.tex0.data = t.d_data; P.tex0.len = t.len; P.tex0.w = t.w; P.tex0.h = t.h; P.tex0.tw = t.tw;
+        P.tex0.bound = 1u | ((t.tw == 4 && t.len < (1ull << 32)) ? 2u : 0u);
     }
     return P;
 }

@@ -72,15 +72,30 @@ __device__ __forceinline__ void sample_texture(const TexInfo &t, const float *lu
     const float xf = fsub(x, truncf(x)), yf = fsub(y, truncf(y)); // f32::fract
     const float omx = fsub(1.0f, xf), omy = fsub(1.0f, yf);
     float tl[4], tr[4], bl[4], br[4];
-    const unsigned long long rs = (unsigned long long)t.tw * t.w; // bytes per texel row
-    const unsigned long long r0 = (unsigned long long)y0 * rs, r1 = (unsigned long long)y1 * rs;
-    const unsigned long long c0 = (unsigned long long)x0 * t.tw, c1 = (unsigned long long)x1 * t.tw;
-    if (t.tw == 4 && r1 + c1 + 3 < t.len && r1 + c0 + 3 < t.len && r0 + c1 + 3 < t.len) {
-        // common case: RGBA8, all four texels inside the buffer -> four 32-bit loads
-        const uint32_t v00 = __ldg(reinterpret_cast<const uint32_t *>(t.data + r0 + c0));
-        const uint32_t v10 = __ldg(reinterpret_cast<const uint32_t *>(t.data + r0 + c1));
-        const uint32_t v01 = __ldg(reinterpret_cast<const uint32_t *>(t.data + r1 + c0));
-        const uint32_t v11 = __ldg(reinterpret_cast<const uint32_t *>(t.data + r1 + c1));
+    uint32_t v00 = 0, v10 = 0, v01 = 0, v11 = 0;
+    bool packed = false;
+    if ((t.bound & 2u) && x1 < t.w && y1 < t.h) {
+        // RGBA8 texture below 4 GB with all four texels inside it (floor <= ceil, so x1 and y1 decide; always the
+        // case for u, v in [0, 1]): the byte offsets x * 4 + y * 4 * width of read_texel fit 32 bits, word index
+        const uint32_t *tex = reinterpret_cast<const uint32_t *>(t.data);
+        const uint32_t r0 = y0 * t.w, r1 = y1 * t.w;
+        v00 = __ldg(tex + r0 + x0); v10 = __ldg(tex + r0 + x1);
+        v01 = __ldg(tex + r1 + x0); v11 = __ldg(tex + r1 + x1);
+        packed = true;
+    } else {
+        const unsigned long long rs = (unsigned long long)t.tw * t.w; // bytes per texel row
+        const unsigned long long r0 = (unsigned long long)y0 * rs, r1 = (unsigned long long)y1 * rs;
+        const unsigned long long c0 = (unsigned long long)x0 * t.tw, c1 = (unsigned long long)x1 * t.tw;
+        if (t.tw == 4 && r1 + c1 + 3 < t.len && r1 + c0 + 3 < t.len && r0 + c1 + 3 < t.len) {
+            // RGBA8, all four texels inside the buffer -> four 32-bit loads
+            v00 = __ldg(reinterpret_cast<const uint32_t *>(t.data + r0 + c0));
+            v10 = __ldg(reinterpret_cast<const uint32_t *>(t.data + r0 + c1));
+            v01 = __ldg(reinterpret_cast<const uint32_t *>(t.data + r1 + c0));
+            v11 = __ldg(reinterpret_cast<const uint32_t *>(t.data + r1 + c1));
+            packed = true;
+        }
+    }
+    if (packed) {
 #pragma unroll
         for (int k = 0; k < (ALPHA ? 4 : 3); k++) {
             tl[k] = lut[(v00 >> (8 * k)) & 0xFFu]; tr[k] = lut[(v10 >> (8 * k)) & 0xFFu];
@@ -149,7 +164,12 @@ __device__ __forceinline__ uint32_t shade(const FrameParams &P, const Setup &s, 
     const float w = clamp01(fsub(fsub(1.0f, u), v));
 #define RZ_INTERP(c) fadd(fadd(fmul(__ldg(a0 + (c)), u), fmul(__ldg(a1 + (c)), v)), fmul(__ldg(a2 + (c)), w))
     if (fs == 1u) return to_argb(RZ_INTERP(0), RZ_INTERP(1), RZ_INTERP(2), RZ_INTERP(3));
-    const float tu = RZ_INTERP(4), tv = RZ_INTERP(5);
+    // (u, v) of a vertex sit at byte offset 24 * i + 16 of an array that starts on a 256-byte boundary (cudaMalloc;
+    // AttrRec is 16-byte aligned with the three attributes at 0, 24, 48): one 64-bit load per vertex
+    const float2 t0 = __ldg(reinterpret_cast<const float2 *>(a0 + 4)), t1 = __ldg(reinterpret_cast<const float2 *>(a1 + 4)),
+                 t2 = __ldg(reinterpret_cast<const float2 *>(a2 + 4));
+    const float tu = fadd(fadd(fmul(t0.x, u), fmul(t1.x, v)), fmul(t2.x, w));
+    const float tv = fadd(fadd(fmul(t0.y, u), fmul(t1.y, v)), fmul(t2.y, w));
     float o[4];
     if (!EXT || texidx == 0u) {
         sample_texture<ALPHA>(P.tex0, lut, tu, tv, oob, o);
