@@ -107,12 +107,16 @@ __device__ __forceinline__ void emit_setup(const FrameParams &P, const DrawParam
     uint32_t tmask = 0;
     if (small) {
         const uint32_t tx1 = (b.x1 - 1) / TW, ty1 = (b.y1 - 1) / TH;
-        if (area2 < GEOM_THIN_AREA2 && bw * bh <= GEOM_THIN_PX) {
+        if (area2 < GEOM_THIN_AREA2 && bw * bh <= GEOM_THIN_PX && setup_is_tame(s)) {
             // (2) thin / tiny triangles usually touch no sample at all: rasterise them exactly right
-            // here so they never reach a tile list (pole slivers of a UV-sphere, distant meshes)
+            // here so they never reach a tile list (pole slivers of a UV-sphere, distant meshes).  Finite
+            // coordinates only (anything else is simply binned): the single-compare form of EdgeFunctions::inside
+            // that the tile stage uses (coverage_mask_fast) is exact under that precondition.
+            float thr[3];
+            edge_thresholds(s, thr);
             for (uint32_t Y = b.y0; Y < b.y1; Y++)
                 for (uint32_t X = b.x0; X < b.x1 && owns_tile_row(P, Y / TH); X++)
-                    if (coverage_mask(s, (int)X, (int)Y)) tmask |= 1u << (((Y / TH - ty0) << 1) | (X / TW - tx0));
+                    if (coverage_mask_fast(s, thr, (int)X, (int)Y)) tmask |= 1u << (((Y / TH - ty0) << 1) | (X / TW - tx0));
             if (!tmask) return; // contributes nothing (its bbox pixels are already counted)
         } else {
             tmask = 1u | (tx1 > tx0 ? 2u : 0u) | (ty1 > ty0 ? 4u : 0u) | ((tx1 > tx0 && ty1 > ty0) ? 8u : 0u);
