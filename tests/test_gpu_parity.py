@@ -168,6 +168,33 @@ def test_exotic_float_inputs():
         assert not msgs, "; ".join(msgs)
 
 
+def test_wild_flag_is_per_frame():
+    """One context, alternating frames with and without non-finite triangles.  The geometry stage raises
+    FrameState::has_wild when it emits a triangle for the literal per-pixel walk and the tile stage only looks for
+    such items when the flag is set: it must neither leak into the next (tame) frame nor be missed in a frame that
+    follows a tame one.  Also mixes list lengths: the tame frame has pixel lists for the register replay of phase B."""
+    from rusterizer_b200.render import Renderer
+
+    rng = np.random.RandomState(11)
+    nt = 300
+    verts = rng.uniform(-2, 2, (nt, 3, 3)).astype(np.float32)
+    verts[..., 2] = rng.uniform(-2, 4, (nt, 3)).astype(np.float32)
+    special = np.array([np.inf, -np.inf, np.nan, 1e30, -1e30, 3e38], np.float32)
+    for t in range(0, nt, 4):
+        verts[t, rng.randint(3), rng.randint(3)] = special[rng.randint(len(special))]
+    wild_mesh = Mesh(verts.reshape(-1, 3), np.arange(nt * 3, dtype=np.uint32), rng.uniform(0, 1, (nt * 3, 6)).astype(np.float32))
+    wild = scenes.sphere_scene(width=320, height=200, mesh=wild_mesh, fs=1)
+    tame = scenes.sphere_scene(65, 33, width=320, height=200, fs=0)
+    r = Renderer(320, 200)
+    r.uniforms().bind_texture(0, tame.texture)
+    ow, ot = oracle_render(wild), oracle_render(tame)
+    for sc, o in ((tame, ot), (wild, ow), (tame, ot), (wild, ow), (wild, ow), (tame, ot)):
+        g = gpu_render(sc, debug=True, renderer=r)
+        msgs = compare(o, g)
+        assert not msgs, sc.name + ": " + "; ".join(msgs)
+    r.close()
+
+
 def test_empty_and_degenerate_inputs():
     """Empty mesh, zero-area triangles, a frame with no draws."""
     from rusterizer_b200.render import Renderer
