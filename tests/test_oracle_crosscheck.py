@@ -1,0 +1,166 @@
+"""Cross-check of the C oracle (oracle/rz_oracle.c) against a second restatement of the reference written
+independently as a numpy array program (oracle/py_restatement.py): every depth sample, every packed colour sample
+and every resolved pixel of whole frames must agree bit for bit.  The reference (Rust) cannot be built in this
+image, so this is what stands behind the oracle's whole-frame behaviour besides the reference's own unit-test
+vectors (tests/test_oracle_kats.py).  CPU only."""
+import numpy as np
+import pytest
+
+from helpers import oracle_render
+from oracle.py_restatement import PyRasterizer
+from rusterizer_b200 import mathx, scenes
+from rusterizer_b200.mesh import Mesh
+from rusterizer_b200.scenes import Draw, Scene
+from rusterizer_b200.texture import Texture
+
+
+def py_render(scene):
+    r = PyRasterizer(scene.width, scene.height)
+    if scene.texture is not None:
+        r.bind_texture(0, scene.texture.texels)
+    r.view, r.projection = scene.view, scene.projection
+    for d in scene.draws:
+        r.world = d.world
+        r.render(d.mesh.vertices, d.mesh.attributes, d.mesh.indices, d.fs)
+    depth, color = r.depth.copy(), r.color.copy()
+    return dict(depth=depth, color=color, fb=r.framebuffer())
+
+
+def crosscheck(scene):
+    o, p = oracle_render(scene), py_render(scene)
+    od, pd = o["depth"].view(np.uint32), p["depth"].view(np.uint32)
+    assert np.array_equal(od, pd), f"{scene.name}: depth bits differ at {np.argwhere(od != pd)[:5].tolist()}"
+    assert np.array_equal(o["color"], p["color"]), f"{scene.name}: colour samples differ at {np.argwhere(o['color'] != p['color'])[:5].tolist()}"
+    assert np.array_equal(o["fb"], p["fb"]), f"{scene.name}: resolved image differs"
+    assert (o["fb"] != 0xFF191919).sum() > 50, f"{scene.name}: nothing was drawn"
+    return o
+
+
+@pytest.mark.parametrize("fs", [0, 1, 2])
+def test_default_scene_all_shaders(fs):
+    """The crate's Mode::Demo frame (cube + sphere, two draws, main.rs:94-104) with FS Texture / Color / Debug."""
+    crosscheck(scenes.default_scene(1.0, fs=fs, width=192, height=108))
+
+
+@pytest.mark.parametrize("elapsed", [0.0, 0.7, 2.5])
+def test_clip_scene(elapsed):
+    """The crate's --clip-test triangle (main.rs:106-125): Sutherland-Hodgman, fan, attribute interpolation."""
+    crosscheck(scenes.clip_test_scene(elapsed, width=160, height=90))
+
+
+def test_small_triangles_sphere():
+    crosscheck(scenes.sphere_scene(49, 25, width=200, height=120))
+
+
+@pytest.mark.parametrize("b2f", [True, False])
+def test_overdraw_order(b2f):
+    """Stacked jittered grids drawn back-to-front / front-to-back: submission order and the strict < depth test."""
+    crosscheck(scenes.overdraw_scene(nx=12, ny=7, width=160, height=96, back_to_front=b2f))
+
+
+def test_near_plane_field():
+    """Every triangle straddles the near plane (BASELINE configs[2] scaled down)."""
+    o = crosscheck(scenes.near_clip_scene(nx=10, ny=6, width=192, height=108))
+    assert o["counters"]["n_clipped_in"] > 50
+
+
+def test_random_soup_and_coincident():
+    """Random triangles of all sizes and windings, partly off screen, plus exact duplicates (the second copy must
+    lose the strict < test) and an RGB (3-byte) non-square texture."""
+    rng = np.random.RandomState(5)
+    nt = 160
+    ctr = rng.uniform(-3, 3, (nt, 1, 3)).astype(np.float32)
+    ctr[..., 2] = rng.uniform(-3.5, 6, (nt, 1)).astype(np.float32)
+    size = (10 ** rng.uniform(-1.5, 0.4, (nt, 1, 1))).astype(np.float32)
+    verts = (ctr + rng.uniform(-1, 1, (nt, 3, 3)).astype(np.float32) * size).reshape(nt, 3, 3)
+    verts = np.concatenate([verts, verts[:40]], 0)  # coincident copies, submitted later
+    nt = verts.shape[0]
+    attrs = rng.uniform(0, 1, (nt * 3, 6)).astype(np.float32)
+    mesh = Mesh(verts.reshape(-1, 3), np.arange(nt * 3, dtype=np.uint32), attrs)
+    for fs in (1, 0):
+        s = scenes.sphere_scene(width=176, height=100, mesh=mesh, fs=fs)
+        if fs == 0:
+            tex = np.random.RandomState(9).randint(0, 256, (23, 37, 3)).astype(np.uint8)
+            s = Scene(s.name + "_rgb", s.width, s.height, s.view, s.projection, s.draws, Texture(tex))
+        crosscheck(s)
+
+
+def test_wide_range_colours_expose_low_bits():
+    """FS Color with attribute values up to 6e4: Color::to_argb neither clamps nor masks (color.rs:15-20), so the
+    integer part of c * 255 (up to 2^24, one ulp = 1) lands in the packed sample and a last-bit difference in the
+    perspective-correct interpolation (five divisions, mod.rs:85-99) changes the colour sample."""
+    rng = np.random.RandomState(21)
+    nt = 120
+    ctr = rng.uniform(-2.5, 2.5, (nt, 1, 3)).astype(np.float32)
+    ctr[..., 2] = rng.uniform(-3.0, 5, (nt, 1)).astype(np.float32)
+    verts = (ctr + rng.uniform(-1, 1, (nt, 3, 3)).astype(np.float32) * np.float32(0.8)).reshape(-1, 3)
+    attrs = rng.uniform(0, 60000, (nt * 3, 6)).astype(np.float32)
+    mesh = Mesh(verts, np.arange(nt * 3, dtype=np.uint32), attrs)
+    crosscheck(scenes.sphere_scene(width=160, height=96, mesh=mesh, fs=1))
+
+
+def sample_grid_scene(seed, n_tris=400, size=64):
+    """Triangles whose vertices sit on the 1/8-pixel lattice of a size x size target (identity matrices, w = 1), so
+    that many edges pass EXACTLY through RGSS sample positions and shared edges abound: exercises the tie-break of
+    EdgeFunctions::inside (mod.rs:148-170) and equal depths under the strict < test."""
+    rng = np.random.RandomState(seed)
+    base = rng.randint(0, size * 8 - 40, (n_tris, 1, 2))
+    sxy = (base + rng.randint(0, 41, (n_tris, 3, 2))).astype(np.float32) / np.float32(8.0)  # screen coordinates
+    pos = np.empty((n_tris, 3, 3), np.float32)
+    pos[..., 0] = sxy[..., 0] * np.float32(2.0 / size) - np.float32(1.0)
+    pos[..., 1] = np.float32(1.0) - sxy[..., 1] * np.float32(2.0 / size)
+    pos[..., 2] = (rng.randint(-4, 5, (n_tris, 1)) / np.float32(8.0)).astype(np.float32)  # few distinct depths: ties
+    # every triangle twice, the copy with reversed winding, so both orientations of every edge occur
+    pos = np.concatenate([pos, pos[:, ::-1]], 0)
+    attrs = rng.uniform(0, 1, (pos.shape[0] * 3, 6)).astype(np.float32)
+    mesh = Mesh(pos.reshape(-1, 3), np.arange(pos.shape[0] * 3, dtype=np.uint32), attrs)
+    eye = mathx.identity()
+    return Scene(f"sample_grid_{seed}", size, size, eye, eye, [Draw(mesh, eye, 1)], Texture.checkerboard())
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_edges_through_sample_points(seed):
+    sc = sample_grid_scene(seed)
+    # the lattice construction must survive the viewport transform exactly, or the test is not testing ties
+    v = sc.draws[0].mesh.vertices
+    sx = np.float32(sc.width) * (v[:, 0] + np.float32(1.0)) / np.float32(2.0)
+    assert np.array_equal(sx * 8, np.round(sx * 8))
+    crosscheck(sc)
+
+
+@pytest.mark.parametrize("shape", [(17, 29, 4), (31, 8, 3), (2, 2, 4)])
+def test_texture_sample_function(shape):
+    """Texture::sample (texture.rs:65-83) as exact f32: 8-bit frame colours hide last-bit differences of the
+    bilinear blend, so the two restatements are also compared on the four output floats, bit for bit, for random
+    (u, v) and for the lattice points where floor == ceil."""
+    from oracle.oracle import get_lib
+    from oracle.py_restatement import Texture as PyTexture
+
+    L = get_lib()
+    rng = np.random.RandomState(shape[0])
+    tex = rng.randint(0, 256, shape).astype(np.uint8)
+    h, w, _ = shape
+    u = rng.uniform(0, 1, 3000).astype(np.float32)
+    v = rng.uniform(0, 1, 3000).astype(np.float32)
+    lat_u = (np.arange(w, dtype=np.float32) / np.float32(w - 1)).astype(np.float32)
+    lat_v = (np.arange(h, dtype=np.float32) / np.float32(h - 1)).astype(np.float32)
+    u = np.concatenate([u, np.repeat(lat_u, h), np.float32([0, 1, 0, 1])])
+    v = np.concatenate([v, np.tile(lat_v, w), np.float32([0, 0, 1, 1])])
+    got = np.stack(PyTexture(tex).sample(u, v), -1).astype(np.float32)
+    want = np.stack([L.tex_sample(tex, float(a), float(b))[0] for a, b in zip(u, v)])
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_two_frames_clear_between():
+    """resolve_and_clear leaves clear depth and colour behind: the second frame of a context equals a fresh one."""
+    sc = scenes.sphere_scene(33, 17, width=128, height=80, fs=1)
+    r = PyRasterizer(sc.width, sc.height)
+    r.view, r.projection = sc.view, sc.projection
+    out = []
+    for _ in range(2):
+        for d in sc.draws:
+            r.world = d.world
+            r.render(d.mesh.vertices, d.mesh.attributes, d.mesh.indices, d.fs)
+        out.append(r.framebuffer())
+    assert np.array_equal(out[0], out[1])
+    assert np.array_equal(out[0], oracle_render(sc)["fb"])
