@@ -18,11 +18,14 @@
 //   phase A0 thread = item          record load, setup, bbox, scan of the bbox areas
 //   phase A1 thread = (item, pixel) exact coverage -> fragment records on per-pixel lists
 //   phase A2 thread = fragment      sample depths
-//   phase B  thread = pixel         m(F), v(F): the pixel's few fragments replayed in key order
+//   phase B  thread = pixel         m(F), v(F): the pixel's few fragments replayed in key order (lists of up to
+//                                   four fragments are ordered and replayed in registers)
 //   phase C  thread = fragment      interpolate + fragment shader + pack; write the visible samples
 // Tiles that need several chunks sort their list by order key first.  Items with non-finite or absurd
 // coordinates take a literal pixel-parallel walk (a thread owns a pixel for the whole run, so it
-// applies the triangles in order by construction) that evaluates EdgeFunctions::inside verbatim.
+// applies the triangles in order by construction) that evaluates EdgeFunctions::inside verbatim; the geometry
+// stage flags frames that contain such items (FrameState::has_wild), all others skip the search for them.
+// A single-chunk tile passes seven CTA barriers: one at the top of the trip, two in A0, one after A1, A2, B, C.
 #pragma once
 #include "rz_exact.cuh"
 #include "rz_geom.cuh"
