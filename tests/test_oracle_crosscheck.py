@@ -99,6 +99,26 @@ def test_wide_range_colours_expose_low_bits():
     crosscheck(scenes.sphere_scene(width=160, height=96, mesh=mesh, fs=1))
 
 
+@pytest.mark.parametrize("seed", [3, 4])
+def test_non_finite_inputs(seed):
+    """inf / NaN / 1e30 coordinates and NaN colours: NaN-ignoring min/max of the bounding box (bounding_box.rs:16-25),
+    saturating `as usize` / `as u32` casts, NaN-propagating clamp, the tie-break on NaN edge values (mod.rs:148-170)
+    and comparisons that are false for NaN in try_clip (clipping.rs:86-104) must come out the same in both."""
+    rng = np.random.RandomState(seed)
+    nt = 120
+    verts = rng.uniform(-2, 2, (nt, 3, 3)).astype(np.float32)
+    verts[..., 2] = rng.uniform(-2, 4, (nt, 3)).astype(np.float32)
+    special = np.array([np.inf, -np.inf, np.nan, 1e30, -1e30, 1e19, 3e38], np.float32)
+    for t in range(0, nt, 3):
+        for _ in range(rng.randint(1, 3)):
+            verts[t, rng.randint(3), rng.randint(3)] = special[rng.randint(len(special))]
+    attrs = rng.uniform(0, 1, (nt * 3, 6)).astype(np.float32)
+    attrs[rng.randint(0, nt * 3, 15), rng.randint(0, 4, 15)] = np.nan
+    mesh = Mesh(verts.reshape(-1, 3), np.arange(nt * 3, dtype=np.uint32), attrs)
+    with np.errstate(all="ignore"):
+        crosscheck(scenes.sphere_scene(width=96, height=60, mesh=mesh, fs=1))
+
+
 def sample_grid_scene(seed, n_tris=400, size=64):
     """Triangles whose vertices sit on the 1/8-pixel lattice of a size x size target (identity matrices, w = 1), so
     that many edges pass EXACTLY through RGSS sample positions and shared edges abound: exercises the tie-break of
