@@ -6,8 +6,11 @@ Every operation is one IEEE binary32 rounding in the reference's source order:
   * dot: sum starts at 0.0, sequential            (math/vector.rs:17-23)
   * Mat x Mat: R[i][j] = dot(row_i(A), col_j(B))  (math/matrix.rs:56-79)
   * Mat x Vec: r[i] = dot(row_i(M), v)            (math/vector.rs:219-240)
-Transcendentals (sin/cos/tan/sqrt) are evaluated in double and rounded once to f32, which
-is the correctly-rounded f32 result the reference's libm calls produce for these inputs.
+Transcendentals (sin/cos/tan/sqrt) are evaluated in double and rounded once to f32, i.e. correctly
+rounded.  Rust's f32::sin/cos/tan call the platform libm (sinf/cosf/tanf), which glibc does NOT round
+correctly for every argument (sinf(0.29452431) is one ulp off): the matrices and meshes the crate itself
+builds come out bit-identical (tests/test_host.py compares them with the C++ mirror, which calls libm),
+other sphere sizes can differ in the last bits of a few percent of the values.  Inputs only.
 """
 from __future__ import annotations
 

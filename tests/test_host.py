@@ -122,6 +122,54 @@ def test_cpp_host_mirror_builds_and_fails_loudly_without_gpu():
     assert p.returncode == 1 and "no CUDA device" in p.stderr
 
 
+def test_cpp_and_python_host_mirrors_build_the_same_data(tmp_path):
+    """Both host mirrors restate math/mod.rs:92-122, math/transform.rs, camera.rs:10-43 and mesh.rs:15-207; what they
+    build crosses the C ABI as plain arrays, so it has to be the same data.  host/host_dump.cpp prints the C++ side.
+    Bit-exact for everything the crate itself builds (projection, rotations, the default and orbit cameras, quad,
+    triangle, cube, the 17 x 9 sphere).  For other sphere sizes the two differ in the last bits of a few values: the
+    C++ mirror calls libm's sinf/cosf like Rust's f32::sin/cos does, the Python mirror rounds the double result, and
+    glibc's sinf is not correctly rounded for every argument (sinf(0.29452431) is one ulp off, a theta and phi of
+    the 65 x 33 sphere).  Inputs only: the GPU path and the oracle always get the same arrays."""
+    from rusterizer_b200 import mathx, mesh as M
+    from rusterizer_b200.camera import Camera
+
+    exe = tmp_path / "host_dump"
+    host = ROOT / "rusterizer_b200" / "host"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-I" + str(ROOT / "include"), str(host / "host_dump.cpp"),
+                    "-o", str(exe), "-L" + str(ROOT / "rusterizer_b200"), "-lrz_b200", "-Wl,-rpath," + str(ROOT / "rusterizer_b200"),
+                    "-Wl,-rpath,/usr/local/cuda/lib64"], check=True)
+    rec = {}
+    for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().split("\n"):
+        name, kind, *vals = line.split()
+        rec[name] = (np.array([int(v, 16) for v in vals], np.uint32).view(np.float32) if kind == "f"
+                     else np.array([int(v) for v in vals], np.uint32))
+    F = np.float32
+    pi = F(3.14159274101257324)
+    py = {
+        "project": mathx.project(1.0, 200.0, F(720.0) / F(1280.0), pi / F(2.0)),
+        "project_1080": mathx.project(1.0, 200.0, F(1080.0) / F(1920.0), pi / F(2.0)),
+        "rotate_110": mathx.rotate(1.0, 1.0, 0.0), "rotate_0303": mathx.rotate(0.3, 0.3, 0.0), "rotate_xyz": mathx.rotate(2.5, -0.7, 4.1),
+        "demo_sphere_world": mathx.matmul(mathx.rotate(1.0, 0.0, pi / F(4.0)), mathx.translate(0.0, 3.0, 0.0)),
+        "view_default": Camera().get_view_matrix(),
+    }
+    for k in (1, 77, 256, 511, 1000):
+        py[f"view_orbit_{k}"] = Camera.orbit(F(2.0) * pi * F(k) / F(1024.0)).get_view_matrix()
+    for name, m in (("centered_quad", M.centered_quad(9.0)), ("triangle", M.triangle()), ("cube", M.cube(1.0)),
+                    ("sphere_default", M.sphere(0.5)), ("sphere_65_33", M.sphere(2.0, 65, 33))):
+        py[name + ".vertices"], py[name + ".attributes"], py[name + ".indices"] = m.vertices, m.attributes, m.indices
+    assert set(py) == set(rec)
+    for k, v in py.items():
+        a, b = np.asarray(v).reshape(-1), rec[k]
+        assert a.shape == b.shape, k
+        if a.dtype != np.float32:
+            assert np.array_equal(a.astype(np.uint32), b), k
+        elif k.startswith("sphere_65_33"):
+            ulp = np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64))
+            assert ulp.max() <= 2 and (ulp > 0).mean() < 0.05, k  # libm sinf vs correctly rounded sin, see above
+        else:
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), k
+
+
 def test_product_package_never_imports_the_oracle():
     """oracle/ is test infrastructure: nothing under rusterizer_b200/ may import, load or call it."""
     for path in (ROOT / "rusterizer_b200").rglob("*"):
