@@ -69,6 +69,8 @@ class OracleLib:
         u64p = C.POINTER(C.c_uint64)
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.c_uint32, C.c_uint32]
+        L.orc_create_rows.restype = C.c_void_p
+        L.orc_create_rows.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_bind_texture.argtypes = [C.c_void_p, C.c_uint32, u8p, C.c_uint32, C.c_uint32, C.c_uint32]
         L.orc_write_block.argtypes = [C.c_void_p, fp, fp, fp]
@@ -211,10 +213,13 @@ def get_lib(fast: bool = False) -> OracleLib:
 class OracleRenderer:
     """The reference's Renderer/Rasterizer surface (render.rs:47-127) on the CPU oracle."""
 
-    def __init__(self, width: int, height: int, lib: OracleLib | None = None):
+    def __init__(self, width: int, height: int, lib: OracleLib | None = None, rows: tuple | None = None):
+        """rows=(r0, r1): hold (and return) only the pixel rows [r0, r1) of the frame -- a large frame is checked band
+        by band, one process per band (see oracle.banded_render)."""
         self.L = lib or get_lib()
         self.width, self.height = width, height
-        self.ctx = self.L.lib.orc_create(width, height)
+        self.row0, self.row1 = (0, height) if rows is None else (int(rows[0]), min(int(rows[1]), height))
+        self.ctx = self.L.lib.orc_create_rows(width, height, self.row0, self.row1)
         if not self.ctx:
             raise MemoryError("orc_create failed")
 
@@ -265,8 +270,9 @@ class OracleRenderer:
         return out
 
     def _view(self, ptr, dtype, per_px):
-        n = self.width * self.height * per_px
-        return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype).reshape(self.height, self.width, per_px).copy()
+        rows = self.row1 - self.row0
+        n = self.width * rows * per_px
+        return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype).reshape(rows, self.width, per_px).copy()
 
     def depth_samples(self):
         return self._view(self.L.lib.orc_depth_samples(self.ctx), np.float32, 4)
@@ -279,7 +285,8 @@ class OracleRenderer:
 
     def framebuffer(self):
         p = self.L.lib.orc_framebuffer(self.ctx)
-        return np.ctypeslib.as_array(p, shape=(self.height * self.width,)).reshape(self.height, self.width).copy()
+        rows = self.row1 - self.row0
+        return np.ctypeslib.as_array(p, shape=(rows * self.width,)).reshape(rows, self.width).copy()
 
     def counters(self):
         c = Counters()
@@ -291,3 +298,76 @@ class OracleRenderer:
 
     def tiles_marked(self, prev=False):
         return int(self.L.lib.orc_tiles_marked(self.ctx, 1 if prev else 0))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Banded oracle: a frame too large for one core / one address space (3840x2160 with 1.6e9 bbox pixels, 8192x8192 with
+# 3.2 GB of sample state) is rendered as horizontal bands by a pool of processes.  Pixels are independent given the
+# ordered triangle stream (rasterizer/mod.rs:443-473), so the bands together are exactly the frame the reference
+# would produce; per-pixel counters add up, per-triangle counters are the same in every band.
+PER_PIXEL_COUNTERS = ("n_bbox_px", "n_covered_px", "n_shaded_px", "n_samples_written", "n_tex_oob")
+
+
+def _band_worker(job):
+    (make_scene, make_args, r0, r1, fast, gpu_paths) = job
+    scene = make_scene(*make_args)
+    r = OracleRenderer(scene.width, scene.height, get_lib(fast=fast), rows=(r0, r1))
+    if scene.texture is not None:
+        r.bind_texture(0, scene.texture.texels)
+        for k, t in enumerate(getattr(scene, "extra_textures", [])):
+            r.bind_texture(k + 1, t.texels)
+    r.write_block(view=scene.view, projection=scene.projection)
+    if getattr(scene, "scissor", None):
+        r.set_scissor(*scene.scissor)
+    for d in scene.draws:
+        r.write_block(world=d.world)
+        r.render(d.mesh.vertices, d.mesh.attributes, d.mesh.indices, 0, d.fs)
+    out = {"rows": (r0, r1), "counters": r.counters(), "mismatch": {}}
+    if gpu_paths:  # compare this band with the GPU's arrays (memory-mapped .npy files) right here: only counts travel back
+        H, W = scene.height, scene.width
+        for name, arr in (("owner", r.owner_samples()), ("depth", r.depth_samples().view(np.uint32)), ("color", r.color_samples())):
+            if name in gpu_paths:
+                g = np.load(gpu_paths[name], mmap_mode="r")[r0:r1]
+                g = g.view(np.uint32) if g.dtype != np.uint32 else g
+                bad = arr != g
+                n = int(bad.sum())
+                out["mismatch"][name] = (n, (np.argwhere(bad)[:3] + [r0, 0, 0]).tolist() if n else [])
+    fb = r.framebuffer()
+    if gpu_paths and "fb" in gpu_paths:
+        g = np.load(gpu_paths["fb"], mmap_mode="r")[r0:r1]
+        bad = fb != g
+        n = int(bad.sum())
+        out["mismatch"]["fb"] = (n, (np.argwhere(bad)[:3] + [r0, 0]).tolist() if n else [])
+    else:
+        out["fb"] = fb
+    r.close()
+    return out
+
+
+def banded_render(make_scene, make_args=(), height=None, n_bands=None, workers=None, fast=True, gpu_paths=None):
+    """Render make_scene(*make_args) with the oracle as `n_bands` row bands in a process pool.  make_scene must be a
+    picklable module-level callable (every worker rebuilds the scene: the builders are deterministic).  Returns
+    dict(fb=[H][W] or None, counters=..., mismatch={array: (count, first positions)}); with gpu_paths = {"fb" | "owner" |
+    "depth" | "color": path of a .npy file holding the GPU's array} every band is compared inside its worker."""
+    import multiprocessing as mp
+
+    workers = workers or max(1, (os.cpu_count() or 2))
+    n_bands = n_bands or workers * 4  # more bands than workers: the bands of a scene are not equally expensive
+    H = height
+    edges = [H * k // n_bands for k in range(n_bands + 1)]
+    jobs = [(make_scene, tuple(make_args), edges[k], edges[k + 1], fast, gpu_paths) for k in range(n_bands) if edges[k + 1] > edges[k]]
+    get_lib(fast=fast)  # compile once, before the pool forks
+    with mp.get_context("fork").Pool(workers) as pool:
+        parts = pool.map(_band_worker, jobs, chunksize=1)
+    counters = dict(parts[0]["counters"])
+    for k in PER_PIXEL_COUNTERS:
+        counters[k] = sum(p["counters"][k] for p in parts)
+    mismatch = {}
+    for p in parts:
+        for name, (n, first) in p["mismatch"].items():
+            tot, firsts = mismatch.get(name, (0, []))
+            mismatch[name] = (tot + n, (firsts + first)[:5])
+    fb = None
+    if parts and "fb" in parts[0]:
+        fb = np.concatenate([p["fb"] for p in sorted(parts, key=lambda p: p["rows"][0])], axis=0)
+    return {"fb": fb, "counters": counters, "mismatch": mismatch}

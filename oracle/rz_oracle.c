@@ -64,6 +64,8 @@ typedef struct {
 
 typedef struct orc_ctx {
     uint32_t width, height;
+    uint32_t row0, row1; /* oracle-only row window [row0,row1): the sample buffers hold just these rows, so a large frame can
+                            be checked band by band (one process per band); default = the whole frame */
     uint32_t sc_x0, sc_y0, sc_x1, sc_y1; /* scissor rect (extension suggested at mod.rs:349-350); default = viewport */
     uint32_t *color;   /* [w*h][4]  buffers.rs:83-105 */
     float *depth;      /* [w*h][4]  buffers.rs:129-147 */
@@ -464,11 +466,24 @@ static void tex_sample(orc_ctx *c, const tex_t *t, float u, float v, float *out)
 
 /* ---------------- context ---------------- */
 
-orc_ctx *orc_create(uint32_t width, uint32_t height) {
+orc_ctx *orc_create_rows(uint32_t width, uint32_t height, uint32_t row0, uint32_t row1);
+orc_ctx *orc_create(uint32_t width, uint32_t height) { return orc_create_rows(width, height, 0, height); }
+
+/* Oracle-only: a context whose per-sample buffers (and returned framebuffer) hold only the pixel rows [row0,row1) of a
+ * width x height frame.  Triangles are transformed with the full viewport and their pixel boxes are additionally bounded
+ * by the window, exactly like the scissor extension bounds them; pixels are independent of each other (mod.rs:443-473),
+ * so the union of the bands of a frame IS the frame.  Per-pixel counters add up over the bands, per-triangle counters
+ * are identical in every band. */
+orc_ctx *orc_create_rows(uint32_t width, uint32_t height, uint32_t row0, uint32_t row1) {
     orc_ctx *c = (orc_ctx *)calloc(1, sizeof *c);
-    size_t n = (size_t)width * height;
+    if (row1 > height) row1 = height;
+    if (row0 > row1) row0 = row1;
+    size_t n = (size_t)width * (row1 - row0);
+    if (n == 0) n = 1;
     c->width = width;
     c->height = height;
+    c->row0 = row0;
+    c->row1 = row1;
     c->sc_x0 = 0; c->sc_y0 = 0; c->sc_x1 = width; c->sc_y1 = height;
     c->color = (uint32_t *)malloc(n * 4 * sizeof(uint32_t));
     c->depth = (float *)malloc(n * 4 * sizeof(float));
@@ -597,6 +612,8 @@ static int rasterize_one(orc_ctx *c, const tri_t *raw, uint32_t fs_id, uint32_t 
          * the viewport bounds 0..width / 0..height become the scissor rect (default: the viewport itself) */
         uint64_t min_x = bb[0] > c->sc_x0 ? bb[0] : c->sc_x0, max_x = bb[1] < c->sc_x1 ? bb[1] : c->sc_x1;
         uint64_t min_y = bb[2] > c->sc_y0 ? bb[2] : c->sc_y0, max_y = bb[3] < c->sc_y1 ? bb[3] : c->sc_y1;
+        if (min_y < c->row0) min_y = c->row0; /* oracle-only row window (orc_create_rows) */
+        if (max_y > c->row1) max_y = c->row1;
         for (uint64_t i = min_y; i < max_y; i++) {
             for (uint64_t j = min_x; j < max_x; j++) {
                 c->cnt.n_bbox_px++;
@@ -605,7 +622,7 @@ static int rasterize_one(orc_ctx *c, const tri_t *raw, uint32_t fs_id, uint32_t 
                 c->cnt.n_covered_px++;
                 float sd[N_MSAA];
                 fragment_depths(&r, sd);
-                size_t idx = (size_t)i * W + j;
+                size_t idx = (size_t)(i - c->row0) * W + j;
                 /* depth_coverage mod.rs:363-378 */
                 uint8_t dcov = 0;
                 for (int s = 0; s < N_MSAA; s++)
@@ -706,17 +723,23 @@ const uint32_t *orc_framebuffer(orc_ctx *c) {
         uint32_t tx = (uint32_t)(t % c->n_horizontal), ty = (uint32_t)(t / c->n_horizontal);
         uint32_t x1 = (tx + 1) * TILE_SIZE < W ? (tx + 1) * TILE_SIZE : W;
         uint32_t y1 = (ty + 1) * TILE_SIZE < H ? (ty + 1) * TILE_SIZE : H;
-        for (uint32_t y = ty * TILE_SIZE; y < y1; y++)
-            for (uint32_t x = tx * TILE_SIZE; x < x1; x++) c->resolve[(size_t)y * W + x] = CLEAR_COLOR;
+        uint32_t y0 = ty * TILE_SIZE;
+        if (y0 < c->row0) y0 = c->row0;
+        if (y1 > c->row1) y1 = c->row1;
+        for (uint32_t y = y0; y < y1; y++)
+            for (uint32_t x = tx * TILE_SIZE; x < x1; x++) c->resolve[(size_t)(y - c->row0) * W + x] = CLEAR_COLOR;
     }
     for (size_t t = 0; t < nt; t++) {
         if (!cur[t]) continue;
         uint32_t tx = (uint32_t)(t % c->n_horizontal), ty = (uint32_t)(t / c->n_horizontal);
         uint32_t x1 = (tx + 1) * TILE_SIZE < W ? (tx + 1) * TILE_SIZE : W;
         uint32_t y1 = (ty + 1) * TILE_SIZE < H ? (ty + 1) * TILE_SIZE : H;
-        for (uint32_t y = ty * TILE_SIZE; y < y1; y++)
+        uint32_t y0 = ty * TILE_SIZE;
+        if (y0 < c->row0) y0 = c->row0;
+        if (y1 > c->row1) y1 = c->row1;
+        for (uint32_t y = y0; y < y1; y++)
             for (uint32_t x = tx * TILE_SIZE; x < x1; x++) {
-                size_t idx = (size_t)y * W + x;
+                size_t idx = (size_t)(y - c->row0) * W + x;
                 c->resolve[idx] = orc_box_filter_color(&c->color[idx * 4]);
                 for (int s = 0; s < N_MSAA; s++) {
                     c->color[idx * 4 + s] = CLEAR_COLOR;

@@ -48,6 +48,100 @@ def test_c2_full_size_parity():
     check_properties(s, g)
 
 
+def _banded_parity(make_scene, make_args, scene, samples=True):
+    """GPU frame (through the C ABI, per-sample capture on) against the oracle run as row bands over every host core
+    (oracle.banded_render): resolved image, all counters and -- band by band inside the workers -- the owner key, the
+    depth bits and the packed colour of every sample.  Tolerance 0."""
+    import os
+    import shutil
+    import tempfile
+
+    from oracle import oracle as orc
+
+    g = gpu_render(scene, debug=samples, device_resident=True)
+    tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None, prefix="rz_parity_")
+    try:
+        paths = {}
+        for name in (("fb", "owner", "depth", "color") if samples else ("fb",)):
+            paths[name] = os.path.join(tmp, name + ".npy")
+            np.save(paths[name], g.pop(name))
+        o = orc.banded_render(make_scene, make_args, height=scene.height, fast=True, gpu_paths=paths)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    bad = {k: v for k, v in o["mismatch"].items() if v[0]}
+    assert not bad, f"GPU differs from the oracle: {bad}"
+    assert set(o["mismatch"]) == set(paths)
+    diff = {k: (v, g["counters"].get(k)) for k, v in o["counters"].items() if g["counters"].get(k) != v}
+    assert not diff, f"counters (oracle, gpu): {diff}"
+    return g, o
+
+
+def test_c3_full_size_oracle_parity():
+    """BASELINE configs[2] at FULL size -- 250 000 triangles that all straddle the near plane, 3840x2160: every sample
+    (owner, depth bits, colour), the resolved image and all counters equal the oracle's (1.6e9 bbox pixels on the CPU:
+    run as row bands over all host cores)."""
+    s = scenes.near_clip_scene()
+    g, o = _banded_parity(scenes.near_clip_scene, (), s)
+    assert o["counters"]["n_clipped_in"] > 0.99 * s.n_triangles
+
+
+def test_c4_sphere_8192_oracle_parity():
+    """BASELINE configs[3] (i) at FULL size: the 1M-triangle sphere on the 8192x8192 framebuffer, per sample."""
+    s = scenes.sphere_scene(width=8192, height=8192)
+    _banded_parity(scenes.sphere_scene, (1001, 501, 2.0, 8192, 8192), s)
+
+
+def test_c4_fullscreen_quad_8192_oracle_parity():
+    """BASELINE configs[3] (ii) at FULL size: the clipped 2-triangle quad covering all 67M pixels of 8192x8192."""
+    s = scenes.fullscreen_quad_scene(8192, 8192)
+    _banded_parity(scenes.fullscreen_quad_scene, (8192, 8192), s)
+
+
+def test_c4_8192_tile_rows_assemble_to_the_oracle_frame():
+    """BASELINE configs[3] as it is sharded: 8 contexts own interleaved bands of 16 tile rows of the 8192x8192 sphere
+    frame and store into ONE shared image (what sharding.PeerFrame does across GPUs); the assembled image equals the
+    oracle's frame."""
+    import torch
+
+    from oracle import oracle as orc
+    from rusterizer_b200.render import Renderer
+
+    s = scenes.sphere_scene(width=8192, height=8192)
+    world = 8
+    ctxs = []
+    for rank in range(world):
+        r = Renderer(s.width, s.height)
+        r.uniforms().bind_texture(0, s.texture)
+        r.set_row_interleave(16, rank, world)
+        ctxs.append(r)
+    img, _ = ctxs[0].shared_alloc(s.width * s.height * 4)
+    sums = {}
+    for r in ctxs:
+        r.reset_counters()
+        m = r.upload(s.draws[0].mesh)
+        scenes.render_scene(r, s, [m])
+        r.framebuffer()  # sizes the device buffers of this context
+        r.reset_counters()
+        scenes.render_scene(r, s, [m])
+        r.framebuffer_async(img)
+    for r in ctxs:
+        r.sync()
+        for k, v in r.counters().items():
+            sums[k] = sums.get(k, 0) + v
+
+    class _Raw:
+        __cuda_array_interface__ = {"shape": (s.height, s.width), "typestr": "<i4", "data": (img, False), "version": 3}
+
+    got = torch.as_tensor(_Raw(), device="cuda").cpu().numpy().view(np.uint32)
+    o = orc.banded_render(scenes.sphere_scene, (1001, 501, 2.0, 8192, 8192), height=s.height, fast=True)
+    assert np.array_equal(got, o["fb"])
+    for k in ("n_bbox_px", "n_covered_px", "n_shaded_px", "n_samples_written"):
+        assert sums[k] == o["counters"][k], k
+    ctxs[0].shared_free(img)
+    for r in ctxs:
+        r.close()
+
+
 def test_c3_full_size_properties():
     """BASELINE configs[2] at full size (250K near-clipped triangles, 3840x2160): the oracle needs
     minutes here (1.6e9 bbox pixels), so check invariants, run-to-run determinism and that a 4-way
