@@ -69,7 +69,10 @@ struct rz_ctx {
 
     // device buffers
     unsigned char *d_state = nullptr; // FrameState + tile_count[]
-    unsigned long long *d_bins = nullptr;
+    uint4 *d_bins = nullptr;          // bin entries of all tiles
+    TileBin *d_tile_bin = nullptr;    // [tiles] {first entry, capacity}
+    uint64_t bins_cap = 0;            // entries allocated in d_bins
+    bool bins_planned = false;
     RasterRec *d_recs = nullptr;
     unsigned long long *d_clipq = nullptr;
     ShadeRec *d_shade = nullptr;
@@ -85,7 +88,7 @@ struct rz_ctx {
     unsigned long long *d_dbg_time = nullptr;
     float4 *d_vtx = nullptr; // vertex-stage scratch [vert_cap][2], sized for the largest mesh
     uint32_t vert_cap = 0;
-    uint32_t rec_cap = 0, bin_cap = 0, large_cap = 0;
+    uint32_t rec_cap = 0, large_cap = 0;
     bool debug = false;
     bool use_direct = true; // tile-kernel instantiation with the large-item path (see enqueue_frame)
 
@@ -161,6 +164,7 @@ static size_t state_bytes(const rz_ctx *c) { return busy_offset(c) + sizeof(unsi
 
 static int free_frame_buffers(rz_ctx *c) {
     cudaFree(c->d_bins); c->d_bins = nullptr;
+    cudaFree(c->d_tile_bin); c->d_tile_bin = nullptr;
     cudaFree(c->d_recs); c->d_recs = nullptr;
     cudaFree(c->d_shade); c->d_shade = nullptr;
     cudaFree(c->d_clipq); c->d_clipq = nullptr;
@@ -180,14 +184,47 @@ static int ensure_vertex_scratch(rz_ctx *c, uint32_t nv) {
     return RZ_OK;
 }
 
-static int ensure_capacity(rz_ctx *c, uint32_t rec_cap, uint32_t bin_cap, uint32_t large_cap, uint32_t attr_cap) {
+// Tile bins.  Every tile owns a slice {off, cap} of one entry array, planned on the host: at first a uniform small
+// capacity, after an overflow from the tile counts of the frame that overflowed (the counters keep counting past the
+// capacity).  Every tile gets at least `floor` entries -- the longest list of the frame + 25 %, as long as that
+// uniform layout stays inside BIN_BUDGET bytes, so a moving object does not overflow the tiles it moves into -- and
+// 1.5 x its own count beyond that: memory is O(total entries), one hot tile no longer sizes every bin.
+static const uint64_t BIN_BUDGET = 512ull << 20;
+static int plan_bins(rz_ctx *c, const uint32_t *counts) {
     const size_t tiles = (size_t)c->tiles_x * c->tiles_y;
-    if (bin_cap > c->bin_cap) {
-        cudaFree(c->d_bins); c->d_bins = nullptr;
-        CU(c, cudaMalloc(&c->d_bins, tiles * bin_cap * sizeof(unsigned long long)));
-        c->bin_cap = bin_cap;
+    std::vector<TileBin> plan(tiles);
+    const uint64_t budget_per_tile = std::max<uint64_t>(32, BIN_BUDGET / sizeof(uint4) / tiles);
+    uint64_t floor_cap = std::min<uint64_t>(256, budget_per_tile);
+    if (counts) {
+        uint32_t mx = 0;
+        for (size_t t = 0; t < tiles; t++) mx = std::max(mx, counts[t]);
+        floor_cap = std::max<uint64_t>(floor_cap, std::min<uint64_t>((uint64_t)mx * 5 / 4 + 64, budget_per_tile));
     }
+    uint64_t off = 0;
+    for (size_t t = 0; t < tiles; t++) {
+        uint64_t cap = floor_cap;
+        if (counts) cap = std::max<uint64_t>(cap, (uint64_t)counts[t] * 3 / 2 + 64);
+        if (off + cap > 0xFFFFFFFFull) return fail(c, RZ_E_NOMEM, "the tile bins of this frame need more than 2^32 entries");
+        plan[t].off = (uint32_t)off;
+        plan[t].cap = (uint32_t)cap;
+        off += cap;
+    }
+    if (off > c->bins_cap) {
+        cudaFree(c->d_bins); c->d_bins = nullptr;
+        c->bins_cap = 0;
+        CU(c, cudaMalloc(&c->d_bins, off * sizeof(uint4)));
+        c->bins_cap = off;
+    }
+    if (!c->d_tile_bin) CU(c, cudaMalloc(&c->d_tile_bin, tiles * sizeof(TileBin)));
+    CU(c, cudaMemcpyAsync(c->d_tile_bin, plan.data(), tiles * sizeof(TileBin), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream)); // `plan` is pageable and dies with this call
+    c->bins_planned = true;
+    return RZ_OK;
+}
+
+static int ensure_capacity(rz_ctx *c, uint32_t rec_cap, uint32_t large_cap, uint32_t attr_cap) {
     if (rec_cap > c->rec_cap) {
+        if (rec_cap > ENTRY_REC_MASK) return fail(c, RZ_E_NOMEM, "a frame may hold at most 2^29 triangle records");
         cudaFree(c->d_recs); c->d_recs = nullptr;
         cudaFree(c->d_shade); c->d_shade = nullptr;
         cudaFree(c->d_clipq); c->d_clipq = nullptr;
@@ -461,11 +498,11 @@ static FrameParams make_params(rz_ctx *c, uint32_t *out_base) {
     P.scissor = make_uint4(c->sc_x0, c->sc_y0, c->sc_x1, c->sc_y1);
     P.ty_begin = c->row_begin / TH;
     P.ty_end = (c->row_end + TH - 1) / TH;
-    P.rec_cap = c->rec_cap; P.bin_cap = c->bin_cap; P.large_cap = c->large_cap;
+    P.rec_cap = c->rec_cap; P.large_cap = c->large_cap;
     P.fs = reinterpret_cast<FrameState *>(c->d_state);
     P.tile_count = reinterpret_cast<uint32_t *>(c->d_state + sizeof(FrameState));
     P.busy = reinterpret_cast<unsigned long long *>(c->d_state + busy_offset(c));
-    P.bins = c->d_bins; P.recs = c->d_recs; P.shade = c->d_shade; P.clipq = c->d_clipq; P.attrs = c->d_attrs; P.large = c->d_large;
+    P.bins = c->d_bins; P.tile_bin = c->d_tile_bin; P.recs = c->d_recs; P.shade = c->d_shade; P.clipq = c->d_clipq; P.attrs = c->d_attrs; P.large = c->d_large;
     P.draws = c->d_draws; P.attr_cap = c->attr_cap;
     P.out = out_base;
     P.spread_clears = (out_base != c->d_out && out_base != c->d_out_ring[1]) ? 1u : 0u;
@@ -498,11 +535,11 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     {
         // records are allocated from REC_STRIPES arenas filled round-robin by CTA: leave 25 % headroom
         uint32_t want_rec = std::max<uint64_t>(c->rec_cap, (total_tris * 5 / 4 + 256 * REC_STRIPES + REC_STRIPES - 1) / REC_STRIPES * REC_STRIPES);
-        uint32_t want_bin = std::max<uint32_t>(c->bin_cap, 256u);
         uint32_t want_large = std::max<uint32_t>(c->large_cap, 1u << 16);
         uint32_t want_attr = std::max<uint32_t>(c->attr_cap, 1u << 14);
-        int rc = ensure_capacity(c, want_rec, want_bin, want_large, want_attr);
+        int rc = ensure_capacity(c, want_rec, want_large, want_attr);
         if (rc != RZ_OK) return rc;
+        if (!c->bins_planned && (rc = plan_bins(c, nullptr)) != RZ_OK) return rc;
         // per-draw table for the shading step
         if (c->draws.size() > c->draw_cap) {
             cudaFree(c->d_draws); c->d_draws = nullptr;
@@ -631,7 +668,7 @@ int rz_framebuffer(rz_ctx *c, uint32_t *out_host, const uint32_t **out_device) {
         }
         // grow what overflowed (the cursors kept counting past the capacity) and replay the frame
         CU(c, cudaMemcpyAsync(dfs->counters, c->d_cnt_backup, sizeof(unsigned long long) * 16 * CNT_STRIPES, cudaMemcpyDeviceToDevice, st));
-        uint32_t want_rec = c->rec_cap, want_bin = c->bin_cap, want_large = c->large_cap, want_attr = c->attr_cap;
+        uint32_t want_rec = c->rec_cap, want_large = c->large_cap, want_attr = c->attr_cap;
         if (flags & ERR_ATTR_OVF) want_attr = std::max<uint64_t>((uint64_t)c->h_state->n_clip_attr * 5 / 4 + 1024, (uint64_t)c->attr_cap * 2);
         if (flags & ERR_REC_OVF) {
             uint32_t mx = 0; // the fullest stripe decides (cursors keep counting past the capacity)
@@ -643,16 +680,10 @@ int rz_framebuffer(rz_ctx *c, uint32_t *out_host, const uint32_t **out_device) {
             std::vector<uint32_t> counts((size_t)c->tiles_x * c->tiles_y);
             CU(c, cudaMemcpyAsync(counts.data(), c->d_state + sizeof(FrameState), counts.size() * 4, cudaMemcpyDeviceToHost, st));
             CU(c, cudaStreamSynchronize(st));
-            uint32_t mx = 0;
-            for (uint32_t v : counts) mx = std::max(mx, v);
-            want_bin = std::max<uint64_t>((uint64_t)mx * 5 / 4 + 64, (uint64_t)c->bin_cap * 2);
-            const size_t bytes = (size_t)c->tiles_x * c->tiles_y * want_bin * 8;
-            if (bytes > ((size_t)64 << 30)) {
-                rc = fail(c, RZ_E_NOMEM, "a screen tile holds %u triangles; its bin would need %zu bytes", mx, bytes);
-                break;
-            }
+            rc = plan_bins(c, counts.data());
+            if (rc != RZ_OK) break;
         }
-        rc = ensure_capacity(c, want_rec, want_bin, want_large, want_attr);
+        rc = ensure_capacity(c, want_rec, want_large, want_attr);
         if (rc != RZ_OK) break;
         if (attempt == 7) rc = fail(c, RZ_E_CAPACITY, "frame still overflows after 8 growth attempts");
     }

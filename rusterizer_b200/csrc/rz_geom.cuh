@@ -29,10 +29,11 @@ __device__ __forceinline__ uint32_t alloc_slot(uint32_t *cursor) {
     return base + __popc(m & lanemask_lt());
 }
 
-// Append (key, rec) to a tile's bin.  Neighbouring triangles land in the same tile, so the lanes
-// that are converged here are first grouped by tile (match.any): one atomic per group reserves the
-// slots, instead of up to 32 same-address atomics serialising in L2.
-__device__ __forceinline__ void push_bin(const FrameParams &P, uint32_t tile, uint32_t key, uint32_t rec) {
+// Append an entry to a tile's bin.  Neighbouring triangles land in the same tile, so the lanes that are converged
+// here are first grouped by tile (match.any): one atomic per group reserves the slots, instead of up to 32
+// same-address atomics serialising in L2.  `rec_tie` = record index | tie-break bits << 29, `box` = in-tile pixel box
+// (see the entry layout in rz_types.cuh).
+__device__ __forceinline__ void push_bin(const FrameParams &P, uint32_t tile, uint32_t key, uint32_t rec_tie, uint32_t box) {
     const unsigned peers = __match_any_sync(__activemask(), tile);
     const int leader = __ffs(peers) - 1;
     uint32_t base = 0;
@@ -41,10 +42,23 @@ __device__ __forceinline__ void push_bin(const FrameParams &P, uint32_t tile, ui
     }
     base = __shfl_sync(peers, base, leader);
     const uint32_t slot = base + __popc(peers & lanemask_lt());
-    if (slot < P.bin_cap)
-        P.bins[(size_t)tile * P.bin_cap + slot] = ((unsigned long long)key << 32) | rec;
+    const uint2 tb = __ldg(reinterpret_cast<const uint2 *>(&P.tile_bin[tile])); // planned on the host before the frame
+    if (slot < tb.y)
+        P.bins[(size_t)tb.x + slot] = make_uint4(key, rec_tie, box, 0u);
     else
         atomicOr(&P.fs->err, ERR_BIN_OVF);
+}
+// in-tile pixel box of the pixel rectangle [x0,x1) x [y0,y1) (non-empty inside tile (tx, ty))
+__device__ __forceinline__ uint32_t tile_box(uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1, uint32_t tx, uint32_t ty) {
+    const uint32_t X0 = max(x0, tx * TW), X1 = min(x1, tx * TW + TW), Y0 = max(y0, ty * TH), Y1 = min(y1, ty * TH + TH);
+    return (X0 - tx * TW) | ((Y0 - ty * TH) << 4) | ((X1 - X0 - 1u) << 8) | ((Y1 - Y0 - 1u) << 12);
+}
+// tie-break bits of EdgeFunctions::inside (mod.rs:160-168): bit k <=> E_k == 0 counts as inside
+__device__ __forceinline__ uint32_t tie_bits(const Setup &s) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) t |= ((s.nx[k] > 0.0f || (!(s.nx[k] < 0.0f) && s.ny[k] < 0.0f)) ? 1u : 0u) << k;
+    return t;
 }
 
 struct GeomLocal {
@@ -72,7 +86,7 @@ __device__ __forceinline__ float4 project_vertex(const float *c, float Wf, float
 // interpolated VertexAttributes ca[0..2] (6 floats each, local memory).
 __device__ __forceinline__ void emit_setup(const FrameParams &P, const DrawParams &D, Setup &s, uint32_t i0, uint32_t i1,
                                            uint32_t i2, const float (*ca)[6], uint32_t key, GeomLocal &lc) {
-    setup_normals(s); // inv_2x_area is recomputed by the tile stage; nothing here needs it
+    setup_normals(s);
     lc.c[C_TRIS_SETUP]++;
 
     BBox b = pixel_bbox(s, P.scissor);
@@ -130,7 +144,8 @@ __device__ __forceinline__ void emit_setup(const FrameParams &P, const DrawParam
 
     // non-finite / absurd coordinates take the literal per-pixel walk of the tile stage; frames without any
     // (all of them, in practice) skip the detection of such items in every chunk
-    if (!setup_is_tame(s)) atomicOr(&P.fs->has_wild, 1u);
+    const bool tame = setup_is_tame(s);
+    if (!tame) atomicOr(&P.fs->has_wild, 1u);
     const uint32_t stripe = blockIdx.x % REC_STRIPES, stripe_cap = P.rec_cap / REC_STRIPES;
     const uint32_t local = alloc_slot(&P.fs->rec_cursor[stripe]);
     if (local >= stripe_cap) {
@@ -157,18 +172,26 @@ __device__ __forceinline__ void emit_setup(const FrameParams &P, const DrawParam
         ar[3] = make_float4(ca[2][0], ca[2][1], ca[2][2], ca[2][3]);
         ar[4] = make_float4(ca[2][4], ca[2][5], 0.0f, 0.0f);
     }
+    // RasterizerTriangle::new (mod.rs:187-222): inv_2x_area = 1.0 / triangle_2x_area(points), once per triangle
+    // (area2 above is the same expression, mod.rs:15-21)
+    const float inv = fdiv(1.0f, area2);
     float4 *rr = reinterpret_cast<float4 *>(&P.recs[rec]);
     rr[0] = make_float4(s.px[0], s.py[0], s.px[1], s.py[1]);
     rr[1] = make_float4(s.px[2], s.py[2], s.z[0], s.z[1]);
-    rr[2] = make_float4(s.z[2], __uint_as_float(key), 0.0f, 0.0f);
-    float4 *sr = reinterpret_cast<float4 *>(&P.shade[rec]);
-    sr[0] = make_float4(s.w[0], s.w[1], s.w[2], __uint_as_float((D.fs & 3u) | (ca ? 4u : 0u) | (((D.fs >> 8) & 31u) << 3) | (D.draw << 8)));
-    sr[1] = make_float4(__uint_as_float(i0), __uint_as_float(i1), __uint_as_float(i2), __uint_as_float(clip_attr));
+    rr[2] = make_float4(s.z[2], inv, __uint_as_float(key), __uint_as_float(b.x0 | (b.y0 << 16)));
+    rr[3] = make_float4(s.w[0], s.w[1], s.w[2], __uint_as_float(b.x1 | (b.y1 << 16)));
+    *reinterpret_cast<uint4 *>(&P.shade[rec]) =
+        make_uint4((D.fs & 3u) | (ca ? 4u : 0u) | (((D.fs >> 8) & 31u) << 3) | (D.draw << 8), ca ? clip_attr : i0, i1, i2);
+    const uint32_t rec_tie = rec | (tie_bits(s) << 29);
+    const uint32_t wild_bit = tame ? 0u : ENTRY_WILD;
 
     if (small) {
 #pragma unroll
         for (uint32_t q = 0; q < 4; q++)
-            if ((tmask >> q) & 1u) push_bin(P, (ty0 + (q >> 1)) * P.tiles_x + tx0 + (q & 1u), key, rec);
+            if ((tmask >> q) & 1u) {
+                const uint32_t tx = tx0 + (q & 1u), ty = ty0 + (q >> 1);
+                push_bin(P, ty * P.tiles_x + tx, key, rec_tie, tile_box(b.x0, b.x1, b.y0, b.y1, tx, ty) | wild_bit);
+            }
     } else {
         const uint32_t tyB = (b.y1 - 1) / TH + 1;
         for (uint32_t ty = ty0; ty < tyB; ty += LARGE_SLAB_ROWS) {
@@ -330,9 +353,10 @@ __global__ void __launch_bounds__(NT, RZ_GEOM_MIN_CTAS) geom_kernel(FrameParams 
             const uint32_t key0 = (D.tri_base + t) * 8u;
             // Everything a triangle may need from its three vertices is requested up front, so the
             // independent gathers overlap instead of paying one L2 round trip per decision.
-            const float4 sv0 = __ldg(&D.vtx[2 * (size_t)i0]), cq0 = __ldg(&D.vtx[2 * (size_t)i0 + 1]);
-            const float4 sv1 = __ldg(&D.vtx[2 * (size_t)i1]), cq1 = __ldg(&D.vtx[2 * (size_t)i1 + 1]);
-            const float4 sv2 = __ldg(&D.vtx[2 * (size_t)i2]), cq2 = __ldg(&D.vtx[2 * (size_t)i2 + 1]);
+            // (written by this draw's vertex kernel, the preceding launch: plain loads, not the read-only path)
+            const float4 sv0 = D.vtx[2 * (size_t)i0], cq0 = D.vtx[2 * (size_t)i0 + 1];
+            const float4 sv1 = D.vtx[2 * (size_t)i1], cq1 = D.vtx[2 * (size_t)i1 + 1];
+            const float4 sv2 = D.vtx[2 * (size_t)i2], cq2 = D.vtx[2 * (size_t)i2 + 1];
             const float2 q0 = make_float2(cq0.x, cq0.y), q1 = make_float2(cq1.x, cq1.y), q2 = make_float2(cq2.x, cq2.y);
             const uint32_t code = __float_as_uint(cq0.w) & __float_as_uint(cq1.w) & __float_as_uint(cq2.w);
             // clipping::try_clip (rasterizer/clipping.rs:62-195): degenerate test on clip-space xy first
@@ -455,15 +479,15 @@ __global__ void __launch_bounds__(NT) clip_kernel(FrameParams P) {
     flush_geom_counters(P, lc, s_part, s_bbox);
 }
 
-__device__ __forceinline__ void load_setup(const RasterRec *recs, uint32_t rec, Setup &s, uint32_t &key) {
+// Screen points of a record (quarters q0, q1) + edge normals.  Records are written by the geometry kernels of the
+// same frame (the preceding launches of the PDL chain): plain loads after griddepcontrol.wait, never the
+// non-coherent read-only path.
+__device__ __forceinline__ void load_points(const RasterRec *recs, uint32_t rec, Setup &s) {
     const float4 *rr = reinterpret_cast<const float4 *>(&recs[rec]);
-    const float4 r0 = __ldg(rr), r1 = __ldg(rr + 1), r2 = __ldg(rr + 2);
+    const float4 r0 = rr[0], r1 = rr[1];
     s.px[0] = r0.x; s.py[0] = r0.y; s.px[1] = r0.z; s.py[1] = r0.w;
     s.px[2] = r1.x; s.py[2] = r1.y; s.z[0] = r1.z; s.z[1] = r1.w;
-    s.z[2] = r2.x;
-    key = __float_as_uint(r2.y);
-    s.w[0] = s.w[1] = s.w[2] = 1.0f;
-    setup_edges(s);
+    setup_normals(s);
 }
 
 // Large-triangle binning: persistent warps steal (triangle, slab of tile rows) items; the 32
@@ -483,11 +507,12 @@ __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
         if (item >= n) break;
         const LargeItem li = P.large[item];
         Setup s;
-        uint32_t key;
-        load_setup(P.recs, li.rec, s, key);
-        BBox b = pixel_bbox(s, P.scissor);
-        b.y0 = max(b.y0, P.row_begin);
-        b.y1 = min(b.y1, P.row_end);
+        load_points(P.recs, li.rec, s);
+        const uint32_t lo = P.recs[li.rec].bbox_lo, hi = P.recs[li.rec].bbox_hi;
+        BBox b; // the record's pixel box: bounded by the scissor and this ctx's row range already
+        b.x0 = lo & 0xFFFFu; b.y0 = lo >> 16; b.x1 = hi & 0xFFFFu; b.y1 = hi >> 16;
+        const uint32_t rec_tie = li.rec | (tie_bits(s) << 29);
+        const uint32_t wild_bit = setup_is_tame(s) ? 0u : ENTRY_WILD;
         const uint32_t tx0 = b.x0 / TW, tx1 = (b.x1 - 1) / TW + 1, ntx = tx1 - tx0;
         const uint32_t total = ntx * (li.ty1 - li.ty0);
         for (uint32_t t = lane; t < total; t += 32) {
@@ -504,7 +529,7 @@ __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
                 const float cy = s.ny[k] >= 0.0f ? sy_hi : sy_lo;
                 keep = keep && edge_pass(edge_eval(s, k, cx, cy), s.nx[k], s.ny[k]);
             }
-            if (keep) push_bin(P, ty * P.tiles_x + tx, key, li.rec);
+            if (keep) push_bin(P, ty * P.tiles_x + tx, li.key, rec_tie, tile_box(b.x0, b.x1, b.y0, b.y1, tx, ty) | wild_bit);
         }
     }
 }

@@ -15,9 +15,10 @@
 // shading position (rasterizer/mod.rs:70-83) and feeds the counters; only fragments with v(F) != 0
 // are shaded, and they write colour + depth of exactly the samples in v(F).  Nothing in a chunk
 // depends on the order in which threads run, so a tile whose list fits one chunk is never sorted.
-//   phase A0 thread = item          record load, setup, bbox, scan of the bbox areas
-//   phase A1 thread = (item, pixel) exact coverage -> fragment records on per-pixel lists
-//   phase A2 thread = fragment      sample depths
+//   phase A0 thread = item          bin entry (order key, record index, in-tile pixel box) -> scan of the box areas
+//   phase A1 thread = (item, pixel) exact coverage; covered units compute their sample depths from the same edge
+//                                   values (as RasterizerTriangle::fragment does, mod.rs:225-253) and become fragment
+//                                   records on per-pixel lists
 //   phase B  thread = pixel         m(F), v(F): the pixel's few fragments replayed in key order (lists of up to
 //                                   four fragments are ordered and replayed in registers)
 //   phase C  thread = fragment      interpolate + fragment shader + pack; write the visible samples
@@ -25,7 +26,9 @@
 // coordinates take a literal pixel-parallel walk (a thread owns a pixel for the whole run, so it
 // applies the triangles in order by construction) that evaluates EdgeFunctions::inside verbatim; the geometry
 // stage flags frames that contain such items (FrameState::has_wild), all others skip the search for them.
-// A single-chunk tile passes seven CTA barriers: one at the top of the trip, two in A0, one after A1, A2, B, C.
+// A single-chunk tile passes six CTA barriers: one at the top of the trip, two in A0, one after A1, B, C.
+// Setup (inv_2x_area, pixel box, tie-break bits) is done once per triangle by the geometry stage; the units of phase A1
+// and the fragments of phase C read the triangle's record straight from global memory (L1: ~7 units share a record).
 #pragma once
 #include "rz_exact.cuh"
 #include "rz_geom.cuh"
@@ -134,21 +137,22 @@ __device__ __forceinline__ uint32_t pack_argb(const float *o) {
 template <bool ALPHA, bool EXT>
 __device__ __forceinline__ uint32_t shade(const FrameParams &P, const Setup &s, uint32_t rec, const float *lut, int X,
                                           int Y, uint32_t mpost, float depth0, uint32_t &oob) {
-    const float4 *sr = reinterpret_cast<const float4 *>(&P.shade[rec]);
-    const float4 s0 = __ldg(sr);
-    const uint32_t info = __float_as_uint(s0.w), fs = info & 3u, texidx = EXT ? (info >> 3) & 31u : 0u;
+    // (records are written by the geometry kernels of this frame: plain loads, not the read-only path)
+    const uint4 sh = *reinterpret_cast<const uint4 *>(&P.shade[rec]);
+    const uint32_t info = sh.x, fs = info & 3u, texidx = EXT ? (info >> 3) & 31u : 0u;
     if (fs == 2u) return to_argb(depth0, depth0, depth0, 1.0f); // Color::grayscale(depths[0])
-    const float4 s1 = __ldg(sr + 1);
+    const float4 wq = reinterpret_cast<const float4 *>(&P.recs[rec])[3]; // depths_camera_space
+    const bool clipped = (info & 4u) != 0u;
     const float *a0, *a1, *a2;
-    if (info & 4u) { // clipped: interpolated attributes live in an AttrRec
-        a0 = P.attrs[__float_as_uint(s1.w)].a;
+    if (clipped) { // interpolated attributes live in an AttrRec (written by clip_kernel in this frame)
+        a0 = P.attrs[sh.y].a;
         a1 = a0 + 6;
         a2 = a0 + 12;
-    } else {         // unclipped: straight from the mesh
+    } else {       // unclipped: straight from the mesh (constant for the frame: read-only path)
         const float *attr = P.draws[info >> 8].attr;
-        a0 = attr + 6 * (size_t)__float_as_uint(s1.x);
-        a1 = attr + 6 * (size_t)__float_as_uint(s1.y);
-        a2 = attr + 6 * (size_t)__float_as_uint(s1.z);
+        a0 = attr + 6 * (size_t)sh.y;
+        a1 = attr + 6 * (size_t)sh.z;
+        a2 = attr + 6 * (size_t)sh.w;
     }
     float xs, ys;
     if (mpost == 0xFu) {
@@ -160,17 +164,19 @@ __device__ __forceinline__ uint32_t shade(const FrameParams &P, const Setup &s, 
         ys = fadd((float)Y, rgss_y(i));
     }
     const float e0 = edge_eval(s, 0, xs, ys), e1 = edge_eval(s, 1, xs, ys), e2 = edge_eval(s, 2, xs, ys);
-    const float fu = fdiv(e1, s0.x), fv = fdiv(e2, s0.y), fw = fdiv(e0, s0.z);
+    const float fu = fdiv(e1, wq.x), fv = fdiv(e2, wq.y), fw = fdiv(e0, wq.z);
     const float sum = fadd(fadd(fu, fv), fw);
     const float u = clamp01(fdiv(fu, sum));
     const float v = clamp01(fdiv(fv, sum));
     const float w = clamp01(fsub(fsub(1.0f, u), v));
-#define RZ_INTERP(c) fadd(fadd(fmul(__ldg(a0 + (c)), u), fmul(__ldg(a1 + (c)), v)), fmul(__ldg(a2 + (c)), w))
+#define RZ_LDA(p) (clipped ? *(p) : __ldg(p))
+#define RZ_INTERP(c) fadd(fadd(fmul(RZ_LDA(a0 + (c)), u), fmul(RZ_LDA(a1 + (c)), v)), fmul(RZ_LDA(a2 + (c)), w))
     if (fs == 1u) return to_argb(RZ_INTERP(0), RZ_INTERP(1), RZ_INTERP(2), RZ_INTERP(3));
     // (u, v) of a vertex sit at byte offset 24 * i + 16 of an array that starts on a 256-byte boundary (cudaMalloc;
     // AttrRec is 16-byte aligned with the three attributes at 0, 24, 48): one 64-bit load per vertex
-    const float2 t0 = __ldg(reinterpret_cast<const float2 *>(a0 + 4)), t1 = __ldg(reinterpret_cast<const float2 *>(a1 + 4)),
-                 t2 = __ldg(reinterpret_cast<const float2 *>(a2 + 4));
+    const float2 *u0p = reinterpret_cast<const float2 *>(a0 + 4), *u1p = reinterpret_cast<const float2 *>(a1 + 4),
+                 *u2p = reinterpret_cast<const float2 *>(a2 + 4);
+    const float2 t0 = RZ_LDA(u0p), t1 = RZ_LDA(u1p), t2 = RZ_LDA(u2p);
     const float tu = fadd(fadd(fmul(t0.x, u), fmul(t1.x, v)), fmul(t2.x, w));
     const float tv = fadd(fadd(fmul(t0.y, u), fmul(t1.y, v)), fmul(t2.y, w));
     float o[4];
@@ -185,13 +191,14 @@ __device__ __forceinline__ uint32_t shade(const FrameParams &P, const Setup &s, 
         for (int k = 0; k < (ALPHA ? 4 : 3); k++) o[k] = fdiv(fadd(o[k], RZ_INTERP(k)), 2.0f);
     }
 #undef RZ_INTERP
+#undef RZ_LDA
     return pack_argb<ALPHA>(o);
 }
 
-// Bitonic network in its "flip then halve" form: every compare-exchange puts the smaller key at
+// Bitonic network in its "flip then halve" form: every compare-exchange puts the smaller element at
 // the lower index, so n need not be a power of two (the missing tail behaves like +inf padding).
-template <typename T>
-__device__ __forceinline__ void block_sort(T *a, int n) {
+template <typename T, typename Less>
+__device__ __forceinline__ void block_sort(T *a, int n, Less less) {
     // Thread t owns the elements t, t + NT, ...: an aligned block of 32 elements belongs to one warp, so an
     // exchange distance below 32 keeps both partners inside the warp and __syncwarp orders the stages; only
     // the wide stages (and the first narrow one after them) need the CTA barrier -- 14 instead of 45 for 512 keys.
@@ -206,7 +213,7 @@ __device__ __forceinline__ void block_sort(T *a, int n) {
             const int p = i ^ (k - 1);
             if (p > i && p < n) {
                 T x = a[i], y = a[p];
-                if (x > y) { a[i] = y; a[p] = x; }
+                if (less(y, x)) { a[i] = y; a[p] = x; }
             }
         }
         for (int j = k >> 2; j > 0; j >>= 1) {
@@ -217,7 +224,7 @@ __device__ __forceinline__ void block_sort(T *a, int n) {
                 const int p = i ^ j;
                 if (p > i && p < n) {
                     T x = a[i], y = a[p];
-                    if (x > y) { a[i] = y; a[p] = x; }
+                    if (less(y, x)) { a[i] = y; a[p] = x; }
                 }
             }
         }
@@ -225,13 +232,13 @@ __device__ __forceinline__ void block_sort(T *a, int n) {
     __syncthreads();
 }
 
-// A large item staged in shared memory for the pixel-parallel walk (24 words).
+// A large item staged in shared memory for the pixel-parallel walks (20 words).
 struct __align__(16) BigSetup {
     float px[3], py[3], nx[3], ny[3], z[3];
     float inv;
     uint32_t key, rec;
     uint32_t box; // lx0 | ly0 << 8 | bw << 16 | bh << 24   (tile-local)
-    uint32_t pad;
+    uint32_t tie; // tie-break bits of the three edges
 };
 static_assert(sizeof(BigSetup) == 80, "BigSetup must be 20 words");
 
@@ -260,11 +267,12 @@ struct TileSmemT {
     uint32_t color[TILE_PX * 4];
     uint32_t okey[DBG ? TILE_PX * 4 : 4]; // owner keys (parity instrumentation only)
     float lut[256];                       // (b as f32) / 255.0   (Color::from_rgba, color.rs:22-29)
-    float it_f[10][NT];                   // items of the current chunk: px,py x3 | z x3 | inv
-    uint32_t it_key[NT], it_rec[NT];
+    uint32_t it_key[NT];                  // items of the current chunk: order key (the rank in the list once it is sorted)
+    uint32_t it_rec[NT];                  // record index | tie-break bits << 29
+    uint32_t it_okey[DBG ? NT : 1];       // the triangle's order key as the oracle reports it (parity instrumentation only)
     uint32_t it_rcp[NT];                  // ceil(65536 / bw): j / bw == (j * rcp) >> 16 for j < 256, bw <= 16
     uint32_t it_box[NT];                  // lx0 | ly0 << 8 | bw << 16
-    uint32_t pre[NT + 1];                 // exclusive prefix of the in-tile bbox areas (work units)
+    uint32_t pre[NT + 1];                 // exclusive prefix of the in-tile box areas (work units)
     uint8_t unit_item[UNIT_CAP];          // work unit -> item
     union {
         FragPool fr;
@@ -279,30 +287,80 @@ struct TileSmemT {
     uint32_t unit_budget;                 // adaptive work-unit budget of a chunk (fragment pool occupancy predictor)
 };
 
-// Sort the tile's list by order key (in shared memory when it fits, else in place in HBM) and
-// leave the sorted entries in the global bin.
+// Sort the tile's list by order key.  Lists of up to SORT_CAP entries: (key, position) pairs are sorted in shared
+// memory, then the entries are gathered in key order and written back over the head of the bin in COMPACT form --
+// uint2 {record | tie bits, box}; the order key of entry i is now simply i (returns true).  Longer lists are sorted in
+// place in HBM as full entries (returns false).
 template <typename SM>
-__device__ __forceinline__ void sort_tile_list(SM &S, unsigned long long *bin, int n) {
+__device__ __forceinline__ bool sort_tile_list(SM &S, uint4 *bin, int n) {
     __syncthreads();
     if (n <= SORT_CAP) {
-        for (int i = threadIdx.x; i < n; i += NT) S.u.sorted[i] = __ldcg(bin + i);
+        for (int i = threadIdx.x; i < n; i += NT)
+            S.u.sorted[i] = ((unsigned long long)__ldcg(reinterpret_cast<const uint32_t *>(bin + i)) << 32) | (uint32_t)i;
         __syncthreads();
-        block_sort(S.u.sorted, n);
-        for (int i = threadIdx.x; i < n; i += NT) __stcg(bin + i, S.u.sorted[i]);
-    } else {
-        block_sort(bin, n);
+        block_sort(S.u.sorted, n, [](unsigned long long a, unsigned long long b) { return a < b; });
+        uint2 e[SORT_CAP / NT];
+#pragma unroll
+        for (int k = 0; k < SORT_CAP / NT; k++) {
+            const int i = threadIdx.x + k * NT;
+            if (i < n) {
+                const uint4 v = __ldcg(bin + (uint32_t)S.u.sorted[i]);
+                e[k] = make_uint2(v.y, v.z);
+            }
+        }
+        __syncthreads(); // every entry has been read: the compact list may overwrite the head of the bin
+#pragma unroll
+        for (int k = 0; k < SORT_CAP / NT; k++) {
+            const int i = threadIdx.x + k * NT;
+            if (i < n) __stcg(reinterpret_cast<uint2 *>(bin) + i, e[k]);
+        }
+        __syncthreads();
+        return true;
     }
+    block_sort(bin, n, [](const uint4 &a, const uint4 &b) { return a.x < b.x; });
     __syncthreads();
+    return false;
+}
+
+// Stage the records of `cnt` chunk items in shared memory for a pixel-parallel walk (thread = item).  The staging
+// area aliases the fragment pool, which these walks do not use.
+template <typename SM>
+__device__ __forceinline__ void stage_big(const FrameParams &P, SM &S, int cnt, uint32_t key, uint32_t rec_tie, int bx0, int by0,
+                                          int bw, int bh) {
+    if ((int)threadIdx.x < cnt) {
+        BigSetup &b = S.u.big[threadIdx.x];
+        const uint32_t rec = rec_tie & ENTRY_REC_MASK;
+        Setup s;
+        load_points(P.recs, rec, s);
+        const float4 r2 = reinterpret_cast<const float4 *>(&P.recs[rec])[2];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            b.px[k] = s.px[k]; b.py[k] = s.py[k]; b.nx[k] = s.nx[k]; b.ny[k] = s.ny[k];
+        }
+        b.z[0] = s.z[0]; b.z[1] = s.z[1]; b.z[2] = r2.x;
+        b.inv = r2.y; b.key = key; b.rec = rec;
+        b.box = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bw << 16) | ((uint32_t)bh << 24);
+        b.tie = rec_tie >> 29;
+    }
+}
+__device__ __forceinline__ void big_to_setup(const BigSetup &b, Setup &q) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        q.px[k] = b.px[k]; q.py[k] = b.py[k]; q.nx[k] = b.nx[k]; q.ny[k] = b.ny[k];
+        q.z[k] = b.z[k];
+    }
+    q.inv = b.inv;
 }
 
 // Chunk dominated by large items: pixel-parallel walk with deferred shading (see the call site).  Only compiled
 // into the DIRECT instantiations of the tile kernel: its register needs perturb the allocation of the fragment
-// path that small-triangle workloads live in (C2 tile stage 90 -> 92 us on the same box), so frames without
-// large triangles run an instantiation that does not contain it.
+// path that small-triangle workloads live in, so frames without large triangles run an instantiation that does not
+// contain it.  The chunk's items are staged in S.u.big (stage_big) and S.it_key holds their order keys.
 template <bool DBG, bool EXT>
 __device__ __forceinline__ uint4 direct_chunk(const FrameParams &P, TileSmemT<DBG> &S, int cnt, bool sorted, int X, int Y) {
     const int tid = threadIdx.x, lx = tid % TW, ly = tid / TW;
     uint32_t c_cov = 0, c_shaded = 0, c_samples = 0, c_oob = 0;
+    const BigSetup *B = S.u.big;
     // the walk needs submission order: an unsorted chunk (it is the whole tile list then) is ranked by
     // order key right in the item table instead of being sorted and reloaded
     if (tid < cnt) {
@@ -320,21 +378,18 @@ __device__ __forceinline__ uint4 direct_chunk(const FrameParams &P, TileSmemT<DB
     uint32_t omp = 0u;          // 4 x 5 bits: that fragment's post-depth mask | (sample 0 covered) << 4
     for (int r = 0; r < cnt; r++) {
         const int it = (int)S.unit_item[r];
-        const uint32_t box = S.it_box[it];
+        const uint32_t box = B[it].box;
         const uint32_t rx = (uint32_t)lx - (box & 0xFFu), ry = (uint32_t)ly - ((box >> 8) & 0xFFu);
-        const uint32_t ibw = (box >> 16) & 0x1Fu;
-        if (rx >= ibw || ry * ibw >= S.pre[it + 1] - S.pre[it]) continue; // outside the in-tile bbox
+        if (rx >= ((box >> 16) & 0xFFu) || ry >= (box >> 24)) continue; // outside the in-tile box
         Setup q;
-        q.px[0] = S.it_f[0][it]; q.py[0] = S.it_f[1][it]; q.px[1] = S.it_f[2][it];
-        q.py[1] = S.it_f[3][it]; q.px[2] = S.it_f[4][it]; q.py[2] = S.it_f[5][it];
-        setup_normals(q);
+        big_to_setup(B[it], q);
+        const uint32_t tie = B[it].tie;
         float thr[3];
-        edge_thresholds(q, thr);
+#pragma unroll
+        for (int k = 0; k < 3; k++) thr[k] = ((tie >> k) & 1u) ? 0.0f : 1.401298464e-45f;
         const uint32_t m = coverage_mask_fast(q, thr, X, Y);
         if (!m) continue;
         c_cov++;
-        q.z[0] = S.it_f[6][it]; q.z[1] = S.it_f[7][it]; q.z[2] = S.it_f[8][it];
-        q.inv = S.it_f[9][it];
         uint32_t mp = 0;
         if (m & 1u) { const float z = sample_depth(q, X, Y, 0); if (z < d.x) { d.x = z; mp |= 1u; } } // strict < (mod.rs:374)
         if (m & 2u) { const float z = sample_depth(q, X, Y, 1); if (z < d.y) { d.y = z; mp |= 2u; } }
@@ -362,18 +417,14 @@ __device__ __forceinline__ uint4 direct_chunk(const FrameParams &P, TileSmemT<DB
         if (!first) continue;
         const uint32_t tag = (omp >> (5 * k)) & 0x1Fu;
         Setup q;
-        q.px[0] = S.it_f[0][it]; q.py[0] = S.it_f[1][it]; q.px[1] = S.it_f[2][it];
-        q.py[1] = S.it_f[3][it]; q.px[2] = S.it_f[4][it]; q.py[2] = S.it_f[5][it];
-        q.z[0] = S.it_f[6][it]; q.z[1] = S.it_f[7][it]; q.z[2] = S.it_f[8][it];
-        q.inv = S.it_f[9][it];
-        setup_normals(q);
+        big_to_setup(B[it], q);
         const float depth0 = (tag & 16u) ? sample_depth(q, X, Y, 0) : 0.0f; // FragCoords.depths[0] (mod.rs:458-463)
-        const uint32_t argb = shade<DBG, EXT>(P, q, S.it_rec[it], S.lut, X, Y, tag & 0xFu, depth0, c_oob);
+        const uint32_t argb = shade<DBG, EXT>(P, q, B[it].rec, S.lut, X, Y, tag & 0xFu, depth0, c_oob);
 #pragma unroll
         for (int j = k; j < 4; j++)
             if (((own >> (8 * j)) & 0xFFu) == it) {
                 S.color[tid * 4 + j] = argb;
-                if (DBG) S.okey[tid * 4 + j] = S.it_key[it];
+                if (DBG) S.okey[tid * 4 + j] = DBG ? S.it_okey[it] : 0u;
             }
     }
     __syncthreads();
@@ -476,8 +527,10 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
         // the entry carries the tile id and its list length (order_kernel): one load instead of two dependent ones
         const unsigned long long e = __ldcg(P.busy + (size_t)b * P.tiles_x * P.tiles_y + (work - start));
         tile = (uint32_t)e;
-        n = (int)min((uint32_t)(e >> 32), P.bin_cap);
+        n = (int)(uint32_t)(e >> 32);
     }
+    const uint2 tbin = __ldg(reinterpret_cast<const uint2 *>(&P.tile_bin[tile])); // {first entry, capacity}
+    n = min(n, (int)tbin.y);
     const uint32_t tx = tile % P.tiles_x, ty = tile / P.tiles_x;
     const int tileX0 = tx * TW, tileY0 = ty * TH;
     const int X = tileX0 + lx, Y = tileY0 + ly;
@@ -496,33 +549,37 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
 
     if (n > 0) {
         S.head[tid] = FR_NONE;
-        unsigned long long *bin = P.bins + (size_t)tile * P.bin_cap;
-        bool sorted = false;
+        uint4 *bin = P.bins + tbin.x;
+        bool sorted = false;  // the list is in submission order
+        bool compact = false; // ... and in its compact form (sort_tile_list)
         if (n > CHUNK) {
-            sort_tile_list(S, bin, n);
+            compact = sort_tile_list(S, bin, n);
             sorted = true;
         }
         // (no barrier needed here: sort_tile_list ends with one, and the clears above are separated from their
         // first readers by the barriers of phase A0)
 
         for (int pos = 0; pos < n;) {
-            // ---- load this window's items (thread = item) ----
+            // ---- load this window's entries (thread = item) ----
             const int item = pos + tid;
             const bool valid = tid < CHUNK && item < n;
-            Setup s;
-            uint32_t rec = 0, key = 0;
-            int bx0 = 0, by0 = 0, bw = 0, bh = 0; // in-tile bbox, tile-local origin
+            uint32_t rec_tie = 0, key = 0;
+            int bx0 = 0, by0 = 0, bw = 0, bh = 0; // in-tile box, tile-local origin
             bool big = false;
             if (valid) {
-                rec = (uint32_t)__ldcg(bin + item);
-                load_setup(P.recs, rec, s, key);
-                BBox b = pixel_bbox(s, P.scissor);
-                const int x0 = max((int)b.x0, tileX0), x1 = min((int)b.x1, tileX0 + TW);
-                const int y0 = max((int)b.y0, tileY0), y1 = min((int)b.y1, tileY0 + TH);
-                if (x0 < x1 && y0 < y1) {
-                    bx0 = x0 - tileX0; by0 = y0 - tileY0; bw = x1 - x0; bh = y1 - y0;
+                uint32_t boxw;
+                if (compact) {
+                    const uint2 e = __ldcg(reinterpret_cast<const uint2 *>(bin) + item);
+                    key = (uint32_t)item; // sorted: the rank orders the items
+                    rec_tie = e.x; boxw = e.y;
+                } else {
+                    const uint4 e = __ldcg(bin + item);
+                    key = e.x; rec_tie = e.y; boxw = e.z;
                 }
-                big = wild && bw > 0 && !setup_is_tame(s); // NaN / inf / absurd coordinates: literal per-pixel path
+                bx0 = (int)(boxw & 15u); by0 = (int)((boxw >> 4) & 15u);
+                bw = (int)((boxw >> 8) & 15u) + 1; bh = (int)((boxw >> 12) & 15u) + 1;
+                big = wild && (boxw & ENTRY_WILD) != 0u; // NaN / inf / absurd coordinates: literal per-pixel path
+                if (DBG) S.it_okey[tid] = compact ? P.recs[rec_tie & ENTRY_REC_MASK].key : key;
             }
             const int nvalid = min(CHUNK, n - pos);
             // items for the literal walk split the window into runs; a frame without any has none to look for
@@ -541,25 +598,16 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
             }
 
             if (!sorted && first_big <= CHUNK) { // large items need the ordered walk
-                sort_tile_list(S, bin, n);
+                compact = sort_tile_list(S, bin, n);
                 sorted = true;
                 continue;
             }
 
             if (first_big == 0) {
-                // ================= run of large items: pixel-parallel =================
+                // ================= run of items for the literal walk: pixel-parallel =================
                 const int run = min(first_small, nvalid);
-                BigSetup *B = S.u.big;
-                if (tid < run) {
-                    BigSetup &b = B[tid];
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        b.px[k] = s.px[k]; b.py[k] = s.py[k]; b.nx[k] = s.nx[k]; b.ny[k] = s.ny[k];
-                        b.z[k] = s.z[k];
-                    }
-                    b.inv = s.inv; b.key = key; b.rec = rec;
-                    b.box = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bw << 16) | ((uint32_t)bh << 24);
-                }
+                const BigSetup *B = S.u.big;
+                stage_big(P, S, run, key, rec_tie, bx0, by0, bw, bh);
                 __syncthreads();
                 float d[4];
                 uint32_t col[4], ok[4];
@@ -574,12 +622,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                     const uint32_t rx = (uint32_t)lx - (box & 0xFF), ry = (uint32_t)ly - ((box >> 8) & 0xFF);
                     if (rx >= ((box >> 16) & 0xFF) || ry >= (box >> 24)) continue;
                     Setup q;
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        q.px[k] = B[it].px[k]; q.py[k] = B[it].py[k]; q.nx[k] = B[it].nx[k]; q.ny[k] = B[it].ny[k];
-                        q.z[k] = B[it].z[k];
-                    }
-                    q.inv = B[it].inv;
+                    big_to_setup(B[it], q);
                     const uint32_t m = coverage_mask(q, X, Y);
                     if (!m) continue;
                     c_cov++;
@@ -599,7 +642,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                         if ((mp >> k) & 1u) {
                             d[k] = zs[k];
                             col[k] = argb;
-                            if (DBG) ok[k] = B[it].key;
+                            if (DBG) ok[k] = DBG ? S.it_okey[it] : 0u;
                         }
                 }
 #pragma unroll
@@ -615,15 +658,11 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
 
             // ================= chunk of small items =================
             int cnt = sorted ? min(first_big, nvalid) : nvalid;
-            // ---- phase A0: item table + exclusive scan of the in-tile bbox areas ----
+            // ---- phase A0: item table + exclusive scan of the in-tile box areas ----
             const uint32_t area = (tid < cnt) ? (uint32_t)(bw * bh) : 0u;
             if (tid < cnt) {
-                S.it_f[0][tid] = s.px[0]; S.it_f[1][tid] = s.py[0]; S.it_f[2][tid] = s.px[1];
-                S.it_f[3][tid] = s.py[1]; S.it_f[4][tid] = s.px[2]; S.it_f[5][tid] = s.py[2];
-                S.it_f[6][tid] = s.z[0]; S.it_f[7][tid] = s.z[1]; S.it_f[8][tid] = s.z[2];
-                S.it_f[9][tid] = s.inv;
-                S.it_key[tid] = key; S.it_rec[tid] = rec;
-                S.it_rcp[tid] = (65536u + (uint32_t)bw - 1u) / (uint32_t)max(bw, 1);
+                S.it_key[tid] = key; S.it_rec[tid] = rec_tie;
+                S.it_rcp[tid] = (65536u + (uint32_t)bw - 1u) / (uint32_t)bw;
                 S.it_box[tid] = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bw << 16);
             }
             uint32_t incl = area;
@@ -650,13 +689,14 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
             }
             __syncthreads();
             // ================= chunk dominated by large items: pixel-parallel, deferred shading =================
-            // When the items of the chunk cover the tile broadly (average in-tile bbox >= DIRECT_MIN_AREA pixels) the
+            // When the items of the chunk cover the tile broadly (average in-tile box >= DIRECT_MIN_AREA pixels) the
             // fragment machinery below only adds barriers: every thread keeps its pixel, walks the chunk's items in
             // submission order (exact coverage, sample depths, strict-< depth test: the literal sequence of
             // rasterizer/mod.rs:443-473), remembers per sample which item wrote it last together with that fragment's
-            // post-depth mask, and shades each surviving owner once at the end.  No fragment pool, three barriers.
+            // post-depth mask, and shades each surviving owner once at the end.  No fragment pool.
             if (DIRECT && cnt > 0 && S.pre[cnt] >= (uint32_t)DIRECT_MIN_AREA * (uint32_t)cnt) {
-                const uint4 dc = direct_chunk<DBG, EXT>(P, S, cnt, sorted, X, Y);
+                stage_big(P, S, cnt, key, rec_tie, bx0, by0, bw, bh);
+                const uint4 dc = direct_chunk<DBG, EXT>(P, S, cnt, sorted, X, Y); // (starts with a barrier)
                 c_cov += dc.x; c_shaded += dc.y; c_samples += dc.z; c_oob += dc.w;
                 pos += cnt;
                 continue;
@@ -672,7 +712,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 // keep the longest prefix of items that fits
                 // (chunks must follow submission order, so an unsorted list is sorted first)
                 if (!sorted) {
-                    sort_tile_list(S, bin, n);
+                    compact = sort_tile_list(S, bin, n);
                     sorted = true;
                     continue;
                 }
@@ -684,15 +724,18 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 cnt = lo;
             }
 
-            RZ_STAMP(0) // A0 done (list + records loaded, item table + scan)
+            RZ_STAMP(0) // A0 done (entries loaded, item table + scan)
             bool need_sort = false;
             for (;;) {
-                // ---- phase A1: thread = (item, bbox pixel) work unit, consecutive lanes = consecutive units ----
+                // ---- phase A1: thread = (item, box pixel) work unit, consecutive lanes = consecutive units ----
                 const int units = (int)S.pre[cnt];
                 uint32_t cov_try = 0;
                 for (int u0 = 0; u0 < units; u0 += NT) {
                     const int u = u0 + tid;
                     uint32_t m = 0, p = 0, it = 0;
+                    float e1s[4], e2s[4]; // edge values 1 and 2 of the four samples (EdgeFunctions.coverage_evaluated)
+                    float z0 = 0.0f, z1 = 0.0f;
+                    const float4 *rr = nullptr;
                     if (u < units) {
                         it = S.unit_item[u];
                         const uint32_t box = S.it_box[it];
@@ -701,13 +744,27 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                         const int ry = (int)(((uint32_t)j * S.it_rcp[it]) >> 16), rx = j - ry * ibw; // j / ibw, j < 256, ibw <= 16
                         const int lpx = (int)(box & 0xFFu) + rx, lpy = (int)((box >> 8) & 0xFFu) + ry;
                         p = (uint32_t)(lpy * TW + lpx);
-                        Setup q;
-                        q.px[0] = S.it_f[0][it]; q.py[0] = S.it_f[1][it]; q.px[1] = S.it_f[2][it];
-                        q.py[1] = S.it_f[3][it]; q.px[2] = S.it_f[4][it]; q.py[2] = S.it_f[5][it];
-                        setup_normals(q);
-                        float thr[3];
-                        edge_thresholds(q, thr);
-                        m = coverage_mask_fast(q, thr, tileX0 + lpx, tileY0 + lpy);
+                        const uint32_t rec_t = S.it_rec[it];
+                        rr = reinterpret_cast<const float4 *>(&P.recs[rec_t & ENTRY_REC_MASK]);
+                        const float4 r0 = rr[0], r1 = rr[1]; // ~7 units share a record: L1 hits
+                        z0 = r1.z; z1 = r1.w;
+                        // EdgeFunctions normals (mod.rs:200-205) and the single-compare form of inside() (rz_exact.cuh)
+                        const float n0x = -fsub(r0.w, r0.y), n0y = fsub(r0.z, r0.x);
+                        const float n1x = -fsub(r1.y, r0.w), n1y = fsub(r1.x, r0.z);
+                        const float n2x = -fsub(r0.y, r1.y), n2y = fsub(r0.x, r1.x);
+                        const float t0 = (rec_t & (1u << 29)) ? 0.0f : 1.401298464e-45f;
+                        const float t1 = (rec_t & (1u << 30)) ? 0.0f : 1.401298464e-45f;
+                        const float t2 = (rec_t & (1u << 31)) ? 0.0f : 1.401298464e-45f;
+                        const float fx = (float)(tileX0 + lpx), fy = (float)(tileY0 + lpy);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const float xs = fadd(fx, rgss_x(i)), ys = fadd(fy, rgss_y(i));
+                            const float e0 = fadd(fmul(n0x, fsub(xs, r0.x)), fmul(n0y, fsub(ys, r0.y)));
+                            const float e1 = fadd(fmul(n1x, fsub(xs, r0.z)), fmul(n1y, fsub(ys, r0.w)));
+                            const float e2 = fadd(fmul(n2x, fsub(xs, r1.x)), fmul(n2y, fsub(ys, r1.y)));
+                            m |= ((e0 >= t0) & (e1 >= t1) & (e2 >= t2)) ? (1u << i) : 0u;
+                            e1s[i] = e1; e2s[i] = e2;
+                        }
                     }
                     const uint32_t bal = __ballot_sync(0xffffffffu, m != 0u);
                     if (bal) { // warp-aggregated fragment allocation (ballot + popc prefix)
@@ -717,6 +774,21 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                         if (m) {
                             cov_try++;
                             if (slot < POOL) {
+                                // RasterizerTriangle::fragment (mod.rs:225-253): the covered samples' depths from the edge
+                                // values of the coverage evaluation.  Vector::dot starts its sum at 0.0 (vector.rs:17-23),
+                                // which only turns a -0.0 edge value into +0.0: `+ 0.0f` restores exactly that.
+                                const float4 r2 = rr[2];
+                                const float z2 = r2.x, inv = r2.y;
+                                float zz[4];
+#pragma unroll
+                                for (int i = 0; i < 4; i++) {
+                                    const float b0 = clamp01(fmul(fadd(e1s[i], 0.0f), inv));
+                                    const float b1 = clamp01(fmul(fadd(e2s[i], 0.0f), inv));
+                                    const float b2 = clamp01(fsub(fsub(1.0f, b0), b1));
+                                    const float z = fadd(fadd(fmul(b0, z0), fmul(b1, z1)), fmul(b2, z2));
+                                    zz[i] = ((m >> i) & 1u) ? z : 0.0f;
+                                }
+                                S.u.fr.z[slot] = make_float4(zz[0], zz[1], zz[2], zz[3]);
                                 S.u.fr.meta[slot] = it | (p << 8) | (m << 16);
                                 S.u.fr.next[slot] = (uint16_t)atomicExch(&S.head[p], slot);
                             } else {
@@ -759,32 +831,13 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 __syncthreads();
             }
             if (need_sort) {
-                sort_tile_list(S, bin, n);
+                compact = sort_tile_list(S, bin, n);
                 sorted = true;
                 continue;
             }
-            RZ_STAMP(1) // A1 done
+            RZ_STAMP(1) // A1 done (coverage + sample depths)
+            RZ_STAMP(2)
             const int nfrag = (int)S.nfrag;
-            // ---- phase A2: thread = fragment; the covered samples' depths (mod.rs:226-245) ----
-            for (int f = tid; f < nfrag; f += NT) {
-                const uint32_t meta = S.u.fr.meta[f];
-                const uint32_t it = meta & 0xFFu, p = (meta >> 8) & 0xFFu, m = (meta >> 16) & 0xFu;
-                Setup q;
-                q.px[0] = S.it_f[0][it]; q.py[0] = S.it_f[1][it]; q.px[1] = S.it_f[2][it];
-                q.py[1] = S.it_f[3][it]; q.px[2] = S.it_f[4][it]; q.py[2] = S.it_f[5][it];
-                q.z[0] = S.it_f[6][it]; q.z[1] = S.it_f[7][it]; q.z[2] = S.it_f[8][it];
-                q.inv = S.it_f[9][it];
-                setup_normals(q);
-                const int PX = tileX0 + (int)(p % TW), PY = tileY0 + (int)(p / TW);
-                float4 z;
-                z.x = (m & 1u) ? sample_depth(q, PX, PY, 0) : 0.0f;
-                z.y = (m & 2u) ? sample_depth(q, PX, PY, 1) : 0.0f;
-                z.z = (m & 4u) ? sample_depth(q, PX, PY, 2) : 0.0f;
-                z.w = (m & 8u) ? sample_depth(q, PX, PY, 3) : 0.0f;
-                S.u.fr.z[f] = z;
-            }
-            __syncthreads();
-            RZ_STAMP(2) // A2 done
             // ---- phase B: thread = pixel; replay this pixel's fragments in submission order ----
             // (depth test exactly as Rasterizer::depth_coverage + write_pixel, mod.rs:363-397); the last writer
             // of every sample is the fragment that stays visible.  A pixel holds 2-3 fragments on average.
@@ -905,18 +958,17 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 const uint32_t vis = fin >> 4;
                 if (!vis) continue;
                 const uint32_t it = meta & 0xFFu;
+                const uint32_t rec = S.it_rec[it] & ENTRY_REC_MASK;
                 Setup q;
-                q.px[0] = S.it_f[0][it]; q.py[0] = S.it_f[1][it]; q.px[1] = S.it_f[2][it];
-                q.py[1] = S.it_f[3][it]; q.px[2] = S.it_f[4][it]; q.py[2] = S.it_f[5][it];
-                setup_normals(q);
-                const float4 z = S.u.fr.z[f];
-                const uint32_t argb = shade<DBG, EXT>(P, q, S.it_rec[it], S.lut, tileX0 + (int)(p % TW), tileY0 + (int)(p / TW),
-                                            fin & 0xFu, z.x, c_oob);
+                load_points(P.recs, rec, q);
+                const float depth0 = S.u.fr.z[f].x;
+                const uint32_t argb = shade<DBG, EXT>(P, q, rec, S.lut, tileX0 + (int)(p % TW), tileY0 + (int)(p / TW),
+                                            fin & 0xFu, depth0, c_oob);
 #pragma unroll
                 for (int k = 0; k < 4; k++)
                     if ((vis >> k) & 1u) {
                         S.color[p * 4 + k] = argb;
-                        if (DBG) S.okey[p * 4 + k] = S.it_key[it];
+                        if (DBG) S.okey[p * 4 + k] = DBG ? S.it_okey[it] : 0u;
                     }
             }
             __syncthreads();

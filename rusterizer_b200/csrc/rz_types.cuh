@@ -74,24 +74,43 @@ struct FrameState {
     uint32_t bucket_n[ORDER_BUCKETS]; // non-empty tiles per list-length class (class 0 = longest lists)
 };
 
-// Raster record: what coverage + depth need to re-create RasterizerTriangle (rasterizer/mod.rs:178-184):
-// the three screen points and depths, and the submission-order key.  48 B = 3 x float4.
+// Raster record: RasterizerTriangle (rasterizer/mod.rs:178-222) as the tile stage needs it -- the three screen points,
+// depths, inv_2x_area, depths_camera_space, the submission-order key and the pixel bounding box.  Everything is computed
+// ONCE per triangle by the geometry stage (the tile stage used to redo setup + bbox per (triangle, tile)).
+// 64 B = 4 x float4; the tile stage loads the quarters it needs:
+//   q0 = p0x p0y p1x p1y      q1 = p2x p2y z0 z1      q2 = z2 inv key bbox_lo      q3 = w0 w1 w2 bbox_hi
+// bbox_lo = x0 | y0 << 16, bbox_hi = x1 | y1 << 16 (half-open pixel ranges, already bounded by the scissor; W, H <= 65535)
 struct __align__(16) RasterRec {
     float p0x, p0y, p1x, p1y;
     float p2x, p2y, z0, z1;
-    float z2;
+    float z2, inv;
     uint32_t key;   // submission order: 8 * (triangle number in frame) + fan index
-    uint32_t pad0, pad1;
+    uint32_t bbox_lo;
+    float w0, w1, w2;
+    uint32_t bbox_hi;
+};
+static_assert(sizeof(RasterRec) == 64, "RasterRec is four 16-byte quarters");
+
+// Shade record: the fragment shader id and where the three VertexAttributes live.  Unclipped triangles point at the
+// mesh's own attribute array through their vertex indices (nothing is copied); clipped ones at an AttrRec.  16 B.
+struct __align__(16) ShadeRec {
+    uint32_t info;        // fs (2 bits) | clipped << 2 | texture index << 3 (5 bits) | draw << 8
+    uint32_t i0, i1, i2;  // vertex indices into the draw's attribute array (unclipped); i0 = AttrRec index (clipped)
 };
 
-// Shade record: what only visible fragments need -- depths_camera_space, the fragment shader id and
-// where the three VertexAttributes live.  Unclipped triangles point at the mesh's own attribute
-// array through their vertex indices (nothing is copied); clipped ones at an AttrRec.  32 B.
-struct __align__(16) ShadeRec {
-    float w0, w1, w2;
-    uint32_t info;        // fs (2 bits) | clipped << 2 | texture index << 3 (5 bits) | draw << 8
-    uint32_t i0, i1, i2;  // vertex indices into the draw's attribute array (unclipped)
-    uint32_t clip_attr;   // index into FrameParams::attrs (clipped)
+// Tile bin entry, 16 B, written by the geometry stage for every (triangle, tile) pair:
+//   x = order key
+//   y = record index (29 bits) | tie-break bits of the three edges << 29  (EdgeFunctions::inside, mod.rs:160-168:
+//       bit k set <=> a sample exactly on edge k counts as inside, i.e. n.x > 0 || (n.x == 0 && n.y < 0))
+//   z = in-tile pixel box: lx0 | ly0 << 4 | (bw - 1) << 8 | (bh - 1) << 12, bit 16 = non-finite / absurd coordinates
+//       (literal per-pixel walk)
+//   w = unused
+constexpr uint32_t ENTRY_REC_MASK = 0x1FFFFFFFu;
+constexpr uint32_t ENTRY_WILD = 1u << 16;
+// Per-tile bin: `off` = first entry in FrameParams::bins, `cap` = entries the tile may hold (planned on the host from the
+// counts of the last frame that overflowed: memory is O(total entries), a single hot tile no longer sizes every bin)
+struct TileBin {
+    uint32_t off, cap;
 };
 
 // Interpolated attributes of a clipped triangle: VertexAttribute x3 (graphics_primitives.rs:10-13),
@@ -128,11 +147,12 @@ struct FrameParams {
     uint32_t row_begin, row_end; // same in pixel rows
     uint4 scissor;               // {x0, y0, x1, y1}: bounds every triangle's pixel bbox (default = the viewport)
     uint32_t il_band, il_rank, il_world; // interleaved ownership of tile-row bands (il_band == 0: off), see owns_tile_row()
-    uint32_t rec_cap, bin_cap, large_cap;
+    uint32_t rec_cap, large_cap;
     FrameState *fs;
     uint32_t *tile_count;        // [tiles_x * tiles_y]
     unsigned long long *busy;    // [ORDER_BUCKETS][tiles_x * tiles_y] non-empty tiles per class: tile id | list length << 32
-    unsigned long long *bins;    // [tiles][bin_cap]  (key << 32 | rec)
+    uint4 *bins;                 // bin entries of all tiles (see TileBin); tile t owns [tile_bin[t].off, +cap)
+    const TileBin *tile_bin;     // [tiles_x * tiles_y]
     RasterRec *recs;
     ShadeRec *shade;
     unsigned long long *clipq;   // [rec_cap] draw << 32 | triangle: triangles that straddle a clip plane
