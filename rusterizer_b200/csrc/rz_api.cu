@@ -160,7 +160,7 @@ static void mat4_mul(const float *A, const float *B, float *R) {
 // entries, so the region starts on the next 16-byte boundary)
 static size_t zeroed_state_bytes(const rz_ctx *c) { return sizeof(FrameState) + sizeof(uint32_t) * (size_t)c->tiles_x * c->tiles_y; }
 static size_t busy_offset(const rz_ctx *c) { return (zeroed_state_bytes(c) + 15) / 16 * 16; }
-static size_t state_bytes(const rz_ctx *c) { return busy_offset(c) + sizeof(unsigned long long) * ORDER_BUCKETS * (size_t)c->tiles_x * c->tiles_y; }
+static size_t state_bytes(const rz_ctx *c) { return busy_offset(c) + sizeof(uint4) * ORDER_BUCKETS * (size_t)c->tiles_x * c->tiles_y; }
 
 static int free_frame_buffers(rz_ctx *c) {
     cudaFree(c->d_bins); c->d_bins = nullptr;
@@ -501,7 +501,7 @@ static FrameParams make_params(rz_ctx *c, uint32_t *out_base) {
     P.rec_cap = c->rec_cap; P.large_cap = c->large_cap;
     P.fs = reinterpret_cast<FrameState *>(c->d_state);
     P.tile_count = reinterpret_cast<uint32_t *>(c->d_state + sizeof(FrameState));
-    P.busy = reinterpret_cast<unsigned long long *>(c->d_state + busy_offset(c));
+    P.busy = reinterpret_cast<uint4 *>(c->d_state + busy_offset(c));
     P.bins = c->d_bins; P.tile_bin = c->d_tile_bin; P.recs = c->d_recs; P.shade = c->d_shade; P.clipq = c->d_clipq; P.attrs = c->d_attrs; P.large = c->d_large;
     P.draws = c->d_draws; P.attr_cap = c->attr_cap;
     P.out = out_base;

@@ -34,6 +34,8 @@ __device__ __forceinline__ uint32_t alloc_slot(uint32_t *cursor) {
 // same-address atomics serialising in L2.  `rec_tie` = record index | tie-break bits << 29, `box` = in-tile pixel box
 // (see the entry layout in rz_types.cuh).
 __device__ __forceinline__ void push_bin(const FrameParams &P, uint32_t tile, uint32_t key, uint32_t rec_tie, uint32_t box) {
+    const uint2 tb = __ldg(reinterpret_cast<const uint2 *>(&P.tile_bin[tile])); // planned on the host before the frame;
+                                                                                // in flight together with the atomic below
     const unsigned peers = __match_any_sync(__activemask(), tile);
     const int leader = __ffs(peers) - 1;
     uint32_t base = 0;
@@ -42,7 +44,6 @@ __device__ __forceinline__ void push_bin(const FrameParams &P, uint32_t tile, ui
     }
     base = __shfl_sync(peers, base, leader);
     const uint32_t slot = base + __popc(peers & lanemask_lt());
-    const uint2 tb = __ldg(reinterpret_cast<const uint2 *>(&P.tile_bin[tile])); // planned on the host before the frame
     if (slot < tb.y)
         P.bins[(size_t)tb.x + slot] = make_uint4(key, rec_tie, box, 0u);
     else
@@ -178,10 +179,10 @@ __device__ __forceinline__ void emit_setup(const FrameParams &P, const DrawParam
     float4 *rr = reinterpret_cast<float4 *>(&P.recs[rec]);
     rr[0] = make_float4(s.px[0], s.py[0], s.px[1], s.py[1]);
     rr[1] = make_float4(s.px[2], s.py[2], s.z[0], s.z[1]);
-    rr[2] = make_float4(s.z[2], inv, __uint_as_float(key), __uint_as_float(b.x0 | (b.y0 << 16)));
-    rr[3] = make_float4(s.w[0], s.w[1], s.w[2], __uint_as_float(b.x1 | (b.y1 << 16)));
-    *reinterpret_cast<uint4 *>(&P.shade[rec]) =
-        make_uint4((D.fs & 3u) | (ca ? 4u : 0u) | (((D.fs >> 8) & 31u) << 3) | (D.draw << 8), ca ? clip_attr : i0, i1, i2);
+    rr[2] = make_float4(s.z[2], inv, __uint_as_float(key), 0.0f);
+    uint4 *sr = reinterpret_cast<uint4 *>(&P.shade[rec]);
+    sr[0] = make_uint4((D.fs & 3u) | (ca ? 4u : 0u) | (((D.fs >> 8) & 31u) << 3) | (D.draw << 8), ca ? clip_attr : i0, i1, i2);
+    sr[1] = make_uint4(__float_as_uint(s.w[0]), __float_as_uint(s.w[1]), __float_as_uint(s.w[2]), 0u);
     const uint32_t rec_tie = rec | (tie_bits(s) << 29);
     const uint32_t wild_bit = tame ? 0u : ENTRY_WILD;
 
@@ -508,9 +509,9 @@ __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
         const LargeItem li = P.large[item];
         Setup s;
         load_points(P.recs, li.rec, s);
-        const uint32_t lo = P.recs[li.rec].bbox_lo, hi = P.recs[li.rec].bbox_hi;
-        BBox b; // the record's pixel box: bounded by the scissor and this ctx's row range already
-        b.x0 = lo & 0xFFFFu; b.y0 = lo >> 16; b.x1 = hi & 0xFFFFu; b.y1 = hi >> 16;
+        BBox b = pixel_bbox(s, P.scissor);
+        b.y0 = max(b.y0, P.row_begin);
+        b.y1 = min(b.y1, P.row_end);
         const uint32_t rec_tie = li.rec | (tie_bits(s) << 29);
         const uint32_t wild_bit = setup_is_tame(s) ? 0u : ENTRY_WILD;
         const uint32_t tx0 = b.x0 / TW, tx1 = (b.x1 - 1) / TW + 1, ntx = tx1 - tx0;
@@ -555,8 +556,9 @@ __global__ void __launch_bounds__(NT) order_kernel(FrameParams P) {
     uint32_t base = 0;
     if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&P.fs->bucket_n[b], (uint32_t)__popc(peers));
     base = __shfl_sync(peers, base, leader);
-    // the entry carries the list length too: the tile stage learns both with one load
-    P.busy[(size_t)b * P.tiles_x * P.tiles_y + base + __popc(peers & lanemask_lt())] = (unsigned long long)tile | ((unsigned long long)n << 32);
+    // the entry carries the list length and the tile's bin slice too: the tile stage learns all of it with one load
+    const uint2 tb = __ldg(reinterpret_cast<const uint2 *>(&P.tile_bin[tile]));
+    P.busy[(size_t)b * P.tiles_x * P.tiles_y + base + __popc(peers & lanemask_lt())] = make_uint4(tile, n, tb.x, tb.y);
 }
 
 // ---- completion flags over peer memory (screen-space sharding, one process per GPU) ----

@@ -141,7 +141,7 @@ __device__ __forceinline__ uint32_t shade(const FrameParams &P, const Setup &s, 
     const uint4 sh = *reinterpret_cast<const uint4 *>(&P.shade[rec]);
     const uint32_t info = sh.x, fs = info & 3u, texidx = EXT ? (info >> 3) & 31u : 0u;
     if (fs == 2u) return to_argb(depth0, depth0, depth0, 1.0f); // Color::grayscale(depths[0])
-    const float4 wq = reinterpret_cast<const float4 *>(&P.recs[rec])[3]; // depths_camera_space
+    const float4 wq = reinterpret_cast<const float4 *>(&P.shade[rec])[1]; // depths_camera_space (same sector)
     const bool clipped = (info & 4u) != 0u;
     const float *a0, *a1, *a2;
     if (clipped) { // interpolated attributes live in an AttrRec (written by clip_kernel in this frame)
@@ -169,7 +169,7 @@ __device__ __forceinline__ uint32_t shade(const FrameParams &P, const Setup &s, 
     const float u = clamp01(fdiv(fu, sum));
     const float v = clamp01(fdiv(fv, sum));
     const float w = clamp01(fsub(fsub(1.0f, u), v));
-#define RZ_LDA(p) (clipped ? *(p) : __ldg(p))
+#define RZ_LDA(p) (*(p)) // plain loads: the pointers may address AttrRecs written by clip_kernel in this frame
 #define RZ_INTERP(c) fadd(fadd(fmul(RZ_LDA(a0 + (c)), u), fmul(RZ_LDA(a1 + (c)), v)), fmul(RZ_LDA(a2 + (c)), w))
     if (fs == 1u) return to_argb(RZ_INTERP(0), RZ_INTERP(1), RZ_INTERP(2), RZ_INTERP(3));
     // (u, v) of a vertex sit at byte offset 24 * i + 16 of an array that starts on a 256-byte boundary (cudaMalloc;
@@ -244,6 +244,19 @@ static_assert(sizeof(BigSetup) == 80, "BigSetup must be 20 words");
 
 constexpr uint32_t FR_NONE = 0xFFFFu;
 
+// Asynchronous global -> shared copies (LDGSTS): no register staging, the issuing thread does not wait.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+#ifndef RZ_DEPTH_IN_A1
+#define RZ_DEPTH_IN_A1 0 // 1: covered units compute their sample depths inside phase A1 (no phase A2); measured slower:
+                         // only ~40 % of the lanes of a unit warp are covered, a fragment warp is full
+#endif
 #ifndef RZ_B_REG_MAXFRAG
 #define RZ_B_REG_MAXFRAG 640 // chunks with more fragments (> 2.5 per pixel: overdraw) replay their pixel lists by re-walking
 #endif
@@ -270,8 +283,9 @@ struct TileSmemT {
     uint32_t it_key[NT];                  // items of the current chunk: order key (the rank in the list once it is sorted)
     uint32_t it_rec[NT];                  // record index | tie-break bits << 29
     uint32_t it_okey[DBG ? NT : 1];       // the triangle's order key as the oracle reports it (parity instrumentation only)
-    uint32_t it_rcp[NT];                  // ceil(65536 / bw): j / bw == (j * rcp) >> 16 for j < 256, bw <= 16
-    uint32_t it_box[NT];                  // lx0 | ly0 << 8 | bw << 16
+    uint32_t it_box[NT];                  // lx0 | ly0 << 4 | bw << 8 | ceil(65536 / bw) << 13   (j / bw == (j * rcp) >> 16 for j < 256)
+    float4 it_q0[NT], it_q1[NT];          // the items' records, quarters 0 and 1 (screen points, z0, z1) and the first half of
+    float2 it_q2[NT];                     //   quarter 2 (z2, inv_2x_area): copied asynchronously (cp.async) while phase A0 scans
     uint32_t pre[NT + 1];                 // exclusive prefix of the in-tile box areas (work units)
     uint8_t unit_item[UNIT_CAP];          // work unit -> item
     union {
@@ -323,21 +337,32 @@ __device__ __forceinline__ bool sort_tile_list(SM &S, uint4 *bin, int n) {
 }
 
 // Stage the records of `cnt` chunk items in shared memory for a pixel-parallel walk (thread = item).  The staging
-// area aliases the fragment pool, which these walks do not use.
-template <typename SM>
+// area aliases the fragment pool, which these walks do not use.  FROM_TABLE: the item table of phase A0 already holds
+// the record (cp.async); otherwise it is read from global memory.
+template <bool FROM_TABLE, typename SM>
 __device__ __forceinline__ void stage_big(const FrameParams &P, SM &S, int cnt, uint32_t key, uint32_t rec_tie, int bx0, int by0,
                                           int bw, int bh) {
     if ((int)threadIdx.x < cnt) {
         BigSetup &b = S.u.big[threadIdx.x];
         const uint32_t rec = rec_tie & ENTRY_REC_MASK;
+        float4 r0, r1;
+        float2 r2;
+        if (FROM_TABLE) {
+            r0 = S.it_q0[threadIdx.x]; r1 = S.it_q1[threadIdx.x]; r2 = S.it_q2[threadIdx.x];
+        } else {
+            const float4 *rr = reinterpret_cast<const float4 *>(&P.recs[rec]);
+            r0 = rr[0]; r1 = rr[1];
+            const float4 q2 = rr[2];
+            r2 = make_float2(q2.x, q2.y);
+        }
         Setup s;
-        load_points(P.recs, rec, s);
-        const float4 r2 = reinterpret_cast<const float4 *>(&P.recs[rec])[2];
+        s.px[0] = r0.x; s.py[0] = r0.y; s.px[1] = r0.z; s.py[1] = r0.w; s.px[2] = r1.x; s.py[2] = r1.y;
+        setup_normals(s);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             b.px[k] = s.px[k]; b.py[k] = s.py[k]; b.nx[k] = s.nx[k]; b.ny[k] = s.ny[k];
         }
-        b.z[0] = s.z[0]; b.z[1] = s.z[1]; b.z[2] = r2.x;
+        b.z[0] = r1.z; b.z[1] = r1.w; b.z[2] = r2.x;
         b.inv = r2.y; b.key = key; b.rec = rec;
         b.box = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bw << 16) | ((uint32_t)bh << 24);
         b.tie = rec_tie >> 29;
@@ -514,7 +539,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
     const uint32_t n_busy = S.bucket_end[ORDER_BUCKETS - 1];
     const uint32_t work = S.cur_tile;
     if (work >= n_busy) break;
-    uint32_t tile;
+    uint32_t tile, bin_off;
     int n;
     {
         uint32_t b = 0, start = 0;
@@ -524,13 +549,13 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 b = k + 1;
                 start = S.bucket_end[k];
             }
-        // the entry carries the tile id and its list length (order_kernel): one load instead of two dependent ones
-        const unsigned long long e = __ldcg(P.busy + (size_t)b * P.tiles_x * P.tiles_y + (work - start));
-        tile = (uint32_t)e;
-        n = (int)(uint32_t)(e >> 32);
+        // the entry carries the tile id, its list length and its bin slice (order_kernel): one load instead of three
+        // dependent ones
+        const uint4 e = __ldcg(P.busy + (size_t)b * P.tiles_x * P.tiles_y + (work - start));
+        tile = e.x;
+        n = (int)min(e.y, e.w);
+        bin_off = e.z;
     }
-    const uint2 tbin = __ldg(reinterpret_cast<const uint2 *>(&P.tile_bin[tile])); // {first entry, capacity}
-    n = min(n, (int)tbin.y);
     const uint32_t tx = tile % P.tiles_x, ty = tile / P.tiles_x;
     const int tileX0 = tx * TW, tileY0 = ty * TH;
     const int X = tileX0 + lx, Y = tileY0 + ly;
@@ -549,7 +574,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
 
     if (n > 0) {
         S.head[tid] = FR_NONE;
-        uint4 *bin = P.bins + tbin.x;
+        uint4 *bin = P.bins + bin_off;
         bool sorted = false;  // the list is in submission order
         bool compact = false; // ... and in its compact form (sort_tile_list)
         if (n > CHUNK) {
@@ -607,7 +632,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 // ================= run of items for the literal walk: pixel-parallel =================
                 const int run = min(first_small, nvalid);
                 const BigSetup *B = S.u.big;
-                stage_big(P, S, run, key, rec_tie, bx0, by0, bw, bh);
+                stage_big<false>(P, S, run, key, rec_tie, bx0, by0, bw, bh);
                 __syncthreads();
                 float d[4];
                 uint32_t col[4], ok[4];
@@ -661,9 +686,14 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
             // ---- phase A0: item table + exclusive scan of the in-tile box areas ----
             const uint32_t area = (tid < cnt) ? (uint32_t)(bw * bh) : 0u;
             if (tid < cnt) {
+                // the record travels to shared memory on its own while the scan below runs (waited for at the barrier
+                // that ends phase A0)
+                const char *rp = reinterpret_cast<const char *>(&P.recs[rec_tie & ENTRY_REC_MASK]);
+                cp_async16(&S.it_q0[tid], rp);
+                cp_async16(&S.it_q1[tid], rp + 16);
+                cp_async8(&S.it_q2[tid], rp + 32);
                 S.it_key[tid] = key; S.it_rec[tid] = rec_tie;
-                S.it_rcp[tid] = (65536u + (uint32_t)bw - 1u) / (uint32_t)bw;
-                S.it_box[tid] = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bw << 16);
+                S.it_box[tid] = (uint32_t)bx0 | ((uint32_t)by0 << 4) | ((uint32_t)bw << 8) | (((65536u + (uint32_t)bw - 1u) / (uint32_t)bw) << 13);
             }
             uint32_t incl = area;
 #pragma unroll
@@ -677,25 +707,31 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 S.ovf = 0;
             }
             __syncthreads();
-            uint32_t wbase = 0;
+            uint32_t wbase = 0, total_units = 0;
 #pragma unroll
-            for (int k = 0; k < NT / 32; k++)
-                if (k < warp) wbase += S.scan[k];
-            {
-                const uint32_t first = wbase + incl - area; // exclusive prefix: first work unit of item <tid>
-                S.pre[tid] = first;
-                if (tid == NT - 1) S.pre[NT] = wbase + incl;
-                for (uint32_t k = 0; k < area && first + k < (uint32_t)UNIT_CAP; k++) S.unit_item[first + k] = (uint8_t)tid;
+            for (int k = 0; k < NT / 32; k++) {
+                const uint32_t v = S.scan[k];
+                if (k < warp) wbase += v;
+                total_units += v;
             }
-            __syncthreads();
             // ================= chunk dominated by large items: pixel-parallel, deferred shading =================
             // When the items of the chunk cover the tile broadly (average in-tile box >= DIRECT_MIN_AREA pixels) the
             // fragment machinery below only adds barriers: every thread keeps its pixel, walks the chunk's items in
             // submission order (exact coverage, sample depths, strict-< depth test: the literal sequence of
             // rasterizer/mod.rs:443-473), remembers per sample which item wrote it last together with that fragment's
-            // post-depth mask, and shades each surviving owner once at the end.  No fragment pool.
-            if (DIRECT && cnt > 0 && S.pre[cnt] >= (uint32_t)DIRECT_MIN_AREA * (uint32_t)cnt) {
-                stage_big(P, S, cnt, key, rec_tie, bx0, by0, bw, bh);
+            // post-depth mask, and shades each surviving owner once at the end.  No fragment pool, no unit table.
+            const bool go_direct = DIRECT && cnt > 0 && total_units >= (uint32_t)DIRECT_MIN_AREA * (uint32_t)cnt;
+            {
+                const uint32_t first = wbase + incl - area; // exclusive prefix: first work unit of item <tid>
+                S.pre[tid] = first;
+                if (tid == NT - 1) S.pre[NT] = wbase + incl;
+                if (!go_direct)
+                    for (uint32_t k = 0; k < area && first + k < (uint32_t)UNIT_CAP; k++) S.unit_item[first + k] = (uint8_t)tid;
+            }
+            cp_async_wait_all();
+            __syncthreads();
+            if (go_direct) {
+                stage_big<true>(P, S, cnt, key, rec_tie, bx0, by0, bw, bh);
                 const uint4 dc = direct_chunk<DBG, EXT>(P, S, cnt, sorted, X, Y); // (starts with a barrier)
                 c_cov += dc.x; c_shaded += dc.y; c_samples += dc.z; c_oob += dc.w;
                 pos += cnt;
@@ -733,21 +769,23 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 for (int u0 = 0; u0 < units; u0 += NT) {
                     const int u = u0 + tid;
                     uint32_t m = 0, p = 0, it = 0;
+#if RZ_DEPTH_IN_A1
                     float e1s[4], e2s[4]; // edge values 1 and 2 of the four samples (EdgeFunctions.coverage_evaluated)
                     float z0 = 0.0f, z1 = 0.0f;
-                    const float4 *rr = nullptr;
+#endif
                     if (u < units) {
                         it = S.unit_item[u];
                         const uint32_t box = S.it_box[it];
-                        const int ibw = (int)((box >> 16) & 0x1Fu);
+                        const int ibw = (int)((box >> 8) & 0x1Fu);
                         const int j = u - (int)S.pre[it];
-                        const int ry = (int)(((uint32_t)j * S.it_rcp[it]) >> 16), rx = j - ry * ibw; // j / ibw, j < 256, ibw <= 16
-                        const int lpx = (int)(box & 0xFFu) + rx, lpy = (int)((box >> 8) & 0xFFu) + ry;
+                        const int ry = (int)(((uint32_t)j * (box >> 13)) >> 16), rx = j - ry * ibw; // j / ibw, j < 256, ibw <= 16
+                        const int lpx = (int)(box & 0xFu) + rx, lpy = (int)((box >> 4) & 0xFu) + ry;
                         p = (uint32_t)(lpy * TW + lpx);
                         const uint32_t rec_t = S.it_rec[it];
-                        rr = reinterpret_cast<const float4 *>(&P.recs[rec_t & ENTRY_REC_MASK]);
-                        const float4 r0 = rr[0], r1 = rr[1]; // ~7 units share a record: L1 hits
+                        const float4 r0 = S.it_q0[it], r1 = S.it_q1[it];
+#if RZ_DEPTH_IN_A1
                         z0 = r1.z; z1 = r1.w;
+#endif
                         // EdgeFunctions normals (mod.rs:200-205) and the single-compare form of inside() (rz_exact.cuh)
                         const float n0x = -fsub(r0.w, r0.y), n0y = fsub(r0.z, r0.x);
                         const float n1x = -fsub(r1.y, r0.w), n1y = fsub(r1.x, r0.z);
@@ -763,7 +801,9 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                             const float e1 = fadd(fmul(n1x, fsub(xs, r0.z)), fmul(n1y, fsub(ys, r0.w)));
                             const float e2 = fadd(fmul(n2x, fsub(xs, r1.x)), fmul(n2y, fsub(ys, r1.y)));
                             m |= ((e0 >= t0) & (e1 >= t1) & (e2 >= t2)) ? (1u << i) : 0u;
+#if RZ_DEPTH_IN_A1
                             e1s[i] = e1; e2s[i] = e2;
+#endif
                         }
                     }
                     const uint32_t bal = __ballot_sync(0xffffffffu, m != 0u);
@@ -774,10 +814,11 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                         if (m) {
                             cov_try++;
                             if (slot < POOL) {
+#if RZ_DEPTH_IN_A1
                                 // RasterizerTriangle::fragment (mod.rs:225-253): the covered samples' depths from the edge
                                 // values of the coverage evaluation.  Vector::dot starts its sum at 0.0 (vector.rs:17-23),
                                 // which only turns a -0.0 edge value into +0.0: `+ 0.0f` restores exactly that.
-                                const float4 r2 = rr[2];
+                                const float2 r2 = S.it_q2[it];
                                 const float z2 = r2.x, inv = r2.y;
                                 float zz[4];
 #pragma unroll
@@ -789,6 +830,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                                     zz[i] = ((m >> i) & 1u) ? z : 0.0f;
                                 }
                                 S.u.fr.z[slot] = make_float4(zz[0], zz[1], zz[2], zz[3]);
+#endif
                                 S.u.fr.meta[slot] = it | (p << 8) | (m << 16);
                                 S.u.fr.next[slot] = (uint16_t)atomicExch(&S.head[p], slot);
                             } else {
@@ -835,9 +877,36 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 sorted = true;
                 continue;
             }
-            RZ_STAMP(1) // A1 done (coverage + sample depths)
-            RZ_STAMP(2)
+            RZ_STAMP(1) // A1 done
             const int nfrag = (int)S.nfrag;
+#if !RZ_DEPTH_IN_A1
+            // ---- phase A2: thread = fragment; the covered samples' depths (RasterizerTriangle::fragment, mod.rs:225-253),
+            // every lane busy (in phase A1 only ~40 % of the units are covered)
+            for (int f = tid; f < nfrag; f += NT) {
+                const uint32_t meta = S.u.fr.meta[f];
+                const uint32_t it = meta & 0xFFu, p = (meta >> 8) & 0xFFu, m = (meta >> 16) & 0xFu;
+                const float4 r0 = S.it_q0[it], r1 = S.it_q1[it];
+                const float2 r2 = S.it_q2[it];
+                const float n1x = -fsub(r1.y, r0.w), n1y = fsub(r1.x, r0.z);
+                const float n2x = -fsub(r0.y, r1.y), n2y = fsub(r0.x, r1.x);
+                const float fx = (float)(tileX0 + (int)(p % TW)), fy = (float)(tileY0 + (int)(p / TW));
+                float zz[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float xs = fadd(fx, rgss_x(i)), ys = fadd(fy, rgss_y(i));
+                    const float e1 = dot2z(n1x, n1y, fsub(xs, r0.z), fsub(ys, r0.w)); // eval_single (mod.rs:125-132)
+                    const float e2 = dot2z(n2x, n2y, fsub(xs, r1.x), fsub(ys, r1.y));
+                    const float b0 = clamp01(fmul(e1, r2.y));
+                    const float b1 = clamp01(fmul(e2, r2.y));
+                    const float b2 = clamp01(fsub(fsub(1.0f, b0), b1));
+                    const float z = fadd(fadd(fmul(b0, r1.z), fmul(b1, r1.w)), fmul(b2, r2.x));
+                    zz[i] = ((m >> i) & 1u) ? z : 0.0f;
+                }
+                S.u.fr.z[f] = make_float4(zz[0], zz[1], zz[2], zz[3]);
+            }
+            __syncthreads();
+#endif
+            RZ_STAMP(2) // sample depths done
             // ---- phase B: thread = pixel; replay this pixel's fragments in submission order ----
             // (depth test exactly as Rasterizer::depth_coverage + write_pixel, mod.rs:363-397); the last writer
             // of every sample is the fragment that stays visible.  A pixel holds 2-3 fragments on average.
@@ -960,7 +1029,11 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 const uint32_t it = meta & 0xFFu;
                 const uint32_t rec = S.it_rec[it] & ENTRY_REC_MASK;
                 Setup q;
-                load_points(P.recs, rec, q);
+                {
+                    const float4 r0 = S.it_q0[it], r1 = S.it_q1[it];
+                    q.px[0] = r0.x; q.py[0] = r0.y; q.px[1] = r0.z; q.py[1] = r0.w; q.px[2] = r1.x; q.py[2] = r1.y;
+                    setup_normals(q);
+                }
                 const float depth0 = S.u.fr.z[f].x;
                 const uint32_t argb = shade<DBG, EXT>(P, q, rec, S.lut, tileX0 + (int)(p % TW), tileY0 + (int)(p / TW),
                                             fin & 0xFu, depth0, c_oob);

@@ -74,28 +74,27 @@ struct FrameState {
     uint32_t bucket_n[ORDER_BUCKETS]; // non-empty tiles per list-length class (class 0 = longest lists)
 };
 
-// Raster record: RasterizerTriangle (rasterizer/mod.rs:178-222) as the tile stage needs it -- the three screen points,
-// depths, inv_2x_area, depths_camera_space, the submission-order key and the pixel bounding box.  Everything is computed
-// ONCE per triangle by the geometry stage (the tile stage used to redo setup + bbox per (triangle, tile)).
-// 64 B = 4 x float4; the tile stage loads the quarters it needs:
-//   q0 = p0x p0y p1x p1y      q1 = p2x p2y z0 z1      q2 = z2 inv key bbox_lo      q3 = w0 w1 w2 bbox_hi
-// bbox_lo = x0 | y0 << 16, bbox_hi = x1 | y1 << 16 (half-open pixel ranges, already bounded by the scissor; W, H <= 65535)
+// Raster record: RasterizerTriangle (rasterizer/mod.rs:178-222) as coverage and depth need it -- the three screen
+// points, the depths, inv_2x_area and the submission-order key.  Computed ONCE per triangle by the geometry stage (the
+// tile stage used to redo the setup per (triangle, tile)).  48 B = 3 x float4:
+//   q0 = p0x p0y p1x p1y      q1 = p2x p2y z0 z1      q2 = z2 inv key -
 struct __align__(16) RasterRec {
     float p0x, p0y, p1x, p1y;
     float p2x, p2y, z0, z1;
     float z2, inv;
     uint32_t key;   // submission order: 8 * (triangle number in frame) + fan index
-    uint32_t bbox_lo;
-    float w0, w1, w2;
-    uint32_t bbox_hi;
+    uint32_t pad;
 };
-static_assert(sizeof(RasterRec) == 64, "RasterRec is four 16-byte quarters");
+static_assert(sizeof(RasterRec) == 48, "RasterRec is three 16-byte quarters");
 
-// Shade record: the fragment shader id and where the three VertexAttributes live.  Unclipped triangles point at the
-// mesh's own attribute array through their vertex indices (nothing is copied); clipped ones at an AttrRec.  16 B.
+// Shade record: what only visible fragments need -- the fragment shader id, where the three VertexAttributes live and
+// depths_camera_space.  Unclipped triangles point at the mesh's own attribute array through their vertex indices
+// (nothing is copied); clipped ones at an AttrRec.  32 B = one sector.
 struct __align__(16) ShadeRec {
     uint32_t info;        // fs (2 bits) | clipped << 2 | texture index << 3 (5 bits) | draw << 8
     uint32_t i0, i1, i2;  // vertex indices into the draw's attribute array (unclipped); i0 = AttrRec index (clipped)
+    float w0, w1, w2;
+    uint32_t pad;
 };
 
 // Tile bin entry, 16 B, written by the geometry stage for every (triangle, tile) pair:
@@ -150,7 +149,7 @@ struct FrameParams {
     uint32_t rec_cap, large_cap;
     FrameState *fs;
     uint32_t *tile_count;        // [tiles_x * tiles_y]
-    unsigned long long *busy;    // [ORDER_BUCKETS][tiles_x * tiles_y] non-empty tiles per class: tile id | list length << 32
+    uint4 *busy;                 // [ORDER_BUCKETS][tiles_x * tiles_y] non-empty tiles per class: {tile id, list length, bin offset, bin capacity}
     uint4 *bins;                 // bin entries of all tiles (see TileBin); tile t owns [tile_bin[t].off, +cap)
     const TileBin *tile_bin;     // [tiles_x * tiles_y]
     RasterRec *recs;
