@@ -15,6 +15,9 @@ Prints ONE JSON line on rank 0 (contract in the task statement):
   e2e        same metric through the host-buffer API: H2D of the mesh + D2H of the image every step
   roofline   dominant kernel: algorithmic bytes / measured kernel time vs the measured HBM peak
   cpu_baseline  the CPU oracle (C port of the reference algorithm) timed on this host, 1 core
+  cpu_baseline_c1  the same for BASELINE configs[0] (the crate's default 1280x720 scene, the config named "on CPU")
+  tiles      (N > 1) BASELINE configs[3]: one 8192x8192 frame split into tile rows across the N GPUs, timed with the
+             NCCL gather and with NVLink peer stores, checked against the single-GPU frame
 """
 from __future__ import annotations
 
@@ -54,7 +57,7 @@ class ClockSampler:
     milliseconds (the timed region of the default run lasts tens of milliseconds); `nvidia-smi -lms` as fallback."""
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int, period_s: float = 0.004):
+    def __init__(self, index: int, period_s: float = 0.0005):
         self.index, self.period, self.rows, self.proc, self.thread, self.stop_flag = index, period_s, [], None, None, False
         self.mode = None
 
@@ -65,16 +68,23 @@ class ClockSampler:
                 "sw_thermal_slowdown": N.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": N.nvmlClocksEventReasonSwPowerCap}
         return [n for n, b in bits.items() if mask & b]
 
-    def _poll(self):
+    def sample_now(self):
+        """One NVML reading right now (called immediately before and after the timed block, so even a timed region of
+        a millisecond carries clock evidence)."""
+        if self.mode != "nvml":
+            return
         import pynvml as N
 
+        try:
+            sm = N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)
+            mask = N.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            self.rows.append((time.time(), float(sm), float(self.max_sm), self._reasons(mask)))
+        except Exception:
+            pass
+
+    def _poll(self):
         while not self.stop_flag:
-            try:
-                sm = N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)
-                mask = N.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                self.rows.append((time.time(), float(sm), float(self.max_sm), self._reasons(mask)))
-            except Exception:
-                pass
+            self.sample_now()
             time.sleep(self.period)
 
     def start(self):
@@ -131,6 +141,168 @@ class ClockSampler:
         reasons = sorted({n for r in rows for n in r[3]})
         return {"sm_mhz": statistics.median(r[1] for r in rows), "sm_max_mhz": max(r[2] for r in rows), "reasons": reasons,
                 "samples": len(rows), "source": self.mode}
+
+
+def bind_host_near_gpu(local: int, world: int):
+    """Pin this rank to host cores near its GPU (NVML's ideal CPU affinity = the GPU's NUMA node) before any pinned
+    buffer is allocated, so first-touch places the staging memory on that node.  When several ranks share one affinity
+    set (one NUMA node for all GPUs) the set is dealt out evenly among them.  Returns what was done (for the JSON line)."""
+    try:
+        import pynvml as N
+
+        N.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = int(vis.split(",")[local]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local
+        h = N.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = N.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        ideal = sorted(c for c in range(ncpu) if (words[c // 64] >> (c % 64)) & 1)
+        allowed = sorted(os.sched_getaffinity(0))
+        cpus = [c for c in ideal if c in allowed] or allowed
+        if world > 1 and len(cpus) >= world:  # ranks that share the set take disjoint slices of it
+            per = len(cpus) // world
+            cpus = cpus[local * per:(local + 1) * per]
+        os.sched_setaffinity(0, cpus)
+        numa = None
+        try:
+            bus = N.nvmlDeviceGetPciInfo(h).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            numa = int(open(f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node").read())
+        except Exception:
+            pass
+        return {"cpus": f"{cpus[0]}-{cpus[-1]}" if cpus else None, "n_cpus": len(cpus), "gpu_ideal_cpus": len(ideal), "gpu_numa_node": numa}
+    except Exception as e:  # no NVML / not permitted: run unbound
+        return {"error": str(e)[:80]}
+
+
+def tiles_subrecord(args, rank, world, local):
+    """BASELINE configs[3] inside the N-GPU run: ONE 8192x8192 frame of the 1M-triangle sphere, geometry replicated, every
+    rank rasterising its tile rows; timed (a) with contiguous row ranges + one NCCL all_gather of the strips and (b) with
+    interleaved bands of tile rows whose tile kernels store straight into rank 0's image over NVLink (CUDA IPC peer
+    memory, flag kernels; sharding.PeerFrame).  Rank 0 also renders the frame alone: that is the strong-scaling
+    baseline and the image the assembled frames must equal.  Per-frame CUDA events, L2 flushed between frames,
+    median over frames, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from rusterizer_b200 import scenes
+    from rusterizer_b200.render import Renderer
+    from rusterizer_b200.sharding import PeerFrame
+
+    W = H = 8192
+    scene = scenes.sphere_scene(args.n_phi, args.n_theta, width=W, height=H)
+    mesh = scene.draws[0].mesh
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    K, Wm = 12, 3
+
+    def make_renderer():
+        r = Renderer(W, H, device=local)
+        r.set_stream(stream.cuda_stream)
+        r.uniforms().bind_texture(0, scene.texture)
+        dm = r.upload(mesh)
+        blk = r.uniforms().write_block()
+        blk.projection, blk.world, blk.view = scene.projection, scene.draws[0].world, scene.view
+        return r, dm
+
+    def timed(frame, r):
+        for _ in range(Wm):
+            frame()
+        r.sync()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ev = []
+        for _ in range(K):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            frame()
+            b.record(stream)
+            ev.append((a, b))
+        r.sync()
+        torch.cuda.synchronize()
+        t = torch.tensor([statistics.median(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    class _Raw:  # zero-copy torch view of a device pointer owned by the library
+        def __init__(self, ptr):
+            self.__cuda_array_interface__ = {"shape": (H, W), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
+
+    solo_ms, want = None, None
+    if rank == 0:  # the whole frame on one GPU
+        r, dm = make_renderer()
+        r.render(dm, 0, 0)
+        r.framebuffer_device()
+        ts = []
+        for i in range(Wm + K):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            r.render(dm, 0, 0)
+            r.framebuffer_async()
+            b.record(stream)
+            r.sync()
+            ts.append(a.elapsed_time(b))
+        solo_ms = statistics.median(ts[Wm:])
+        r.render(dm, 0, 0)
+        want = torch.as_tensor(_Raw(r.framebuffer_device()), device="cuda").clone()
+        r.close()
+    dist.barrier()
+    th = 16
+    rows_per = ((H // th + world - 1) // world) * th
+    r0, r1 = min(H, rank * rows_per), min(H, (rank + 1) * rows_per)
+    out = {"workload": "BASELINE configs[3]: 8192x8192, 1M-triangle sphere, tile rows split over %d GPUs" % world,
+           "single_gpu_ms_per_frame": solo_ms, "root_ingest_bytes_per_frame": (world - 1) * W * H * 4 // world,
+           "nvlink_peak_gb_per_s_one_way": 900.0, "frames_timed": K, "l2": "flushed between frames (256 MiB memset, not timed)"}
+    for mode in ("nccl", "peer"):
+        r, dm = make_renderer()
+        pf = None
+        if mode == "nccl":
+            r.set_row_range(r0, r1)
+            strip = torch.empty((rows_per, W), dtype=torch.int32, device="cuda")
+            gather = torch.empty((world * rows_per, W), dtype=torch.int32, device="cuda")
+            last = [None]
+
+            def frame():
+                r.render(dm, 0, 0)
+                r.framebuffer_async(strip.data_ptr())
+                dist.all_gather_into_tensor(gather, strip)
+                last[0] = gather[:H]
+        else:
+            pf = PeerFrame(r, root=0, n_buffers=2, interleave_band=args.band)
+            last = [None]
+
+            def frame():
+                r.render(dm, 0, 0)
+                img = pf.finish_frame()
+                pf.release()
+                if img is not None:
+                    last[0] = torch.as_tensor(_Raw(img), device="cuda")
+        r.render(dm, 0, 0)
+        r.framebuffer_device()  # the synchronous call sizes the device buffers
+        ms = timed(frame, r)
+        frame()
+        r.sync()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ok = torch.tensor([1 if (rank != 0 or torch.equal(last[0], want)) else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        dist.barrier()
+        key = "nccl_gather" if mode == "nccl" else "peer_stores"
+        out[key] = {"ms_per_frame": ms, "assembled_frame_matches_single_gpu": bool(ok.item()),
+                    "rows": ("contiguous tile-row ranges" if mode == "nccl" else f"interleaved bands of {args.band} tile rows"),
+                    "strong_scaling_efficiency": (None if solo_ms is None else solo_ms / (world * ms)),
+                    "root_ingest_gb_per_s": (world - 1) * W * H * 4 / world / (ms / 1e3) / 1e9}
+        if pf is not None:
+            pf.close()
+        r.close()
+        del last
+    if solo_ms is not None:
+        for k in ("nccl_gather", "peer_stores"):
+            out[k]["speedup_vs_single_gpu"] = solo_ms / out[k]["ms_per_frame"]
+    return out
 
 
 def build_scene(args):
@@ -242,6 +414,9 @@ def main():
                          "(CUDA IPC peer memory + flag kernels); 'nccl' = local strips + one all_gather")
     ap.add_argument("--band", type=int, default=16,
                     help="tiles mode with --gather peer: tile rows per interleaved band (0 = contiguous row ranges)")
+    ap.add_argument("--min-timed-s", type=float, default=0.25, help="repeat the K-step block until this much device time is timed")
+    ap.add_argument("--max-blocks", type=int, default=400)
+    ap.add_argument("--no-tiles", action="store_true", help="N > 1: skip the configs[3] sub-record (8192x8192 tile-row split)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     args = ap.parse_args()
@@ -264,6 +439,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    host_binding = bind_host_near_gpu(local, world)  # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
@@ -397,7 +573,10 @@ def main():
         dist.barrier()
         torch.cuda.synchronize()
     launches0 = sum(x[0].launch_count() for x in lanes)
+    if rank == 0:
+        sampler.sample_now()
     t_wall0 = time.time()
+    blocks, block_ev = 1, []
     if tiles_mode:
         ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
         ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
@@ -408,21 +587,36 @@ def main():
             ev1[s].record(stream)
         r.sync()
     else:
+        # The K-step block is repeated back to back until >= args.min_timed_s of device time has been timed (a 20-step
+        # block lasts 2 ms: too short for clock sampling and for a stable number).  ONE event pair brackets all blocks
+        # (value = frames / that time); an event after every block gives the spread.  Every rank runs the same number
+        # of blocks: it is derived from the warm-up estimate of rank 0.
+        est = torch.tensor([max(frame_latency_ms or 0.1, 0.02) * 0.85 * K], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.broadcast(est, 0)
+        blocks = int(min(args.max_blocks, max(1, -(-args.min_timed_s * 1e3 // float(est.item())))))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for s in range(K):
-            rj, sj, bj, mj = lanes[s % L]
-            bj.view = views[Wm + s]
-            rj.render(mj[(s // L) % len(mj)], 0, 0)
-            rj.framebuffer_async()
-        for rj, sj, bj, mj in lanes[1:]:
-            done = torch.cuda.Event()
-            done.record(sj)
-            stream.wait_event(done)
-        e1.record(stream)
+        step = 0
+        for b in range(blocks):
+            for s in range(K):
+                rj, sj, bj, mj = lanes[step % L]
+                bj.view = views[Wm + s]
+                rj.render(mj[(step // L) % len(mj)], 0, 0)
+                rj.framebuffer_async()
+                step += 1
+            for rj, sj, bj, mj in lanes[1:]:
+                done = torch.cuda.Event()
+                done.record(sj)
+                stream.wait_event(done)
+            eb = e1 if b == blocks - 1 else torch.cuda.Event(enable_timing=True)
+            eb.record(stream)
+            block_ev.append(eb)
         for x in lanes:
             x[0].sync()
     torch.cuda.synchronize()
+    if rank == 0:
+        sampler.sample_now()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -440,8 +634,14 @@ def main():
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
     total_ms_max = float(tot.item())
-    frames_total = K * (1 if tiles_mode else n_gpus)
+    frames_total = K * blocks * (1 if tiles_mode else n_gpus)
     value = (scene.n_triangles * frames_total) / (total_ms_max / 1e3) / 1e6
+    block_ms = []
+    if block_ev:
+        prev = e0
+        for eb in block_ev:
+            block_ms.append(prev.elapsed_time(eb))
+            prev = eb
     samples = torch.tensor([cnt["n_samples_written"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(samples, op=dist.ReduceOp.SUM)
@@ -538,8 +738,58 @@ def main():
     if world > 1:
         dist.all_reduce(e2, op=dist.ReduceOp.MAX)
     e2e_value = scene.n_triangles * e2e_steps * (1 if tiles_mode else n_gpus) / float(e2.item()) / 1e6
+    # PCIe / host-memory ceiling of this leg: the same bytes per step (mesh H2D on one stream, image D2H on another,
+    # all ranks at once) with no kernels at all.  e2e ms / ceiling ms says how much of the e2e step is the copies.
+    dev_in = torch.empty(pos_h.numel() * 4 + att_h.numel() * 4 + idx_h.numel() * 4, dtype=torch.uint8, device="cuda")
+    dev_out = torch.empty((H, W), dtype=torch.int32, device="cuda")
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+    host_in = [pos_h.view(torch.uint8).reshape(-1), att_h.view(torch.uint8).reshape(-1), idx_h.view(torch.uint8).reshape(-1)]
+
+    def copies(nsteps):
+        for i in range(nsteps):
+            with torch.cuda.stream(s_up):
+                o = 0
+                for h in host_in:
+                    dev_in[o:o + h.numel()].copy_(h, non_blocking=True)
+                    o += h.numel()
+            with torch.cuda.stream(s_dn):
+                out_h[i % 2].copy_(dev_out, non_blocking=True)
+    copies(3)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    copies(e2e_steps)
+    torch.cuda.synchronize()
+    cp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(cp, op=dist.ReduceOp.MAX)
+    copy_ms = float(cp.item()) / e2e_steps * 1e3
+    del dev_in, dev_out
     h2d = mesh.vertices.nbytes + mesh.attributes.nbytes + mesh.indices.nbytes + 192
     d2h = W * H * 4
+
+    # ---- N > 1: BASELINE configs[3] (one 8192x8192 frame split into tile rows) as a sub-record of the same line ----
+    tiles_rec = None
+    if world > 1 and not tiles_mode and not args.no_tiles:
+        r.close()
+        done = threading.Event()
+
+        def bail():  # a hung collective must not cost the run its JSON line: give up on the sub-record
+            if not done.wait(240.0):
+                if rank == 0:
+                    print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": Wm,
+                                      "ms_per_step": total_ms_max / (K * blocks), "higher_is_better": True, "scaling": "weak",
+                                      "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, scene),
+                                      "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                                      "gpu_launches": int(launches), "tiles": {"error": "sub-record timed out after 240 s"}}), flush=True)
+                os._exit(0)
+        threading.Thread(target=bail, daemon=True).start()
+        try:
+            tiles_rec = tiles_subrecord(args, rank, world, local)
+        except Exception as e:  # recorded, never fatal for the headline line
+            tiles_rec = {"error": repr(e)[:300]}
+        done.set()
 
     if rank != 0:
         if world > 1:
@@ -555,7 +805,7 @@ def main():
     kt = {"geometry": stage_avg["geometry_ms"], "tile": stage_avg["tile_ms"]}
     dom = max(kt, key=kt.get)
     achieved = alg[dom] / (kt[dom] / 1e3) / 1e9
-    traffic, ncu_detail = None, None
+    traffic, ncu_detail, tj = None, None, None
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
         try:
@@ -564,14 +814,18 @@ def main():
             det = tj.get("_detail", {}).get("tile" if dom == "tile" else "geom", {})
             # the path is issue/latency bound, not HBM bound: quote the issue-slot utilisation ncu saw
             ncu_detail = {"issue_active_pct": det.get("issue_active_pct"), "warp_instructions": det.get("warp_inst"),
-                          "registers": det.get("regs"), "source": tj.get("_source")}
+                          "registers": det.get("regs"), "source": tj.get("_source"), "measured_in_run": False,
+                          "capture_commit": tj.get("_commit")}
         except Exception:
             traffic = None
     frame_alg = scene.algorithmic_bytes()
-    ms_per_step = total_ms_max / K
+    ms_per_step = total_ms_max / (K * blocks)
     roofline = {
         "bound": "hbm", "kernel": f"{dom}_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+        "frac": achieved / peak, "traffic": traffic,
+        "traffic_source": {"measured_in_run": False, "what": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel from one "
+                           "ncu --set full capture of the same command (profiles/traffic.json)", "capture_commit": (tj or {}).get("_commit")},
+        "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
         "algorithmic_bytes_per_launch": alg[dom], "kernel_ms": kt[dom],
         "kernel_ms_all": stage_avg, "kernel_share_of_frame": kt[dom] / max(stage_avg["total_ms"], 1e-9),
         "frame_algorithmic_bytes": frame_alg, "frame_frac": frame_alg / (ms_per_step / 1e3) / 1e9 / peak,
@@ -582,7 +836,7 @@ def main():
     }
     # secondary bound: algorithmic f32 operations of the reference algorithm (FMA is off:
     # 1 flop/lane/clock) from the work counters, against 148 SMs x 128 lanes x the max SM clock
-    cpf = {k: v / K for k, v in cnt.items()}
+    cpf = {k: v / (K * blocks) for k, v in cnt.items()}
     f_alg = (28 * scene.n_vertices + 40 * cpf["n_tris_in"] + 60 * cpf["n_tris_setup"] + 72 * cpf["n_bbox_px"]
              + 30 * cpf["n_samples_written"] + 180 * cpf["n_shaded_px"])
     sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
@@ -599,12 +853,29 @@ def main():
             issue_peak = 148 * 4 * sm_mhz * 1e6
             roofline["issue"] = {"warp_instructions_per_frame": winst, "achieved_ginst_per_s": winst / (ms_per_step / 1e3) / 1e9,
                                  "peak_ginst_per_s": issue_peak / 1e9, "frac": winst / (ms_per_step / 1e3) / issue_peak,
+                                 "measured_in_run": False,
                                  "source": "smsp__inst_executed.sum per kernel from profiles/traffic.json (ncu --set full, same workload)"}
     except Exception:
         pass
-    cb = None
+    cb, cb_c1 = None, None
     if not args.no_cpu_baseline and not tiles_mode and n_gpus == 1:  # rank 0 at N=1 only (bounded sample)
         cb = cpu_baseline(scene, budget_s=args.cpu_budget)
+        # BASELINE configs[0]: the crate's default scene (main.rs:93-105, 1280x720, cube + sphere, 268 triangles) -- the config
+        # BASELINE names "on CPU" -- next to the same frame on the GPU
+        c1 = scenes.default_scene(1.0)
+        cb_c1 = cpu_baseline(c1, budget_s=3.0)
+        r1 = Renderer(c1.width, c1.height, device=local)
+        r1.uniforms().bind_texture(0, c1.texture)
+        dms = [r1.upload(d.mesh) for d in c1.draws]
+        ts = []
+        for i in range(12):
+            scenes.render_scene(r1, c1, dms)
+            r1.framebuffer_device()
+            ts.append(r1.timings()["total_ms"])
+        r1.close()
+        cb_c1["gpu_ms_per_frame"] = statistics.median(ts[2:])
+        cb_c1["gpu_mtris_per_s"] = c1.n_triangles / cb_c1["gpu_ms_per_frame"] / 1e3
+        cb_c1["workload"] = "BASELINE configs[0]: default `cargo run --release` scene at elapsed = 1.0 (main.rs:93-105), 1280x720, 4xMSAA"
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": Wm,
@@ -617,13 +888,23 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(e2.item()) / e2e_steps * 1e3, "steps": e2e_steps,
                 "sync_call_latency_ms": e2e_sync_ms,
+                "copies_only_ms_per_step": copy_ms, "pcie_ceiling_frac": copy_ms / (float(e2.item()) / e2e_steps * 1e3),
+                "copies_only_gb_per_s_all_ranks": (h2d + d2h) * n_gpus / (copy_ms / 1e3) / 1e9,
+                "host_binding": host_binding,
                 "how": "rz_render_host (pinned host mesh, H2D on the upload stream) + rz_framebuffer_host_async (D2H of the "
                        "image on the download stream) every step; copies of neighbouring steps overlap the kernels, "
                        "wall clock over all steps incl. the final rz_sync"},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "tiles": tiles_rec,
         "cpu_baseline": cb,
-        "counters_per_frame": {k: v / K for k, v in cnt.items()},
+        "cpu_baseline_c1": cb_c1,
+        "counters_per_frame": cpf,
+        "timed": {"blocks_of_K_steps": blocks, "frames": K * blocks, "device_ms": total_ms_max,
+                  "block_ms_min_median_max": ([min(block_ms), statistics.median(block_ms), max(block_ms)] if block_ms else None),
+                  "how": "the K-step block repeated back to back until >= %.2f s are timed; one CUDA-event pair around all "
+                         "blocks (barrier + synchronize on both sides), max over ranks; block spread from an event after "
+                         "every block (frames of neighbouring blocks overlap, so single blocks are approximate)" % args.min_timed_s},
     }
     print(json.dumps(line), flush=True)
     if world > 1:
