@@ -37,8 +37,8 @@ extern "C" {
 #define RZ_E_TEXTURE -4   /* bind index != number of bound textures (assert! at uniform.rs:31),
                              or FS Texture used with no texture bound (index panic uniform.rs:36) */
 #define RZ_E_INDEX -5     /* a mesh index >= nv (slice-index panic at render.rs:83-87)            */
-#define RZ_E_CAPACITY -6  /* an async frame outgrew its device buffers; re-issue it through
-                             rz_framebuffer(), which grows them and retries                       */
+#define RZ_E_CAPACITY -6  /* async frames outgrew the device buffers; rz_sync has grown them and replayed
+                             the last one, earlier ones must be re-issued (see rz_sync)            */
 #define RZ_E_NOMEM -7     /* device or host allocation failed                                     */
 #define RZ_E_PEER -8      /* a peer GPU did not raise its completion flag within the timeout      */
 
@@ -145,8 +145,16 @@ int rz_framebuffer_async(rz_ctx *ctx, uint32_t *device_dst, const uint32_t **out
  * the arrays passed to rz_render_host must stay unchanged until that rz_sync(). */
 int rz_framebuffer_host_async(rz_ctx *ctx, uint32_t *out_host);
 
-/* Wait for all enqueued frames and report their sticky status (RZ_E_CAPACITY, RZ_E_INDEX ...). */
+/* Wait for all enqueued frames and report their sticky status (RZ_E_INDEX, RZ_E_PEER ...).  An async frame cannot know
+ * that it outgrew the device buffers (the cursors live on the device); rz_sync finds out, grows the buffers from the
+ * counts the device kept and REPLAYS the last async frame into its original destination, so after RZ_OK the latest
+ * image is complete.  Only when more than one async frame was issued since the previous rz_sync does it return
+ * RZ_E_CAPACITY: the last frame is complete, the ones before it may not be (re-issue them; the buffers are large
+ * enough now).  The work counters then include the overflowed attempt. */
 int rz_sync(rz_ctx *ctx);
+/* Drop the draws recorded since the last rz_framebuffer* without executing them (a rank of a screen-space split that owns
+ * no rows of this frame still receives the application's rz_render calls).  No reference counterpart. */
+int rz_discard_frame(rz_ctx *ctx);
 
 /* Screen-space sharding (multi-GPU tile ranges): this ctx rasterises and resolves only the pixel
  * rows [row_begin, row_end) (rounded outwards to tile rows by the caller via rz_tile_height()).

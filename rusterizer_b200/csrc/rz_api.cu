@@ -91,6 +91,18 @@ struct rz_ctx {
     uint32_t rec_cap = 0, large_cap = 0;
     bool debug = false;
     bool use_direct = true; // tile-kernel instantiation with the large-item path (see enqueue_frame)
+    // The last frame issued through an async entry point, kept so that rz_sync can grow the device buffers and replay it
+    // when it turns out to have overflowed them (an async call cannot know: the cursors live on the device).
+    struct AsyncFrame {
+        bool valid = false;
+        std::vector<DrawCmd> draws;
+        uint32_t *out_base = nullptr;
+        uint32_t *out_host = nullptr; // rz_framebuffer_host_async: destination of the D2H copy
+        int ring = 0;                 //   ... and the output buffer it ran in
+        size_t staging_used = 0;
+        int parity = 0;
+    } last_async;
+    uint32_t async_pending = 0;       // async frames issued since the last rz_sync / rz_framebuffer
 
     FrameState *h_state = nullptr; // pinned
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -361,20 +373,25 @@ int rz_bind_texture(rz_ctx *c, uint32_t index, const uint8_t *texels, uint32_t w
     if (index != c->textures.size())
         return fail(c, RZ_E_TEXTURE, "rz_bind_texture: index %u != number of bound textures %zu (uniform.rs:31)", index,
                     c->textures.size());
+    if (c->textures.size() >= RZ_MAX_TEXTURES)
+        return fail(c, RZ_E_TEXTURE, "rz_bind_texture: at most %d textures can be bound", RZ_MAX_TEXTURES);
     CU(c, cudaSetDevice(c->device));
+    if (!c->d_textab) CU(c, cudaMalloc(&c->d_textab, sizeof(TexInfo) * RZ_MAX_TEXTURES));
     Texture t;
     t.w = width; t.h = height; t.tw = texel_width;
     t.len = (size_t)width * height * texel_width;
     CU(c, cudaMalloc(&t.d_data, t.len));
-    if (c->textures.size() >= RZ_MAX_TEXTURES)
-        return fail(c, RZ_E_TEXTURE, "rz_bind_texture: at most %d textures can be bound", RZ_MAX_TEXTURES);
-    CU(c, cudaMemcpyAsync(t.d_data, texels, t.len, cudaMemcpyHostToDevice, c->stream));
     TexInfo ti;
     ti.data = t.d_data; ti.len = t.len; ti.w = t.w; ti.h = t.h; ti.tw = t.tw;
     ti.bound = 1u | ((t.tw == 4 && t.len < (1ull << 32)) ? 2u : 0u); // bit 1: RGBA8 with 32-bit byte offsets (rz_tile.cuh)
-    if (!c->d_textab) CU(c, cudaMalloc(&c->d_textab, sizeof(TexInfo) * RZ_MAX_TEXTURES));
-    CU(c, cudaMemcpyAsync(c->d_textab + c->textures.size(), &ti, sizeof ti, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
+    cudaError_t e = cudaMemcpyAsync(t.d_data, texels, t.len, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_textab + c->textures.size(), &ti, sizeof ti, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { // nothing was bound: give the texels back
+        cudaFree(t.d_data);
+        c->sticky = RZ_E_CUDA;
+        return fail(c, RZ_E_CUDA, "rz_bind_texture: %s", cudaGetErrorString(e));
+    }
     c->textures.push_back(t);
     return RZ_OK;
 }
@@ -636,6 +653,29 @@ static int map_err_flags(rz_ctx *c, uint32_t flags) {
     return RZ_OK;
 }
 
+// Grow the device buffers an overflowed frame asked for.  c->h_state holds the frame's final state: the cursors keep
+// counting past the capacities, so one look says how much is needed.
+static int grow_after_overflow(rz_ctx *c, uint32_t flags) {
+    cudaStream_t st = c->stream;
+    uint32_t want_rec = c->rec_cap, want_large = c->large_cap, want_attr = c->attr_cap;
+    if (flags & ERR_ATTR_OVF) want_attr = std::max<uint64_t>((uint64_t)c->h_state->n_clip_attr * 5 / 4 + 1024, (uint64_t)c->attr_cap * 2);
+    if (flags & ERR_REC_OVF) {
+        uint32_t mx = 0; // the fullest stripe decides
+        for (int i = 0; i < REC_STRIPES; i++) mx = std::max(mx, c->h_state->rec_cursor[i]);
+        want_rec = std::max<uint64_t>(((uint64_t)mx * 5 / 4 + 64) * REC_STRIPES, (uint64_t)c->rec_cap * 3 / 2);
+        want_rec = std::max<uint64_t>(want_rec, (uint64_t)c->h_state->n_clipq); // the clip queue shares the capacity
+    }
+    if (flags & ERR_LARGE_OVF) want_large = std::max<uint64_t>((uint64_t)c->h_state->n_large * 5 / 4 + 1024, (uint64_t)c->large_cap * 2);
+    if (flags & ERR_BIN_OVF) {
+        std::vector<uint32_t> counts((size_t)c->tiles_x * c->tiles_y);
+        CU(c, cudaMemcpyAsync(counts.data(), c->d_state + sizeof(FrameState), counts.size() * 4, cudaMemcpyDeviceToHost, st));
+        CU(c, cudaStreamSynchronize(st));
+        int rc = plan_bins(c, counts.data());
+        if (rc != RZ_OK) return rc;
+    }
+    return ensure_capacity(c, want_rec, want_large, want_attr);
+}
+
 int rz_framebuffer(rz_ctx *c, uint32_t *out_host, const uint32_t **out_device) {
     if (!c) return RZ_E_INVALID;
     if (c->sticky != RZ_OK) return c->sticky;
@@ -646,11 +686,14 @@ int rz_framebuffer(rz_ctx *c, uint32_t *out_host, const uint32_t **out_device) {
     CU(c, cudaMemcpyAsync(c->h_state, dfs, sizeof(FrameState), cudaMemcpyDeviceToHost, st));
     CU(c, cudaStreamSynchronize(st));
     if (c->h_state->err) {
+        // an error of an EARLIER async frame (nobody called rz_sync): report it, keep the draws recorded for the current
+        // frame -- the caller may simply call rz_framebuffer() again
         uint32_t flags = c->h_state->err;
         CU(c, cudaMemsetAsync(&dfs->err, 0, sizeof(uint32_t), st));
-        end_frame(c);
+        c->async_pending = 0;
         return map_err_flags(c, flags);
     }
+    c->async_pending = 0;
     CU(c, cudaMemcpyAsync(c->d_cnt_backup, dfs->counters, sizeof(unsigned long long) * 16 * CNT_STRIPES, cudaMemcpyDeviceToDevice, st));
     int rc = RZ_OK;
     for (int attempt = 0; attempt < 8; attempt++) {
@@ -668,22 +711,7 @@ int rz_framebuffer(rz_ctx *c, uint32_t *out_host, const uint32_t **out_device) {
         }
         // grow what overflowed (the cursors kept counting past the capacity) and replay the frame
         CU(c, cudaMemcpyAsync(dfs->counters, c->d_cnt_backup, sizeof(unsigned long long) * 16 * CNT_STRIPES, cudaMemcpyDeviceToDevice, st));
-        uint32_t want_rec = c->rec_cap, want_large = c->large_cap, want_attr = c->attr_cap;
-        if (flags & ERR_ATTR_OVF) want_attr = std::max<uint64_t>((uint64_t)c->h_state->n_clip_attr * 5 / 4 + 1024, (uint64_t)c->attr_cap * 2);
-        if (flags & ERR_REC_OVF) {
-            uint32_t mx = 0; // the fullest stripe decides (cursors keep counting past the capacity)
-            for (int i = 0; i < REC_STRIPES; i++) mx = std::max(mx, c->h_state->rec_cursor[i]);
-            want_rec = std::max<uint64_t>(((uint64_t)mx * 5 / 4 + 64) * REC_STRIPES, (uint64_t)c->rec_cap * 3 / 2);
-        }
-        if (flags & ERR_LARGE_OVF) want_large = std::max<uint64_t>((uint64_t)c->h_state->n_large * 5 / 4 + 1024, (uint64_t)c->large_cap * 2);
-        if (flags & ERR_BIN_OVF) {
-            std::vector<uint32_t> counts((size_t)c->tiles_x * c->tiles_y);
-            CU(c, cudaMemcpyAsync(counts.data(), c->d_state + sizeof(FrameState), counts.size() * 4, cudaMemcpyDeviceToHost, st));
-            CU(c, cudaStreamSynchronize(st));
-            rc = plan_bins(c, counts.data());
-            if (rc != RZ_OK) break;
-        }
-        rc = ensure_capacity(c, want_rec, want_large, want_attr);
+        rc = grow_after_overflow(c, flags);
         if (rc != RZ_OK) break;
         if (attempt == 7) rc = fail(c, RZ_E_CAPACITY, "frame still overflows after 8 growth attempts");
     }
@@ -702,6 +730,16 @@ int rz_framebuffer(rz_ctx *c, uint32_t *out_host, const uint32_t **out_device) {
     return RZ_OK;
 }
 
+// the frame just enqueued by an async entry point, for rz_sync's overflow replay
+static void remember_async(rz_ctx *c, uint32_t *out_base, uint32_t *out_host, int ring) {
+    auto &a = c->last_async;
+    a.valid = true;
+    a.draws = c->draws;
+    a.out_base = out_base; a.out_host = out_host; a.ring = ring;
+    a.staging_used = c->staging_used; a.parity = c->parity;
+    c->async_pending++;
+}
+
 int rz_framebuffer_async(rz_ctx *c, uint32_t *device_dst, const uint32_t **out_device) {
     if (!c) return RZ_E_INVALID;
     if (c->sticky != RZ_OK) return c->sticky;
@@ -710,9 +748,21 @@ int rz_framebuffer_async(rz_ctx *c, uint32_t *device_dst, const uint32_t **out_d
     // (with interleaved bands the row range is the whole frame, so device_dst is the full image)
     uint32_t *base = device_dst ? device_dst - (size_t)c->row_begin * c->W : c->d_out;
     int rc = enqueue_frame(c, base, false);
+    if (rc == RZ_OK) remember_async(c, base, nullptr, 0);
     end_frame(c);
     if (rc != RZ_OK) return rc;
     if (out_device) *out_device = device_dst ? device_dst : c->d_out;
+    return RZ_OK;
+}
+
+// D2H copy of the image rendered into output buffer `p`, on the download stream
+static int enqueue_download(rz_ctx *c, int p, uint32_t *out_host) {
+    CU(c, cudaEventRecord(c->ev_frame_done[p], c->stream));
+    CU(c, cudaStreamWaitEvent(c->down_stream, c->ev_frame_done[p], 0));
+    const size_t off = (size_t)c->row_begin * c->W, cnt = (size_t)(c->row_end - c->row_begin) * c->W;
+    CU(c, cudaMemcpyAsync(out_host + off, c->d_out_ring[p] + off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                          c->down_stream));
+    CU(c, cudaEventRecord(c->ev_d2h_done[p], c->down_stream));
     return RZ_OK;
 }
 
@@ -725,15 +775,18 @@ int rz_framebuffer_host_async(rz_ctx *c, uint32_t *out_host) {
     // the image rendered into this buffer two frames ago must have left for the host
     CU(c, cudaStreamWaitEvent(c->stream, c->ev_d2h_done[p], 0));
     int rc = enqueue_frame(c, c->d_out_ring[p], false);
+    if (rc == RZ_OK) remember_async(c, c->d_out_ring[p], out_host, p);
     end_frame(c);
     if (rc != RZ_OK) return rc;
-    CU(c, cudaEventRecord(c->ev_frame_done[p], c->stream));
-    CU(c, cudaStreamWaitEvent(c->down_stream, c->ev_frame_done[p], 0));
-    const size_t off = (size_t)c->row_begin * c->W, cnt = (size_t)(c->row_end - c->row_begin) * c->W;
-    CU(c, cudaMemcpyAsync(out_host + off, c->d_out_ring[p] + off, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                          c->down_stream));
-    CU(c, cudaEventRecord(c->ev_d2h_done[p], c->down_stream));
+    rc = enqueue_download(c, p, out_host);
+    if (rc != RZ_OK) return rc;
     c->out_parity ^= 1;
+    return RZ_OK;
+}
+
+int rz_discard_frame(rz_ctx *c) {
+    if (!c) return RZ_E_INVALID;
+    end_frame(c);
     return RZ_OK;
 }
 
@@ -746,14 +799,48 @@ int rz_sync(rz_ctx *c) {
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaStreamSynchronize(c->down_stream));
     c->use_direct = c->h_state->n_large > 0;
+    const uint32_t pending = c->async_pending;
+    c->async_pending = 0;
     if (c->h_state->peer_timeout) {
         CU(c, cudaMemsetAsync(&dfs->peer_timeout, 0, sizeof(uint32_t), c->stream));
         return fail(c, RZ_E_PEER, "rz_wait_flags: a peer did not signal within the timeout");
     }
     if (c->h_state->err) {
-        const uint32_t flags = c->h_state->err;
+        uint32_t flags = c->h_state->err;
         CU(c, cudaMemsetAsync(&dfs->err, 0, sizeof(uint32_t), c->stream));
-        return map_err_flags(c, flags);
+        if ((flags & ERR_INDEX) || !c->last_async.valid) return map_err_flags(c, flags);
+        // An async frame outgrew the device buffers.  Grow them from the counts the device kept and replay the LAST
+        // async frame (its draw list and destination were kept), so the caller's latest image is complete; frames
+        // issued before it since the previous rz_sync cannot be re-created and are reported.  The work counters include
+        // the overflowed attempt.
+        std::vector<DrawCmd> recorded;
+        recorded.swap(c->draws); // draws recorded after the frame stay recorded
+        const size_t staging_used = c->staging_used;
+        const int parity = c->parity;
+        int rc = RZ_OK;
+        for (int attempt = 0; attempt < 8 && flags; attempt++) {
+            rc = grow_after_overflow(c, flags);
+            if (rc != RZ_OK) break;
+            auto &a = c->last_async;
+            c->draws = a.draws;
+            c->staging_used = a.staging_used; c->parity = a.parity;
+            rc = enqueue_frame(c, a.out_base, false);
+            c->draws.clear();
+            if (rc == RZ_OK && a.out_host) rc = enqueue_download(c, a.ring, a.out_host);
+            if (rc != RZ_OK) break;
+            CU(c, cudaMemcpyAsync(c->h_state, dfs, sizeof(FrameState), cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+            CU(c, cudaStreamSynchronize(c->down_stream));
+            flags = c->h_state->err;
+            if (flags) CU(c, cudaMemsetAsync(&dfs->err, 0, sizeof(uint32_t), c->stream));
+        }
+        c->draws.swap(recorded);
+        c->staging_used = staging_used; c->parity = parity;
+        if (rc != RZ_OK) return rc;
+        if (flags) return map_err_flags(c, flags);
+        if (pending > 1)
+            return fail(c, RZ_E_CAPACITY, "an async frame outgrew the device buffers: the buffers were grown and the last frame was "
+                                          "replayed (its image is complete); the %u frame(s) issued before it may be incomplete", pending - 1);
     }
     return RZ_OK;
 }

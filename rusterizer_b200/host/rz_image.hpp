@@ -111,6 +111,8 @@ inline std::vector<uint8_t> inflate(const uint8_t *src, size_t n, size_t expect)
     static const uint16_t DBASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
     static const uint8_t DEXT[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
     static const uint8_t ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    // `expect` is a HARD cap on the output (the caller knows the image size from IHDR): a stream that inflates to more
+    // is rejected instead of growing without bound (zip bomb)
     std::vector<uint8_t> out;
     out.reserve(expect);
     BitReader br{src, n};
@@ -123,6 +125,7 @@ inline std::vector<uint8_t> inflate(const uint8_t *src, size_t n, size_t expect)
             const uint32_t len = src[br.pos] | (src[br.pos + 1] << 8), nlen = src[br.pos + 2] | (src[br.pos + 3] << 8);
             br.pos += 4;
             if ((len ^ 0xFFFFu) != nlen || br.pos + len > n) throw std::runtime_error("png: bad stored block");
+            if (out.size() + len > expect) throw std::runtime_error("png: image data longer than the header says");
             out.insert(out.end(), src + br.pos, src + br.pos + len);
             br.pos += len;
             continue;
@@ -172,6 +175,7 @@ inline std::vector<uint8_t> inflate(const uint8_t *src, size_t n, size_t expect)
         for (;;) {
             const int sym = lit.decode(br);
             if (sym < 256) {
+                if (out.size() >= expect) throw std::runtime_error("png: image data longer than the header says");
                 out.push_back((uint8_t)sym);
             } else if (sym == 256) {
                 break;
@@ -182,6 +186,7 @@ inline std::vector<uint8_t> inflate(const uint8_t *src, size_t n, size_t expect)
                 if (ds > 29) throw std::runtime_error("png: bad distance symbol");
                 const size_t d = DBASE[ds] + br.bits(DEXT[ds]);
                 if (d > out.size()) throw std::runtime_error("png: distance too far back");
+                if (out.size() + (size_t)len > expect) throw std::runtime_error("png: image data longer than the header says");
                 for (int k = 0; k < len; k++) out.push_back(out[out.size() - d]);
             }
         }
@@ -230,6 +235,9 @@ inline Image decode_png(const uint8_t *data, size_t size) {
         pos += 12 + (size_t)len;
     }
     if (W == 0 || H == 0 || ctype < 0) throw std::runtime_error("png: missing IHDR");
+    // dimensions are untrusted: bound them (the framebuffers and textures of this library are <= 65535 on a side), so
+    // that (stride + 1) * H below cannot wrap size_t and a header cannot ask for an absurd allocation
+    if (W > 65535u || H > 65535u) throw std::runtime_error("png: image larger than 65535 pixels on a side");
     int samples;
     switch (ctype) {
     case 0: samples = 1; break;

@@ -90,9 +90,17 @@ def decode_png(data: bytes) -> np.ndarray:
         raise ValueError("png: bad colour type")
     if not (depth == 8 or (depth == 16 and ctype != 3) or (depth in (1, 2, 4) and ctype in (0, 3))):
         raise ValueError("png: bad bit depth for the colour type")
+    if w == 0 or h == 0:
+        raise ValueError("png: missing IHDR")
+    if w > 65535 or h > 65535:  # untrusted header: bound the allocation (host/rz_image.hpp does the same)
+        raise ValueError("png: image larger than 65535 pixels on a side")
     bpp = (samples * depth + 7) // 8
     stride = (w * samples * depth + 7) // 8
-    raw = np.frombuffer(zlib.decompress(b"".join(idat)), np.uint8)
+    d = zlib.decompressobj()
+    blob = d.decompress(b"".join(idat), (stride + 1) * h)  # output capped at what the header announces (zip bomb)
+    if d.unconsumed_tail:
+        raise ValueError("png: image data longer than the header says")
+    raw = np.frombuffer(blob, np.uint8)
     if raw.size < (stride + 1) * h:
         raise ValueError("png: image data too short")
     raw = raw[: (stride + 1) * h].reshape(h, stride + 1)

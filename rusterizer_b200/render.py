@@ -34,7 +34,7 @@ COUNTER_FIELDS = (
 ABI_SYMBOLS = (
     "rz_create", "rz_destroy", "rz_set_stream", "rz_bind_texture", "rz_write_block", "rz_read_block",
     "rz_mesh_create", "rz_mesh_destroy", "rz_render", "rz_render_host", "rz_framebuffer",
-    "rz_framebuffer_async", "rz_framebuffer_host_async", "rz_sync", "rz_shared_alloc", "rz_shared_open",
+    "rz_framebuffer_async", "rz_framebuffer_host_async", "rz_sync", "rz_discard_frame", "rz_shared_alloc", "rz_shared_open",
     "rz_shared_close", "rz_shared_free", "rz_signal", "rz_wait_flags", "rz_set_row_range", "rz_set_row_interleave", "rz_set_scissor", "rz_tile_width", "rz_tile_height",
     "rz_counters", "rz_reset_counters", "rz_timings", "rz_launch_count", "rz_debug_capture",
     "rz_debug_read", "rz_debug_tile_times", "rz_debug_vertex_stage", "rz_last_error", "rz_version",
@@ -94,6 +94,7 @@ def load_library() -> C.CDLL:
     L.rz_framebuffer_async.argtypes = [vp, vp, C.POINTER(vp)]
     L.rz_framebuffer_host_async.argtypes = [vp, vp]
     L.rz_sync.argtypes = [vp]
+    L.rz_discard_frame.argtypes = [vp]
     L.rz_shared_alloc.argtypes = [vp, C.c_uint64, C.POINTER(vp), u8p]
     L.rz_shared_open.argtypes = [vp, u8p, C.POINTER(vp)]
     L.rz_shared_close.argtypes = [vp, vp]
@@ -289,6 +290,11 @@ class Renderer:
 
     def sync(self):
         self._check(self._L.rz_sync(self._ctx))
+        self._keepalive.clear()
+
+    def discard_frame(self):
+        """Drop the draws recorded for the current frame without executing them."""
+        self._check(self._L.rz_discard_frame(self._ctx))
         self._keepalive.clear()
 
     # ---- peer memory (screen-space sharding over NVLink, see include/rz.h) ----

@@ -115,6 +115,8 @@ class PeerFrame:
             r.wait_flags(self.ack, 1, FLAG_STRIDE, f - self.nbuf + 1, self.timeout_ms)  # image buffer is free again
         if self.rows[0] < self.rows[1]:
             r.framebuffer_async(img + self.rows[0] * r.width * 4)
+        else:
+            r.discard_frame()  # this rank owns no rows (more ranks than tile rows): drop the recorded draws
         self.frame += 1
         if self.rank != self.root:
             r.signal(self.flags + self.rank * FLAG_STRIDE, seq)

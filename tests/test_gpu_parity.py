@@ -328,6 +328,52 @@ def test_capacity_growth_dense_tile():
     check(s)
 
 
+def test_async_overflow_is_replayed_by_sync():
+    """An async frame issued FIRST on a fresh context (device buffers still at their initial size) overflows its tile
+    bins; it cannot know.  rz_sync grows the buffers from the device's own counts and replays the frame into the same
+    destination, so the image is complete -- here equal to the oracle's.  With several unsynchronised async frames
+    only the last one can be re-created: RZ_E_CAPACITY says so, and the next frame just works."""
+    import torch
+
+    from rusterizer_b200.render import Renderer, RzError
+
+    s = scenes.overdraw_scene(8, 8, width=64, height=64)
+    s.draws = [scenes.Draw(d.mesh, d.world, d.fs) for d in s.draws] * 100  # 400 draws, 51 200 triangles into 16 tiles
+    o = oracle_render(s)
+    r = Renderer(s.width, s.height)
+    r.uniforms().bind_texture(0, s.texture)
+    scenes.render_scene(r, s)
+    ptr = r.framebuffer_async()
+    r.sync()  # grows + replays, returns RZ_OK (one async frame pending)
+
+    class _Raw:
+        __cuda_array_interface__ = {"shape": (s.height, s.width), "typestr": "<i4", "data": (ptr, False), "version": 3}
+
+    got = torch.as_tensor(_Raw(), device="cuda").cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, o["fb"])
+    r.close()
+    # host-streaming form, two frames in flight on a fresh context: the last image is complete, the error names the rest
+    r = Renderer(s.width, s.height)
+    r.uniforms().bind_texture(0, s.texture)
+    outs = [torch.empty((s.height, s.width), dtype=torch.int32).pin_memory() for _ in range(2)]
+    for k in range(2):
+        scenes.render_scene(r, s)
+        r.framebuffer_host_async(outs[k].data_ptr())
+    with pytest.raises(RzError) as e:
+        r.sync()
+    assert e.value.code == -6
+    assert np.array_equal(outs[1].numpy().view(np.uint32), o["fb"])
+    scenes.render_scene(r, s)  # buffers are large enough now
+    r.framebuffer_host_async(outs[0].data_ptr())
+    r.sync()
+    assert np.array_equal(outs[0].numpy().view(np.uint32), o["fb"])
+    # discard: recorded draws are dropped, the next frame is just the clear colour
+    scenes.render_scene(r, s)
+    r.discard_frame()
+    assert (r.framebuffer() == 0xFF191919).all()
+    r.close()
+
+
 def test_cpp_host_demo_runs(tmp_path):
     """The C++ mirror of the crate API renders the Mode::Demo frame on the GPU (main.rs:93-105): texture loaded
     from a PNG file (Texture::from_png_file, texture.rs:26-45), image written as PNG instead of a window."""

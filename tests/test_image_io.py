@@ -174,3 +174,23 @@ def test_png_errors(image_tool, tmp_path):
     (tmp_path / "bad.png").write_bytes(bytes(bad_crc))
     r = subprocess.run([str(image_tool), "decode", str(tmp_path / "bad.png"), str(tmp_path / "o.raw")], capture_output=True, text=True)
     assert r.returncode == 1 and "png:" in r.stderr
+
+
+def _raw_png(w, h, idat_payload: bytes, depth=8, ctype=6) -> bytes:
+    def chunk(kind, body):
+        return struct.pack(">I", len(body)) + kind + body + struct.pack(">I", zlib.crc32(kind + body) & 0xFFFFFFFF)
+    return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0)) + chunk(b"IDAT", idat_payload)
+            + chunk(b"IEND", b""))
+
+
+def test_png_untrusted_header_and_zip_bomb(image_tool, tmp_path):
+    """A crafted file must be rejected, not trusted: IHDR dimensions whose scanline arithmetic would wrap size_t
+    (W = 2^30 RGBA16, H = 2^31) and image data that inflates far beyond what the header announces."""
+    huge = _raw_png(1 << 30, 1 << 31, zlib.compress(b"\0" * 64), depth=16)
+    bomb = _raw_png(4, 4, zlib.compress(b"\0" * (64 << 20), 9))  # 64 MiB of zeros behind a 4x4 header
+    for name, blob in (("huge", huge), ("bomb", bomb)):
+        with pytest.raises(ValueError):
+            image.decode_png(blob)
+        (tmp_path / f"{name}.png").write_bytes(blob)
+        r = subprocess.run([str(image_tool), "decode", str(tmp_path / f"{name}.png"), str(tmp_path / "o.raw")], capture_output=True, text=True)
+        assert r.returncode != 0 and "png:" in (r.stderr + r.stdout)
