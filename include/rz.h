@@ -185,6 +185,18 @@ int rz_wait_flags(rz_ctx *ctx, const uint32_t *flags, uint32_t n, uint32_t strid
  * frame, like the resolution).  Default: the whole viewport. */
 int rz_set_scissor(rz_ctx *ctx, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1);
 
+/* Runtime sample count, SURVEY.md section 8 f-4: the reference fixes N_MSAA_SAMPLES = 4 with the rotated-grid pattern
+ * (rasterizer/mod.rs:23,109-114); here 1, 2, 4 (default, the reference) or 8 samples per pixel can be selected between
+ * frames.  1 = the pixel centre, 2 and 8 = the D3D11 standard patterns.  Everything that depends on the count in the
+ * reference follows it: CoverageMask::all() (mod.rs:42-44), the shading position rule of Fragment::interpolate
+ * (mod.rs:70-83), box_filter_color (buffers.rs:111-125).  rz_debug_read then returns [height][width][samples]. */
+int rz_set_msaa(rz_ctx *ctx, uint32_t samples);
+/* Guard-band clipping, the extension the reference sketches at rasterizer/mod.rs:417-419: the four side clip planes move
+ * out to |x|, |y| <= factor * w (near / far stay), so triangles that leave the viewport but stay inside the band are
+ * rasterised unclipped -- their pixel boxes are bounded by the viewport / scissor as before (mod.rs:347-361).  Trivial
+ * rejection still uses the view frustum itself.  factor = 1 (default) is the reference's clipping bit for bit. */
+int rz_set_guard_band(rz_ctx *ctx, float factor);
+
 /* Interleaved screen-space sharding: this ctx owns the bands k of `band_tile_rows` tile rows with
  * k % world == rank (inside its row range, normally the whole frame), which balances a centred object
  * across the GPUs; only owned tiles are rasterised, resolved and written, so with rz_framebuffer_async

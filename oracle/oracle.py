@@ -75,6 +75,8 @@ class OracleLib:
         L.orc_bind_texture.argtypes = [C.c_void_p, C.c_uint32, u8p, C.c_uint32, C.c_uint32, C.c_uint32]
         L.orc_write_block.argtypes = [C.c_void_p, fp, fp, fp]
         L.orc_set_scissor.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.orc_set_msaa.argtypes = [C.c_void_p, C.c_uint32]
+        L.orc_set_guard_band.argtypes = [C.c_void_p, C.c_float]
         L.orc_render.argtypes = [C.c_void_p, fp, fp, C.c_uint32, u32p, C.c_uint64, C.c_uint32, C.c_uint32]
         L.orc_rasterize.argtypes = [C.c_void_p, fp, fp, C.c_uint64, C.c_uint32]
         L.orc_vertex_stage.argtypes = [C.c_void_p, fp, C.c_uint32, fp]
@@ -220,6 +222,7 @@ class OracleRenderer:
         self.width, self.height = width, height
         self.row0, self.row1 = (0, height) if rows is None else (int(rows[0]), min(int(rows[1]), height))
         self.ctx = self.L.lib.orc_create_rows(width, height, self.row0, self.row1)
+        self.ns = 4
         if not self.ctx:
             raise MemoryError("orc_create failed")
 
@@ -243,6 +246,16 @@ class OracleRenderer:
 
     def set_scissor(self, x0, y0, x1, y1):
         self.L.lib.orc_set_scissor(self.ctx, x0, y0, x1, y1)
+
+    def set_msaa(self, n: int):
+        """Samples per pixel (1, 2, 4, 8); the reference's N_MSAA_SAMPLES = 4 is the default."""
+        if self.L.lib.orc_set_msaa(self.ctx, n) != 0:
+            raise ValueError(f"orc_set_msaa({n})")
+        self.ns = n
+
+    def set_guard_band(self, g: float):
+        if self.L.lib.orc_set_guard_band(self.ctx, g) != 0:
+            raise ValueError(f"orc_set_guard_band({g})")
 
     def write_block(self, world=None, view=None, projection=None):
         arrs = [None if m is None else f32(m).reshape(16) for m in (world, view, projection)]
@@ -275,13 +288,13 @@ class OracleRenderer:
         return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype).reshape(rows, self.width, per_px).copy()
 
     def depth_samples(self):
-        return self._view(self.L.lib.orc_depth_samples(self.ctx), np.float32, 4)
+        return self._view(self.L.lib.orc_depth_samples(self.ctx), np.float32, self.ns)
 
     def color_samples(self):
-        return self._view(self.L.lib.orc_color_samples(self.ctx), np.uint32, 4)
+        return self._view(self.L.lib.orc_color_samples(self.ctx), np.uint32, self.ns)
 
     def owner_samples(self):
-        return self._view(self.L.lib.orc_owner_samples(self.ctx), np.uint32, 4)
+        return self._view(self.L.lib.orc_owner_samples(self.ctx), np.uint32, self.ns)
 
     def framebuffer(self):
         p = self.L.lib.orc_framebuffer(self.ctx)
@@ -319,6 +332,10 @@ def _band_worker(job):
     r.write_block(view=scene.view, projection=scene.projection)
     if getattr(scene, "scissor", None):
         r.set_scissor(*scene.scissor)
+    if getattr(scene, "msaa", 4) != 4:
+        r.set_msaa(scene.msaa)
+    if getattr(scene, "guard_band", 1.0) != 1.0:
+        r.set_guard_band(scene.guard_band)
     for d in scene.draws:
         r.write_block(world=d.world)
         r.render(d.mesh.vertices, d.mesh.attributes, d.mesh.indices, 0, d.fs)

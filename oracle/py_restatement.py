@@ -24,6 +24,14 @@ CLEAR_DEPTH = np.finfo(np.float32).max  # rasterizer/buffers.rs:6
 # rasterizer/mod.rs:109-114
 RGSS = [(F(5.0) / F(8.0), F(1.0) / F(8.0)), (F(7.0) / F(8.0), F(5.0) / F(8.0)),
         (F(3.0) / F(8.0), F(7.0) / F(8.0)), (F(1.0) / F(8.0), F(3.0) / F(8.0))]
+# runtime sample counts (extension; N_MSAA_SAMPLES is the constant 4 in the reference, mod.rs:23):
+# 1 = pixel centre, 2 and 8 = the D3D11 standard patterns in sixteenths of a pixel
+PATTERNS = {
+    1: [(F(0.5), F(0.5))],
+    2: [(F(0.75), F(0.75)), (F(0.25), F(0.25))],
+    4: RGSS,
+    8: [(F(k[0]) / F(16.0), F(k[1]) / F(16.0)) for k in ((9, 5), (7, 11), (13, 9), (5, 3), (3, 13), (1, 7), (11, 15), (15, 1))],
+}
 FS_TEXTURE, FS_COLOR, FS_DEBUG = 0, 1, 2  # enum FS, main.rs:23-27
 
 
@@ -114,13 +122,15 @@ class Texture:
         return out
 
 
-def _distance_measure(plane, p):
-    """clipping.rs:29-38; planes in CLIP_PLANES order LEFT, RIGHT, BOTTOM, TOP, NEAR, FAR (53-60)."""
+def _distance_measure(plane, p, guard=ONE):
+    """clipping.rs:29-38; planes in CLIP_PLANES order LEFT, RIGHT, BOTTOM, TOP, NEAR, FAR (53-60).  guard: the four side
+    planes sit at |x|, |y| <= guard * w (guard band, mod.rs:417-419; 1 = the reference)."""
     c = p[plane >> 1]
-    return p[3] - c if (plane & 1) else p[3] + c
+    w = guard * p[3] if plane < 4 else p[3]
+    return w - c if (plane & 1) else w + c
 
 
-def try_clip(verts, attrs):
+def try_clip(verts, attrs, guard=ONE):
     """clipping::try_clip, clipping.rs:62-195.  verts: 3 x [x, y, z, w], attrs: 3 x [r, g, b, a, u, v] (np.float32
     scalars).  Returns None (Outside), "inside", or a list of (verts, attrs) fan triangles."""
     v10 = (verts[1][0] - verts[0][0], verts[1][1] - verts[0][1])
@@ -132,8 +142,9 @@ def try_clip(verts, attrs):
     outside = [[True, True] for _ in range(3)]
     for v in verts:
         for a in range(3):
-            inside[a][0] &= bool(v[a] >= -v[3])
-            inside[a][1] &= bool(v[a] <= v[3])
+            gw = guard * v[3] if a < 2 else v[3]  # "inside" against the guard band, "outside" against the frustum
+            inside[a][0] &= bool(v[a] >= -gw)
+            inside[a][1] &= bool(v[a] <= gw)
             outside[a][0] &= bool(v[a] < -v[3])
             outside[a][1] &= bool(v[a] > v[3])
     if any(any(x) for x in outside):
@@ -148,7 +159,7 @@ def try_clip(verts, attrs):
         for i in range(n):
             pv, pa = in_v[(i + n - 1) % n], in_a[(i + n - 1) % n]
             cv, ca = in_v[i], in_a[i]
-            pd, cd = _distance_measure(plane, pv), _distance_measure(plane, cv)
+            pd, cd = _distance_measure(plane, pv, guard), _distance_measure(plane, cv, guard)
             pin, cin = bool(pd >= ZERO), bool(cd >= ZERO)
             if pin != cin:
                 alpha = pd / (pd - cd)  # compute_intersection, clipping.rs:43-51
@@ -165,10 +176,11 @@ def try_clip(verts, attrs):
 class PyRasterizer:
     """Renderer + Rasterizer of the reference (render.rs:38-114, rasterizer/mod.rs:264-522) for the cross-check."""
 
-    def __init__(self, width, height):
+    def __init__(self, width, height, msaa=4, guard_band=1.0):
         self.W, self.H = int(width), int(height)
-        self.depth = np.full((self.H, self.W, 4), CLEAR_DEPTH, np.float32)  # DepthBuffer, buffers.rs:129-157
-        self.color = np.full((self.H, self.W, 4), CLEAR_COLOR, np.uint32)   # ColorBuffer, buffers.rs:83-109
+        self.ns, self.pat, self.guard = int(msaa), PATTERNS[int(msaa)], F(guard_band)
+        self.depth = np.full((self.H, self.W, self.ns), CLEAR_DEPTH, np.float32)  # DepthBuffer, buffers.rs:129-157
+        self.color = np.full((self.H, self.W, self.ns), CLEAR_COLOR, np.uint32)   # ColorBuffer, buffers.rs:83-109
         self.textures = []
         self.world = self.view = self.projection = np.eye(4, dtype=np.float32)
 
@@ -193,7 +205,7 @@ class PyRasterizer:
             for tri in idx:  # primitive_assembly, render.rs:75-96; Rasterizer::rasterize, mod.rs:399-476
                 verts = [[F(clip[i, k]) for k in range(4)] for i in tri]
                 attrs = [[F(att[i, k]) for k in range(6)] for i in tri]
-                res = try_clip(verts, attrs)
+                res = try_clip(verts, attrs, self.guard)
                 if res is None:
                     continue
                 for v, a in ([(verts, attrs)] if res == "inside" else res):
@@ -233,8 +245,9 @@ class PyRasterizer:
         tie = [bool(n[k][0] > ZERO) or (not bool(n[k][0] < ZERO) and bool(n[k][1] < ZERO)) for k in range(3)]
         shape = (y1 - y0, x1 - x0)
         cov, sampled = [], []
-        for i in range(4):  # EdgeFunctions::eval + inside, mod.rs:134-170; RasterizerTriangle::fragment, 225-253
-            ef = eval_single(Xp + RGSS[i][0], Yp + RGSS[i][1])
+        NS, PAT = self.ns, self.pat
+        for i in range(NS):  # EdgeFunctions::eval + inside, mod.rs:134-170; RasterizerTriangle::fragment, 225-253
+            ef = eval_single(Xp + PAT[i][0], Yp + PAT[i][1])
             ins = np.ones(shape, bool)
             for k in range(3):
                 ins &= (ef[k] > ZERO) | (~(ef[k] < ZERO) & ~(ef[k] > ZERO) & tie[k])
@@ -246,19 +259,19 @@ class PyRasterizer:
             sampled.append(np.where(ins, z, ZERO).astype(np.float32))
         dview = self.depth[y0:y1, x0:x1]
         cview = self.color[y0:y1, x0:x1]
-        dcov = [cov[i] & (sampled[i] < dview[..., i]) for i in range(4)]  # depth_coverage, mod.rs:363-378 (strict <)
-        shade = dcov[0] | dcov[1] | dcov[2] | dcov[3]
+        dcov = [cov[i] & (sampled[i] < dview[..., i]) for i in range(NS)]  # depth_coverage, mod.rs:363-378 (strict <)
+        shade = np.logical_or.reduce(dcov)
         if not shade.any():
             return
-        # Fragment::interpolate, mod.rs:69-100: pixel centre if all four samples passed, else the first passing sample
-        allc = dcov[0] & dcov[1] & dcov[2] & dcov[3]
+        # Fragment::interpolate, mod.rs:69-100: pixel centre if all samples passed, else the first passing sample
+        allc = np.logical_and.reduce(dcov)
         xs = np.broadcast_to(Xp + HALF, shape).copy()
         ys = np.broadcast_to(Yp + HALF, shape).copy()
         taken = allc.copy()
-        for i in range(4):
+        for i in range(NS):
             sel = dcov[i] & ~taken
-            xs = np.where(sel, Xp + RGSS[i][0], xs)
-            ys = np.where(sel, Yp + RGSS[i][1], ys)
+            xs = np.where(sel, Xp + PAT[i][0], xs)
+            ys = np.where(sel, Yp + PAT[i][1], ys)
             taken |= sel
         ef = eval_single(xs.astype(np.float32), ys.astype(np.float32))
         fu, fv, fw = ef[1] / wcam[0], ef[2] / wcam[1], ef[0] / wcam[2]
@@ -276,7 +289,7 @@ class PyRasterizer:
         else:
             col = [sampled[0], sampled[0], sampled[0], np.full(shape, ONE, np.float32)]  # grayscale(frag_coords.depths[0])
         argb = to_argb(col[0], col[1], col[2], col[3])
-        for i in range(4):  # write_pixel, mod.rs:380-397
+        for i in range(NS):  # write_pixel, mod.rs:380-397
             cview[..., i] = np.where(dcov[i], argb, cview[..., i])
             dview[..., i] = np.where(dcov[i], sampled[i], dview[..., i])
 
@@ -287,7 +300,8 @@ class PyRasterizer:
         r = ((c & np.uint32(0x00FF0000)) >> np.uint32(16)).sum(-1, dtype=np.uint32)
         g = ((c & np.uint32(0x0000FF00)) >> np.uint32(8)).sum(-1, dtype=np.uint32)
         b = (c & np.uint32(0x000000FF)).sum(-1, dtype=np.uint32)
-        out = (np.uint32(0xFF) << np.uint32(24)) | ((r // np.uint32(4)) << np.uint32(16)) | ((g // np.uint32(4)) << np.uint32(8)) | (b // np.uint32(4))
+        n = np.uint32(self.ns)
+        out = (np.uint32(0xFF) << np.uint32(24)) | ((r // n) << np.uint32(16)) | ((g // n) << np.uint32(8)) | (b // n)
         self.depth[...] = CLEAR_DEPTH
         self.color[...] = CLEAR_COLOR
         return out.astype(np.uint32)

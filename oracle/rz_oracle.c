@@ -25,7 +25,8 @@
 #include <stdlib.h>
 #include <string.h>
 
-#define N_MSAA 4                       /* rasterizer/mod.rs:23 */
+#define N_MSAA 4                       /* rasterizer/mod.rs:23 : the reference's (only) sample count */
+#define MAX_MSAA 8                     /* runtime sample counts 1 / 2 / 4 / 8 (extension) */
 #define CLEAR_COLOR 0xFF191919u        /* rasterizer/buffers.rs:5 */
 #define CLEAR_DEPTH 3.40282347e+38f    /* f32::MAX, rasterizer/buffers.rs:6 */
 #define TILE_SIZE 64u                  /* rasterizer/buffers.rs:8 */
@@ -40,6 +41,15 @@ static const float RGSS[N_MSAA][2] = {
     {3.0f / 8.0f, 7.0f / 8.0f},
     {1.0f / 8.0f, 3.0f / 8.0f},
 };
+
+/* Sample patterns for the runtime sample counts the reference does not define (N_MSAA_SAMPLES is a constant there,
+ * mod.rs:23,109-114): 1 = the pixel centre, 2 and 8 = the standard patterns of the D3D11 specification (in sixteenths
+ * of a pixel, exactly representable).  4 stays the reference's rotated grid. */
+static const float PAT1[1][2] = {{0.5f, 0.5f}};
+static const float PAT2[2][2] = {{0.75f, 0.75f}, {0.25f, 0.25f}};
+static const float PAT8[8][2] = {{0.5625f, 0.3125f}, {0.4375f, 0.6875f}, {0.8125f, 0.5625f}, {0.3125f, 0.1875f},
+                                 {0.1875f, 0.8125f}, {0.0625f, 0.4375f}, {0.6875f, 0.9375f}, {0.9375f, 0.0625f}};
+static const float (*pattern_of(int ns))[2] { return ns == 1 ? PAT1 : ns == 2 ? PAT2 : ns == 8 ? PAT8 : RGSS; }
 
 typedef struct {
     float v[6]; /* r g b a u v : graphics_primitives.rs:10-13, color.rs:7-12 */
@@ -64,12 +74,14 @@ typedef struct {
 
 typedef struct orc_ctx {
     uint32_t width, height;
+    int ns;          /* samples per pixel: N_MSAA_SAMPLES (mod.rs:23) made a runtime value; default 4 */
+    float guard;     /* guard band factor g >= 1 (mod.rs:417-419): x / y clip planes at |x| <= g*w; default 1 = the reference */
     uint32_t row0, row1; /* oracle-only row window [row0,row1): the sample buffers hold just these rows, so a large frame can
                             be checked band by band (one process per band); default = the whole frame */
     uint32_t sc_x0, sc_y0, sc_x1, sc_y1; /* scissor rect (extension suggested at mod.rs:349-350); default = viewport */
-    uint32_t *color;   /* [w*h][4]  buffers.rs:83-105 */
-    float *depth;      /* [w*h][4]  buffers.rs:129-147 */
-    uint32_t *owner;   /* [w*h][4]  oracle-only: order key of the last writer */
+    uint32_t *color;   /* [w*h][ns]  buffers.rs:83-105 */
+    float *depth;      /* [w*h][ns]  buffers.rs:129-147 */
+    uint32_t *owner;   /* [w*h][ns]  oracle-only: order key of the last writer */
     uint32_t *resolve; /* [w*h] */
     /* BufferTiles, buffers.rs:11-79 */
     uint32_t n_horizontal, n_vertical;
@@ -160,26 +172,28 @@ uint32_t orc_to_argb(const float *rgba) {
            (f32_as_u32(rgba[1] * 255.0f) << 8) | f32_as_u32(rgba[2] * 255.0f);
 }
 
-/* rasterizer/buffers.rs:111-125 */
-uint32_t orc_box_filter_color(const uint32_t *c) {
+/* rasterizer/buffers.rs:111-125 with N_MSAA_SAMPLES = ns */
+static uint32_t box_filter_n(const uint32_t *c, int ns) {
     uint32_t r = 0, g = 0, b = 0;
-    for (int i = 0; i < N_MSAA; i++) {
+    for (int i = 0; i < ns; i++) {
         r += (c[i] & 0x00FF0000u) >> 16;
         g += (c[i] & 0x0000FF00u) >> 8;
         b += c[i] & 0x000000FFu;
     }
-    return (0xFFu << 24) | ((r / N_MSAA) << 16) | ((g / N_MSAA) << 8) | (b / N_MSAA);
+    return (0xFFu << 24) | ((r / (uint32_t)ns) << 16) | ((g / (uint32_t)ns) << 8) | (b / (uint32_t)ns);
 }
+uint32_t orc_box_filter_color(const uint32_t *c) { return box_filter_n(c, N_MSAA); }
 
 /* ---------------- clipping ---------------- */
 
-/* rasterizer/clipping.rs:29-38 */
-static float distance_measure(int plane, const float *p) {
+/* rasterizer/clipping.rs:29-38.  Guard band (extension sketched at mod.rs:417-419): the four side planes move out to
+ * |x|, |y| <= g*w; g*w is one f32 product, and 1.0f * w == w, so g = 1 is the reference bit for bit. */
+static float distance_measure(int plane, const float *p, float guard) {
     switch (plane) {
-    case 0: return p[3] + p[0]; /* LEFT   */
-    case 1: return p[3] - p[0]; /* RIGHT  */
-    case 2: return p[3] + p[1]; /* BOTTOM */
-    case 3: return p[3] - p[1]; /* TOP    */
+    case 0: return guard * p[3] + p[0]; /* LEFT   */
+    case 1: return guard * p[3] - p[0]; /* RIGHT  */
+    case 2: return guard * p[3] + p[1]; /* BOTTOM */
+    case 3: return guard * p[3] - p[1]; /* TOP    */
     case 4: return p[3] + p[2]; /* NEAR   */
     default: return p[3] - p[2]; /* FAR   */
     }
@@ -198,7 +212,7 @@ static float compute_intersection(const float *p0, float d0, const float *p1, fl
  * Returns: -1 = Outside, 0 = Inside, n>0 = Clipped into n triangles written to out[].
  * *overflow is set when the polygon outgrew ORC_MAX_POLY (never expected).
  */
-static int try_clip(const tri_t *t, tri_t *out, int out_cap, int *overflow) {
+static int try_clip(const tri_t *t, tri_t *out, int out_cap, int *overflow, float guard) {
     if (fabsf(area2(t->p[0][0], t->p[0][1], t->p[1][0], t->p[1][1], t->p[2][0], t->p[2][1])) < CULL_EPS)
         return -1;
 
@@ -208,8 +222,11 @@ static int try_clip(const tri_t *t, tri_t *out, int out_cap, int *overflow) {
         const float *v = t->p[i];
         float w = v[3], nw = -v[3];
         for (int ax = 0; ax < 3; ax++) {
-            inside[ax][0] &= v[ax] >= nw;
-            inside[ax][1] &= v[ax] <= w;
+            /* guard band: "inside" (no clipping needed) is judged against the widened side planes, "outside" (nothing
+             * can be visible) still against the view frustum itself; z is never widened */
+            float gw = ax < 2 ? guard * w : w, ngw = -gw;
+            inside[ax][0] &= v[ax] >= ngw;
+            inside[ax][1] &= v[ax] <= gw;
             outside[ax][0] &= v[ax] < nw;
             outside[ax][1] &= v[ax] > w;
         }
@@ -238,8 +255,8 @@ static int try_clip(const tri_t *t, tri_t *out, int out_cap, int *overflow) {
         for (int i = 0; i < n_in; i++) {
             int prev_i = (i + n_in - 1) % n_in;
             const float *pv = iv[prev_i], *cv = iv[i];
-            float pd = distance_measure(plane, pv);
-            float cd = distance_measure(plane, cv);
+            float pd = distance_measure(plane, pv, guard);
+            float cd = distance_measure(plane, cv, guard);
             int pin = pd >= 0.0f, cin = cd >= 0.0f;
             if (n_out + 2 > ORC_MAX_POLY) {
                 *overflow = 1;
@@ -283,7 +300,7 @@ int orc_try_clip(const float *pos, const float *attrs, float *out_pos, float *ou
     memcpy(t.p, pos, sizeof t.p);
     memcpy(t.a, attrs, sizeof t.a);
     int ovf = 0;
-    int n = try_clip(&t, out, cap < ORC_MAX_POLY ? cap : ORC_MAX_POLY, &ovf);
+    int n = try_clip(&t, out, cap < ORC_MAX_POLY ? cap : ORC_MAX_POLY, &ovf, 1.0f);
     for (int i = 0; i < n; i++) {
         memcpy(out_pos + i * 12, out[i].p, sizeof out[i].p);
         memcpy(out_attrs + i * 18, out[i].a, sizeof out[i].a);
@@ -296,8 +313,10 @@ int orc_try_clip(const float *pos, const float *attrs, float *out_pos, float *ou
 typedef struct {
     float px[3], py[3];      /* EdgeFunctions.points   mod.rs:118 */
     float nx[3], ny[3];      /* EdgeFunctions.normals  mod.rs:119 */
-    float cov_eval[N_MSAA][3];
+    float cov_eval[MAX_MSAA][3];
     uint8_t cov_mask;
+    int ns;                  /* N_MSAA_SAMPLES */
+    const float (*pat)[2];   /* sample pattern (RGSS_SAMPLE_PATTERN for ns = 4) */
     float w[3];              /* depths_camera_space */
     float z[3];              /* depths */
     attr_t a[3];
@@ -342,6 +361,8 @@ static void viewport_setup(uint32_t width, uint32_t height, const float *ndc12, 
     }
     memset(r->cov_eval, 0, sizeof r->cov_eval);
     r->cov_mask = 0;
+    r->ns = N_MSAA;
+    r->pat = RGSS;
 }
 
 /* rasterizer/mod.rs:125-132 */
@@ -364,9 +385,9 @@ static int inside(const rtri_t *r, const float *e) {
 
 /* rasterizer/mod.rs:134-146 */
 static void eval_cov(rtri_t *r, uint64_t x, uint64_t y) {
-    for (int i = 0; i < N_MSAA; i++) {
-        float xs = (float)x + RGSS[i][0];
-        float ys = (float)y + RGSS[i][1];
+    for (int i = 0; i < r->ns; i++) {
+        float xs = (float)x + r->pat[i][0];
+        float ys = (float)y + r->pat[i][1];
         eval_single(r, xs, ys, r->cov_eval[i]);
         int v = inside(r, r->cov_eval[i]);
         r->cov_mask = (uint8_t)((r->cov_mask & ~(1u << i)) | ((unsigned)v << i));
@@ -375,7 +396,7 @@ static void eval_cov(rtri_t *r, uint64_t x, uint64_t y) {
 
 /* rasterizer/mod.rs:225-253 */
 static void fragment_depths(const rtri_t *r, float *sampled) {
-    for (int i = 0; i < N_MSAA; i++) {
+    for (int i = 0; i < r->ns; i++) {
         sampled[i] = 0.0f;
         if ((r->cov_mask >> i) & 1) {
             const float *e = r->cov_eval[i];
@@ -390,11 +411,11 @@ static void fragment_depths(const rtri_t *r, float *sampled) {
 /* rasterizer/mod.rs:69-100 */
 static attr_t interpolate(const rtri_t *r, uint64_t x, uint64_t y, uint8_t cov) {
     float xs = (float)x + 0.5f, ys = (float)y + 0.5f;
-    if (cov != 0xF) {
-        for (int i = 0; i < N_MSAA; i++)
+    if (cov != (uint8_t)((1u << r->ns) - 1u)) { /* CoverageMask::all() (mod.rs:42-44) */
+        for (int i = 0; i < r->ns; i++)
             if ((cov >> i) & 1) {
-                xs = (float)x + RGSS[i][0];
-                ys = (float)y + RGSS[i][1];
+                xs = (float)x + r->pat[i][0];
+                ys = (float)y + r->pat[i][1];
                 break;
             }
     }
@@ -484,12 +505,14 @@ orc_ctx *orc_create_rows(uint32_t width, uint32_t height, uint32_t row0, uint32_
     c->height = height;
     c->row0 = row0;
     c->row1 = row1;
+    c->ns = N_MSAA;
+    c->guard = 1.0f;
     c->sc_x0 = 0; c->sc_y0 = 0; c->sc_x1 = width; c->sc_y1 = height;
-    c->color = (uint32_t *)malloc(n * 4 * sizeof(uint32_t));
-    c->depth = (float *)malloc(n * 4 * sizeof(float));
-    c->owner = (uint32_t *)malloc(n * 4 * sizeof(uint32_t));
+    c->color = (uint32_t *)malloc(n * N_MSAA * sizeof(uint32_t));
+    c->depth = (float *)malloc(n * N_MSAA * sizeof(float));
+    c->owner = (uint32_t *)malloc(n * N_MSAA * sizeof(uint32_t));
     c->resolve = (uint32_t *)malloc(n * sizeof(uint32_t));
-    for (size_t i = 0; i < n * 4; i++) {
+    for (size_t i = 0; i < n * N_MSAA; i++) {
         c->color[i] = CLEAR_COLOR;
         c->depth[i] = CLEAR_DEPTH;
         c->owner[i] = ORC_NO_OWNER;
@@ -514,6 +537,34 @@ void orc_destroy(orc_ctx *c) {
     free(c->tile_mask[0]); free(c->tile_mask[1]); free(c->vs_out);
     for (uint32_t i = 0; i < c->n_tex; i++) free(c->tex[i].buf);
     free(c);
+}
+
+/* Runtime sample count (extension: N_MSAA_SAMPLES is a constant in the reference, mod.rs:23): 1, 2, 4 or 8 samples per
+ * pixel with the patterns above.  Call between frames; the sample buffers are re-created in their cleared state. */
+int orc_set_msaa(orc_ctx *c, uint32_t ns) {
+    if (ns != 1 && ns != 2 && ns != 4 && ns != 8) return -1;
+    size_t n = (size_t)c->width * (c->row1 - c->row0);
+    if (n == 0) n = 1;
+    free(c->color); free(c->depth); free(c->owner);
+    c->ns = (int)ns;
+    c->color = (uint32_t *)malloc(n * ns * sizeof(uint32_t));
+    c->depth = (float *)malloc(n * ns * sizeof(float));
+    c->owner = (uint32_t *)malloc(n * ns * sizeof(uint32_t));
+    for (size_t i = 0; i < n * ns; i++) {
+        c->color[i] = CLEAR_COLOR;
+        c->depth[i] = CLEAR_DEPTH;
+        c->owner[i] = ORC_NO_OWNER;
+    }
+    return 0;
+}
+
+/* Guard band (extension sketched at mod.rs:417-419): g >= 1 widens the four side clip planes to |x|, |y| <= g*w, so
+ * triangles that leave the viewport but stay inside the band are rasterised unclipped (their pixel boxes are bounded
+ * by the viewport, mod.rs:347-361).  g = 1 is the reference. */
+int orc_set_guard_band(orc_ctx *c, float g) {
+    if (!(g >= 1.0f) || g > 1048576.0f) return -1;
+    c->guard = g;
+    return 0;
 }
 
 /* Scissor rect [x0,x1) x [y0,y1), clamped to the viewport; x0 >= x1 or y0 >= y1 draws nothing. */
@@ -579,7 +630,7 @@ static int rasterize_one(orc_ctx *c, const tri_t *raw, uint32_t fs_id, uint32_t 
     tri_t clipped[ORC_MAX_POLY];
     const tri_t *list = raw;
     int n = 1, ovf = 0;
-    int res = try_clip(raw, clipped, ORC_MAX_POLY, &ovf);
+    int res = try_clip(raw, clipped, ORC_MAX_POLY, &ovf, c->guard);
     if (ovf) c->cnt.n_clip_overflow++;
     if (res < 0) {
         /* distinguish the degenerate cull for the counters only */
@@ -602,6 +653,9 @@ static int rasterize_one(orc_ctx *c, const tri_t *raw, uint32_t fs_id, uint32_t 
         rtri_t r;
         orc_perspective_divide(&list[ti].p[0][0], ndc);
         viewport_setup(W, H, ndc, list[ti].a, &r);
+        r.ns = c->ns;
+        r.pat = pattern_of(c->ns);
+        const int NS = c->ns;
         c->cnt.n_tris_setup++;
         uint32_t key = order_base * 8u + (uint32_t)(ti < 8 ? ti : 7);
         /* mod.rs:347-361 */
@@ -620,13 +674,13 @@ static int rasterize_one(orc_ctx *c, const tri_t *raw, uint32_t fs_id, uint32_t 
                 eval_cov(&r, j, i);
                 if (!r.cov_mask) continue;
                 c->cnt.n_covered_px++;
-                float sd[N_MSAA];
+                float sd[MAX_MSAA];
                 fragment_depths(&r, sd);
                 size_t idx = (size_t)(i - c->row0) * W + j;
                 /* depth_coverage mod.rs:363-378 */
                 uint8_t dcov = 0;
-                for (int s = 0; s < N_MSAA; s++)
-                    if (((r.cov_mask >> s) & 1) && sd[s] < c->depth[idx * 4 + s]) dcov |= (uint8_t)(1u << s);
+                for (int s = 0; s < NS; s++)
+                    if (((r.cov_mask >> s) & 1) && sd[s] < c->depth[idx * NS + s]) dcov |= (uint8_t)(1u << s);
                 if (!dcov) continue;
                 c->cnt.n_shaded_px++;
                 attr_t a = interpolate(&r, j, i, dcov);
@@ -635,11 +689,11 @@ static int rasterize_one(orc_ctx *c, const tri_t *raw, uint32_t fs_id, uint32_t 
                 /* write_pixel mod.rs:380-397 */
                 uint32_t argb = orc_to_argb(rgba);
                 c->tile_mask[c->mask_idx][(i / TILE_SIZE) * c->n_horizontal + (j / TILE_SIZE)] = 1;
-                for (int s = 0; s < N_MSAA; s++)
+                for (int s = 0; s < NS; s++)
                     if ((dcov >> s) & 1) {
-                        c->color[idx * 4 + s] = argb;
-                        c->depth[idx * 4 + s] = sd[s];
-                        c->owner[idx * 4 + s] = key;
+                        c->color[idx * NS + s] = argb;
+                        c->depth[idx * NS + s] = sd[s];
+                        c->owner[idx * NS + s] = key;
                         c->cnt.n_samples_written++;
                     }
             }
@@ -740,11 +794,11 @@ const uint32_t *orc_framebuffer(orc_ctx *c) {
         for (uint32_t y = y0; y < y1; y++)
             for (uint32_t x = tx * TILE_SIZE; x < x1; x++) {
                 size_t idx = (size_t)(y - c->row0) * W + x;
-                c->resolve[idx] = orc_box_filter_color(&c->color[idx * 4]);
-                for (int s = 0; s < N_MSAA; s++) {
-                    c->color[idx * 4 + s] = CLEAR_COLOR;
-                    c->depth[idx * 4 + s] = CLEAR_DEPTH;
-                    c->owner[idx * 4 + s] = ORC_NO_OWNER;
+                c->resolve[idx] = box_filter_n(&c->color[idx * c->ns], c->ns);
+                for (int s = 0; s < c->ns; s++) {
+                    c->color[idx * c->ns + s] = CLEAR_COLOR;
+                    c->depth[idx * c->ns + s] = CLEAR_DEPTH;
+                    c->owner[idx * c->ns + s] = ORC_NO_OWNER;
                 }
             }
     }
@@ -800,6 +854,8 @@ static void rtri_from_screen(const float *screen9, const float *w3, const float 
     r->inv_2x_area = 1.0f / area2(sx[0], sy[0], sx[1], sy[1], sx[2], sy[2]);
     memset(r->cov_eval, 0, sizeof r->cov_eval);
     r->cov_mask = 0;
+    r->ns = N_MSAA;
+    r->pat = RGSS;
 }
 
 /* eval(x,y) + fragment() + interpolate(x,y,mask_for_interp or own coverage if 0xFF):

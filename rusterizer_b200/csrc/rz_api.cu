@@ -17,6 +17,7 @@
 #include "rz_exact.cuh"
 #include "rz_geom.cuh"
 #include "rz_tile.cuh"
+#include "rz_msaa.cuh"
 #include "rz_types.cuh"
 
 using namespace rz;
@@ -50,6 +51,9 @@ struct rz_ctx {
     uint32_t row_begin = 0, row_end = 0;
     uint32_t il_band = 0, il_rank = 0, il_world = 1;
     uint32_t sc_x0 = 0, sc_y0 = 0, sc_x1 = 0, sc_y1 = 0; // scissor rect (rz_set_scissor), default = viewport
+    uint32_t msaa = 4;     // samples per pixel (rz_set_msaa); 4 = the reference
+    uint32_t dbg_msaa = 0; // sample count the debug capture buffers were sized for
+    float guard = 1.0f;    // guard band factor (rz_set_guard_band); 1 = the reference's clip planes
     cudaStream_t own_stream = nullptr, stream = nullptr;
     float world[16], view[16], proj[16];
     std::vector<Texture> textures;
@@ -323,6 +327,11 @@ int rz_create(int device, uint32_t width, uint32_t height, rz_ctx **out) {
             {(const void *)tile_kernel<true, false, false>, sizeof(TileSmemT<true>)},   {(const void *)tile_kernel<true, false, true>, sizeof(TileSmemT<true>)},
             {(const void *)tile_kernel<true, true, false>, sizeof(TileSmemT<true>)},    {(const void *)tile_kernel<true, true, true>, sizeof(TileSmemT<true>)}};
         for (auto &e : k) CU_NEW(cudaFuncSetAttribute(e.f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem));
+        struct { const void *f; size_t smem; } km[] = {
+            {(const void *)msaa_tile_kernel<1, false>, sizeof(MsaaSmemT<false>)}, {(const void *)msaa_tile_kernel<1, true>, sizeof(MsaaSmemT<true>)},
+            {(const void *)msaa_tile_kernel<2, false>, sizeof(MsaaSmemT<false>)}, {(const void *)msaa_tile_kernel<2, true>, sizeof(MsaaSmemT<true>)},
+            {(const void *)msaa_tile_kernel<8, false>, sizeof(MsaaSmemT<false>)}, {(const void *)msaa_tile_kernel<8, true>, sizeof(MsaaSmemT<true>)}};
+        for (auto &e : km) CU_NEW(cudaFuncSetAttribute(e.f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem));
     }
 #undef CU_NEW
     *out = c;
@@ -513,6 +522,7 @@ static FrameParams make_params(rz_ctx *c, uint32_t *out_base) {
     P.row_begin = c->row_begin; P.row_end = c->row_end;
     P.il_band = c->il_band; P.il_rank = c->il_rank; P.il_world = c->il_world;
     P.scissor = make_uint4(c->sc_x0, c->sc_y0, c->sc_x1, c->sc_y1);
+    P.msaa = c->msaa; P.guard = c->guard;
     P.ty_begin = c->row_begin / TH;
     P.ty_end = (c->row_end + TH - 1) / TH;
     P.rec_cap = c->rec_cap; P.large_cap = c->large_cap;
@@ -617,7 +627,16 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     }
     if (timed) CU(c, cudaEventRecord(c->ev[2], st));
     const dim3 tile_grid(std::min<uint32_t>(n_tiles, (uint32_t)c->num_sms * (c->debug ? 3u : 4u))); // persistent CTAs, 4 per SM
-    if (n_tiles) {
+    if (n_tiles && c->msaa != 4u) {
+        // runtime sample counts other than the reference's 4: the generic pixel-parallel tile kernel (rz_msaa.cuh)
+        const dim3 g(std::min<uint32_t>(n_tiles, (uint32_t)c->num_sms * 2u));
+#define RZ_MSAA_LAUNCH(NS, D) CU(c, launch_pdl(msaa_tile_kernel<NS, D>, g, dim3(NT), sizeof(MsaaSmemT<D>), st, P))
+        if (c->msaa == 1u) { if (c->debug) RZ_MSAA_LAUNCH(1, true); else RZ_MSAA_LAUNCH(1, false); }
+        else if (c->msaa == 2u) { if (c->debug) RZ_MSAA_LAUNCH(2, true); else RZ_MSAA_LAUNCH(2, false); }
+        else { if (c->debug) RZ_MSAA_LAUNCH(8, true); else RZ_MSAA_LAUNCH(8, false); }
+#undef RZ_MSAA_LAUNCH
+        c->launches++;
+    } else if (n_tiles) {
         bool ext = false; // does any draw use the shader-registry extension (texture index != 0, TextureBlend)?
         for (auto &d : c->draws) ext = ext || (d.fs >> 8) != 0 || (d.fs & 0xFFu) == RZ_FS_TEXTURE_BLEND;
         // DIRECT: the pixel-parallel path for chunks of large items is only compiled into the instantiations used
@@ -937,6 +956,37 @@ int rz_set_scissor(rz_ctx *c, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1
     return RZ_OK;
 }
 
+static int alloc_debug_buffers(rz_ctx *c) {
+    if (c->d_dbg_depth && c->dbg_msaa == c->msaa) return RZ_OK;
+    cudaFree(c->d_dbg_depth); cudaFree(c->d_dbg_color); cudaFree(c->d_dbg_owner);
+    c->d_dbg_depth = nullptr; c->d_dbg_color = nullptr; c->d_dbg_owner = nullptr;
+    const size_t n = (size_t)c->W * c->H * c->msaa;
+    CU(c, cudaMalloc(&c->d_dbg_depth, n * 4));
+    CU(c, cudaMalloc(&c->d_dbg_color, n * 4));
+    CU(c, cudaMalloc(&c->d_dbg_owner, n * 4));
+    c->dbg_msaa = c->msaa;
+    return RZ_OK;
+}
+
+int rz_set_msaa(rz_ctx *c, uint32_t samples) {
+    if (!c) return RZ_E_INVALID;
+    if (samples != 1 && samples != 2 && samples != 4 && samples != 8)
+        return fail(c, RZ_E_INVALID, "rz_set_msaa: %u samples per pixel (supported: 1, 2, 4, 8; the reference has 4, rasterizer/mod.rs:23)", samples);
+    if (!c->draws.empty()) return fail(c, RZ_E_INVALID, "rz_set_msaa: draws are recorded for the current frame (one sample count per frame)");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->msaa = samples;
+    if (c->d_dbg_depth) return alloc_debug_buffers(c);
+    return RZ_OK;
+}
+
+int rz_set_guard_band(rz_ctx *c, float factor) {
+    if (!c) return RZ_E_INVALID;
+    if (!(factor >= 1.0f) || factor > 1048576.0f) return fail(c, RZ_E_INVALID, "rz_set_guard_band: the factor must be in [1, 2^20]");
+    c->guard = factor;
+    return RZ_OK;
+}
+
 int rz_set_row_interleave(rz_ctx *c, uint32_t band_tile_rows, uint32_t rank, uint32_t world) {
     if (!c) return RZ_E_INVALID;
     if (band_tile_rows == 0 || world <= 1) {
@@ -981,13 +1031,13 @@ uint64_t rz_launch_count(rz_ctx *c) { return c ? c->launches : 0; }
 int rz_debug_capture(rz_ctx *c, int enable) {
     if (!c) return RZ_E_INVALID;
     CU(c, cudaSetDevice(c->device));
-    if (enable && !c->d_dbg_depth) {
-        const size_t n = (size_t)c->W * c->H * 4;
-        CU(c, cudaMalloc(&c->d_dbg_depth, n * 4));
-        CU(c, cudaMalloc(&c->d_dbg_color, n * 4));
-        CU(c, cudaMalloc(&c->d_dbg_owner, n * 4));
-        CU(c, cudaMalloc(&c->d_dbg_time, (size_t)c->tiles_x * c->tiles_y * 64));
-        CU(c, cudaMemset(c->d_dbg_time, 0, (size_t)c->tiles_x * c->tiles_y * 64));
+    if (enable) {
+        int rc = alloc_debug_buffers(c);
+        if (rc != RZ_OK) return rc;
+        if (!c->d_dbg_time) {
+            CU(c, cudaMalloc(&c->d_dbg_time, (size_t)c->tiles_x * c->tiles_y * 64));
+            CU(c, cudaMemset(c->d_dbg_time, 0, (size_t)c->tiles_x * c->tiles_y * 64));
+        }
     }
     c->debug = enable != 0;
     return RZ_OK;
@@ -997,7 +1047,7 @@ int rz_debug_read(rz_ctx *c, float *depth, uint32_t *color, uint32_t *owner) {
     if (!c) return RZ_E_INVALID;
     if (!c->d_dbg_depth) return fail(c, RZ_E_INVALID, "rz_debug_read: capture was never enabled");
     CU(c, cudaSetDevice(c->device));
-    const size_t bytes = (size_t)c->W * c->H * 16;
+    const size_t bytes = (size_t)c->W * c->H * 4 * c->dbg_msaa;
     CU(c, cudaStreamSynchronize(c->stream));
     if (depth) CU(c, cudaMemcpy(depth, c->d_dbg_depth, bytes, cudaMemcpyDeviceToHost));
     if (color) CU(c, cudaMemcpy(color, c->d_dbg_color, bytes, cudaMemcpyDeviceToHost));

@@ -122,7 +122,7 @@ __device__ __forceinline__ void emit_setup(const FrameParams &P, const DrawParam
     uint32_t tmask = 0;
     if (small) {
         const uint32_t tx1 = (b.x1 - 1) / TW, ty1 = (b.y1 - 1) / TH;
-        if (area2 < GEOM_THIN_AREA2 && bw * bh <= GEOM_THIN_PX && setup_is_tame(s)) {
+        if (P.msaa == 4u && area2 < GEOM_THIN_AREA2 && bw * bh <= GEOM_THIN_PX && setup_is_tame(s)) {
             // (2) thin / tiny triangles usually touch no sample at all: rasterise them exactly right
             // here so they never reach a tile list (pole slivers of a UV-sphere, distant meshes).  Finite
             // coordinates only (anything else is simply binned): the single-compare form of EdgeFunctions::inside
@@ -209,20 +209,26 @@ __device__ __forceinline__ void emit_setup(const FrameParams &P, const DrawParam
 }
 
 // clipping::distance_measure (rasterizer/clipping.rs:29-38); planes in CLIP_PLANES order (53-60)
-__device__ __forceinline__ float clip_distance(int plane, const float *p) {
+// Guard band (the extension sketched at rasterizer/mod.rs:417-419): the four side planes sit at |x|, |y| <= g * w; g * w is
+// one f32 product and 1.0f * w == w, so g = 1 is the reference bit for bit.
+__device__ __forceinline__ float clip_distance(int plane, const float *p, float guard) {
     float c = p[plane >> 1];
-    return (plane & 1) ? fsub(p[3], c) : fadd(p[3], c);
+    const float w = plane < 4 ? fmul(guard, p[3]) : p[3];
+    return (plane & 1) ? fsub(w, c) : fadd(w, c);
 }
 
 // outcode bits of one clip-space vertex (clipping.rs:86-104): for axis a in x,y,z
 //   bit a     : v[a] >= -w     bit 3+a : v[a] <= w     bit 6+a : v[a] < -w     bit 9+a : v[a] > w
-__device__ __forceinline__ uint32_t clip_code(const float *c) {
+// With a guard band the "inside" bits (no clipping needed) are judged against the widened side planes, the "outside"
+// bits (nothing can be visible) still against the view frustum; z is never widened.
+__device__ __forceinline__ uint32_t clip_code(const float *c, float guard) {
     const float w = c[3], nw = -w;
     uint32_t code = 0;
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-        code |= (c[a] >= nw ? 1u : 0u) << a;
-        code |= (c[a] <= w ? 1u : 0u) << (3 + a);
+        const float gw = a < 2 ? fmul(guard, w) : w, ngw = -gw;
+        code |= (c[a] >= ngw ? 1u : 0u) << a;
+        code |= (c[a] <= gw ? 1u : 0u) << (3 + a);
         code |= (c[a] < nw ? 1u : 0u) << (6 + a);
         code |= (c[a] > w ? 1u : 0u) << (9 + a);
     }
@@ -305,7 +311,7 @@ __global__ void __launch_bounds__(NT) vertex_kernel(FrameParams P, DrawParams D,
         for (int r = 0; r < 4; r++)
             c[r] = dot4z(D.M[4 * r], D.M[4 * r + 1], D.M[4 * r + 2], D.M[4 * r + 3], x[k], y[k], z[k], 1.0f);
         D.vtx[2 * (size_t)v] = project_vertex(c, (float)P.W, (float)P.H);
-        D.vtx[2 * (size_t)v + 1] = make_float4(c[0], c[1], c[2], __uint_as_float(clip_code(c)));
+        D.vtx[2 * (size_t)v + 1] = make_float4(c[0], c[1], c[2], __uint_as_float(clip_code(c, P.guard)));
     }
 }
 
@@ -431,7 +437,7 @@ __global__ void __launch_bounds__(NT) clip_kernel(FrameParams P) {
             for (int i = 0; i < n_in; i++) {
                 const int prev = (i + n_in - 1) % n_in;
                 const float *pvv = pv[in][prev], *cvv = pv[in][i];
-                const float pd = clip_distance(plane, pvv), cd = clip_distance(plane, cvv);
+                const float pd = clip_distance(plane, pvv, P.guard), cd = clip_distance(plane, cvv, P.guard);
                 const bool pin = pd >= 0.0f, cin = cd >= 0.0f;
                 if (!pin && !cin) continue;
                 if (n_out + 2 > MAX_POLY) {
@@ -521,8 +527,11 @@ __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
             const uint32_t X0 = max(b.x0, tx * TW), X1 = min(b.x1, tx * TW + TW);
             const uint32_t Y0 = max(b.y0, ty * TH), Y1 = min(b.y1, ty * TH + TH);
             if (X0 >= X1 || Y0 >= Y1 || !owns_tile_row(P, ty)) continue;
-            const float sx_lo = fadd((float)X0, 0.125f), sx_hi = fadd((float)(X1 - 1), 0.875f);
-            const float sy_lo = fadd((float)Y0, 0.125f), sy_hi = fadd((float)(Y1 - 1), 0.875f);
+            // bounds of the sample positions: the 4-sample rotated grid spans [1/8, 7/8] of a pixel, the other patterns
+            // are simply bounded by the pixel itself
+            const float o_lo = P.msaa == 4u ? 0.125f : 0.0f, o_hi = P.msaa == 4u ? 0.875f : 1.0f;
+            const float sx_lo = fadd((float)X0, o_lo), sx_hi = fadd((float)(X1 - 1), o_hi);
+            const float sy_lo = fadd((float)Y0, o_lo), sy_hi = fadd((float)(Y1 - 1), o_hi);
             bool keep = true;
 #pragma unroll
             for (int k = 0; k < 3; k++) {

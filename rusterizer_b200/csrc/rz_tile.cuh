@@ -134,9 +134,11 @@ __device__ __forceinline__ uint32_t pack_argb(const float *o) {
 // attribute locations come from the triangle's ShadeRec.
 // EXT = false compiles the reference's three shaders on texture 0 only (the registry extension costs registers in
 // the hottest loop of the frame; frames that do not use it run the lean instantiation).
+// shade_at: the same at an explicit sample position (xs, ys) -- the caller applies the position rule of
+// Fragment::interpolate (mod.rs:70-83) for its sample pattern.
 template <bool ALPHA, bool EXT>
-__device__ __forceinline__ uint32_t shade(const FrameParams &P, const Setup &s, uint32_t rec, const float *lut, int X,
-                                          int Y, uint32_t mpost, float depth0, uint32_t &oob) {
+__device__ __forceinline__ uint32_t shade_at(const FrameParams &P, const Setup &s, uint32_t rec, const float *lut, float xs,
+                                             float ys, float depth0, uint32_t &oob) {
     // (records are written by the geometry kernels of this frame: plain loads, not the read-only path)
     const uint4 sh = *reinterpret_cast<const uint4 *>(&P.shade[rec]);
     const uint32_t info = sh.x, fs = info & 3u, texidx = EXT ? (info >> 3) & 31u : 0u;
@@ -148,20 +150,11 @@ __device__ __forceinline__ uint32_t shade(const FrameParams &P, const Setup &s, 
         a0 = P.attrs[sh.y].a;
         a1 = a0 + 6;
         a2 = a0 + 12;
-    } else {       // unclipped: straight from the mesh (constant for the frame: read-only path)
+    } else {       // unclipped: straight from the mesh
         const float *attr = P.draws[info >> 8].attr;
         a0 = attr + 6 * (size_t)sh.y;
         a1 = attr + 6 * (size_t)sh.z;
         a2 = attr + 6 * (size_t)sh.w;
-    }
-    float xs, ys;
-    if (mpost == 0xFu) {
-        xs = fadd((float)X, 0.5f);
-        ys = fadd((float)Y, 0.5f);
-    } else {
-        const int i = __ffs(mpost) - 1;
-        xs = fadd((float)X, rgss_x(i));
-        ys = fadd((float)Y, rgss_y(i));
     }
     const float e0 = edge_eval(s, 0, xs, ys), e1 = edge_eval(s, 1, xs, ys), e2 = edge_eval(s, 2, xs, ys);
     const float fu = fdiv(e1, wq.x), fv = fdiv(e2, wq.y), fw = fdiv(e0, wq.z);
@@ -193,6 +186,23 @@ __device__ __forceinline__ uint32_t shade(const FrameParams &P, const Setup &s, 
 #undef RZ_INTERP
 #undef RZ_LDA
     return pack_argb<ALPHA>(o);
+}
+
+// 4-sample form: the position rule of Fragment::interpolate (mod.rs:70-83) for the rotated-grid pattern -- the pixel
+// centre when all four samples passed the depth test, else the first passing sample.
+template <bool ALPHA, bool EXT>
+__device__ __forceinline__ uint32_t shade(const FrameParams &P, const Setup &s, uint32_t rec, const float *lut, int X,
+                                          int Y, uint32_t mpost, float depth0, uint32_t &oob) {
+    float xs, ys;
+    if (mpost == 0xFu) {
+        xs = fadd((float)X, 0.5f);
+        ys = fadd((float)Y, 0.5f);
+    } else {
+        const int i = __ffs(mpost) - 1;
+        xs = fadd((float)X, rgss_x(i));
+        ys = fadd((float)Y, rgss_y(i));
+    }
+    return shade_at<ALPHA, EXT>(P, s, rec, lut, xs, ys, depth0, oob);
 }
 
 // Bitonic network in its "flip then halve" form: every compare-exchange puts the smaller element at
@@ -305,20 +315,19 @@ struct TileSmemT {
 // memory, then the entries are gathered in key order and written back over the head of the bin in COMPACT form --
 // uint2 {record | tie bits, box}; the order key of entry i is now simply i (returns true).  Longer lists are sorted in
 // place in HBM as full entries (returns false).
-template <typename SM>
-__device__ __forceinline__ bool sort_tile_list(SM &S, uint4 *bin, int n) {
+__device__ __forceinline__ bool sort_tile_list_ptr(unsigned long long *sorted, uint4 *bin, int n) {
     __syncthreads();
     if (n <= SORT_CAP) {
         for (int i = threadIdx.x; i < n; i += NT)
-            S.u.sorted[i] = ((unsigned long long)__ldcg(reinterpret_cast<const uint32_t *>(bin + i)) << 32) | (uint32_t)i;
+            sorted[i] = ((unsigned long long)__ldcg(reinterpret_cast<const uint32_t *>(bin + i)) << 32) | (uint32_t)i;
         __syncthreads();
-        block_sort(S.u.sorted, n, [](unsigned long long a, unsigned long long b) { return a < b; });
+        block_sort(sorted, n, [](unsigned long long a, unsigned long long b) { return a < b; });
         uint2 e[SORT_CAP / NT];
 #pragma unroll
         for (int k = 0; k < SORT_CAP / NT; k++) {
             const int i = threadIdx.x + k * NT;
             if (i < n) {
-                const uint4 v = __ldcg(bin + (uint32_t)S.u.sorted[i]);
+                const uint4 v = __ldcg(bin + (uint32_t)sorted[i]);
                 e[k] = make_uint2(v.y, v.z);
             }
         }
@@ -334,6 +343,10 @@ __device__ __forceinline__ bool sort_tile_list(SM &S, uint4 *bin, int n) {
     block_sort(bin, n, [](const uint4 &a, const uint4 &b) { return a.x < b.x; });
     __syncthreads();
     return false;
+}
+template <typename SM>
+__device__ __forceinline__ bool sort_tile_list(SM &S, uint4 *bin, int n) {
+    return sort_tile_list_ptr(S.u.sorted, bin, n);
 }
 
 // Stage the records of `cnt` chunk items in shared memory for a pixel-parallel walk (thread = item).  The staging

@@ -145,6 +145,8 @@ struct FrameParams {
     uint32_t ty_begin, ty_end;   // tile rows owned by this ctx (screen-space shard)
     uint32_t row_begin, row_end; // same in pixel rows
     uint4 scissor;               // {x0, y0, x1, y1}: bounds every triangle's pixel bbox (default = the viewport)
+    uint32_t msaa;               // samples per pixel: 4 = the reference (mod.rs:23); 1, 2, 8 run the generic tile kernel
+    float guard;                 // guard band factor g >= 1: side clip planes at |x|, |y| <= g * w (mod.rs:417-419); 1 = reference
     uint32_t il_band, il_rank, il_world; // interleaved ownership of tile-row bands (il_band == 0: off), see owns_tile_row()
     uint32_t rec_cap, large_cap;
     FrameState *fs;

@@ -239,6 +239,12 @@ class Renderer { // render.rs:38-127 without the minifb window
 
     // Scissor rect [x0,x1) x [y0,y1): the extension sketched in Rasterizer::bounding_box (rasterizer/mod.rs:349-350)
     void set_scissor(uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1) { check(rz_set_scissor(ctx_, x0, y0, x1, y1)); }
+    // N_MSAA_SAMPLES as a runtime value (rasterizer/mod.rs:23): 1, 2, 4 (the reference) or 8 samples per pixel
+    void set_msaa(uint32_t samples) { check(rz_set_msaa(ctx_, samples)); }
+    // guard-band clipping (rasterizer/mod.rs:417-419): side clip planes at |x|, |y| <= factor * w; 1 = the reference
+    void set_guard_band(float factor) { check(rz_set_guard_band(ctx_, factor)); }
+    // drop the draws recorded for the current frame
+    void discard_frame() { check(rz_discard_frame(ctx_)); }
 
     // Headless replacement of Renderer::display (render.rs:116-127): the last framebuffer() as a file
     void save_png(const std::string &path) const { image::write_png(path, fb_.data(), width_, height_); }

@@ -35,7 +35,7 @@ ABI_SYMBOLS = (
     "rz_create", "rz_destroy", "rz_set_stream", "rz_bind_texture", "rz_write_block", "rz_read_block",
     "rz_mesh_create", "rz_mesh_destroy", "rz_render", "rz_render_host", "rz_framebuffer",
     "rz_framebuffer_async", "rz_framebuffer_host_async", "rz_sync", "rz_discard_frame", "rz_shared_alloc", "rz_shared_open",
-    "rz_shared_close", "rz_shared_free", "rz_signal", "rz_wait_flags", "rz_set_row_range", "rz_set_row_interleave", "rz_set_scissor", "rz_tile_width", "rz_tile_height",
+    "rz_shared_close", "rz_shared_free", "rz_signal", "rz_wait_flags", "rz_set_row_range", "rz_set_row_interleave", "rz_set_scissor", "rz_set_msaa", "rz_set_guard_band", "rz_tile_width", "rz_tile_height",
     "rz_counters", "rz_reset_counters", "rz_timings", "rz_launch_count", "rz_debug_capture",
     "rz_debug_read", "rz_debug_tile_times", "rz_debug_vertex_stage", "rz_last_error", "rz_version",
 )
@@ -104,6 +104,8 @@ def load_library() -> C.CDLL:
     L.rz_set_row_range.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.rz_set_row_interleave.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32]
     L.rz_set_scissor.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.rz_set_msaa.argtypes = [vp, C.c_uint32]
+    L.rz_set_guard_band.argtypes = [vp, C.c_float]
     L.rz_tile_width.restype = C.c_uint32
     L.rz_tile_height.restype = C.c_uint32
     L.rz_counters.argtypes = [vp, C.POINTER(CountersT)]
@@ -217,6 +219,7 @@ class Renderer:
             raise RzError(rc, (self._L.rz_last_error(None) or b"").decode())
         self._uniforms = Uniforms(self)
         self._keepalive: list = []
+        self.msaa = 4
 
     @classmethod
     def new(cls, width: int, height: int, device: int = 0) -> "Renderer":
@@ -334,6 +337,15 @@ class Renderer:
         """Scissor rect [x0,x1) x [y0,y1) (the extension sketched at rasterizer/mod.rs:349-350)."""
         self._check(self._L.rz_set_scissor(self._ctx, x0, y0, x1, y1))
 
+    def set_msaa(self, samples: int):
+        """Samples per pixel: 1, 2, 4 (the reference, rasterizer/mod.rs:23) or 8."""
+        self._check(self._L.rz_set_msaa(self._ctx, samples))
+        self.msaa = int(samples)
+
+    def set_guard_band(self, factor: float):
+        """Guard-band clipping (rasterizer/mod.rs:417-419): side clip planes at |x|, |y| <= factor * w."""
+        self._check(self._L.rz_set_guard_band(self._ctx, factor))
+
     def set_row_interleave(self, band_tile_rows: int, rank: int, world: int):
         self._check(self._L.rz_set_row_interleave(self._ctx, band_tile_rows, rank, world))
 
@@ -357,7 +369,7 @@ class Renderer:
         self._check(self._L.rz_debug_capture(self._ctx, 1 if enable else 0))
 
     def debug_read(self):
-        shape = (self.height, self.width, 4)
+        shape = (self.height, self.width, self.msaa)
         d, c, o = np.empty(shape, np.float32), np.empty(shape, np.uint32), np.empty(shape, np.uint32)
         self._check(self._L.rz_debug_read(self._ctx, d.ctypes.data, c.ctypes.data, o.ctypes.data))
         return d, c, o

@@ -47,6 +47,8 @@ class Scene:
     texture: Texture | None = None          # texture 0
     extra_textures: list = field(default_factory=list)  # textures 1.. (bind order, uniform.rs:29-33)
     scissor: tuple | None = None            # (x0, y0, x1, y1), the extension sketched at rasterizer/mod.rs:349-350
+    msaa: int = 4                           # samples per pixel: 4 = the reference (mod.rs:23); 1, 2, 8 = runtime extension
+    guard_band: float = 1.0                 # guard band factor (mod.rs:417-419); 1 = the reference's clip planes
 
     @property
     def n_triangles(self) -> int:

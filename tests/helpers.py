@@ -16,6 +16,10 @@ def oracle_render(scene, fast=False):
     r.write_block(view=scene.view, projection=scene.projection)
     if getattr(scene, "scissor", None):
         r.set_scissor(*scene.scissor)
+    if getattr(scene, "msaa", 4) != 4:
+        r.set_msaa(scene.msaa)
+    if getattr(scene, "guard_band", 1.0) != 1.0:
+        r.set_guard_band(scene.guard_band)
     for d in scene.draws:
         r.write_block(world=d.world)
         r.render(d.mesh.vertices, d.mesh.attributes, d.mesh.indices, 0, d.fs)
@@ -39,6 +43,10 @@ def gpu_render(scene, debug=True, device_resident=False, renderer=None):
         r.debug_capture(True)
     if getattr(scene, "scissor", None):
         r.set_scissor(*scene.scissor)
+    if getattr(scene, "msaa", 4) != 4:
+        r.set_msaa(scene.msaa)
+    if getattr(scene, "guard_band", 1.0) != 1.0:
+        r.set_guard_band(scene.guard_band)
     r.reset_counters()
     meshes = [r.upload(d.mesh) for d in scene.draws] if device_resident else None
     render_scene(r, scene, meshes)
