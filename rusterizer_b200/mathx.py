@@ -6,11 +6,11 @@ Every operation is one IEEE binary32 rounding in the reference's source order:
   * dot: sum starts at 0.0, sequential            (math/vector.rs:17-23)
   * Mat x Mat: R[i][j] = dot(row_i(A), col_j(B))  (math/matrix.rs:56-79)
   * Mat x Vec: r[i] = dot(row_i(M), v)            (math/vector.rs:219-240)
-Transcendentals (sin/cos/tan/sqrt) are evaluated in double and rounded once to f32, i.e. correctly
-rounded.  Rust's f32::sin/cos/tan call the platform libm (sinf/cosf/tanf), which glibc does NOT round
-correctly for every argument (sinf(0.29452431) is one ulp off): the matrices and meshes the crate itself
-builds come out bit-identical (tests/test_host.py compares them with the C++ mirror, which calls libm),
-other sphere sizes can differ in the last bits of a few percent of the values.  Inputs only.
+Transcendentals: Rust's f32::sin / cos / tan lower to the platform libm (sinf / cosf / tanf), which glibc does NOT
+round correctly for every argument (sinf(0.29452431) is one ulp off the correctly rounded value).  To hand the raster
+path the very inputs the Rust host would, sin / cos / tan call the same libm through ctypes (sinf_array etc. for the
+mesh generators); tests/test_host.py compares everything built here, bit for bit, with the C++ mirror.  sqrt is
+correctly rounded in every libm.
 """
 from __future__ import annotations
 
@@ -25,16 +25,39 @@ def _f(x) -> np.float32:
     return np.float32(x)
 
 
+def _libm():
+    import ctypes
+    import ctypes.util
+
+    lib = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    for name in ("sinf", "cosf", "tanf"):
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = ctypes.c_float, [ctypes.c_float]
+    return lib
+
+
+_M = _libm()
+
+
 def sin(x) -> np.float32:
-    return F(math.sin(float(F(x))))
+    return F(_M.sinf(float(F(x))))
 
 
 def cos(x) -> np.float32:
-    return F(math.cos(float(F(x))))
+    return F(_M.cosf(float(F(x))))
 
 
 def tan(x) -> np.float32:
-    return F(math.tan(float(F(x))))
+    return F(_M.tanf(float(F(x))))
+
+
+def sinf_array(a: np.ndarray) -> np.ndarray:
+    """libm sinf over an f32 array (what a Rust loop over f32::sin computes)."""
+    return np.array([_M.sinf(float(v)) for v in np.asarray(a, np.float32).reshape(-1)], np.float32).reshape(np.shape(a))
+
+
+def cosf_array(a: np.ndarray) -> np.ndarray:
+    return np.array([_M.cosf(float(v)) for v in np.asarray(a, np.float32).reshape(-1)], np.float32).reshape(np.shape(a))
 
 
 def sqrt(x) -> np.float32:

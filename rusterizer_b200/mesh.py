@@ -10,6 +10,8 @@ from dataclasses import dataclass
 
 import numpy as np
 
+from . import mathx
+
 F = np.float32
 _RED, _GREEN, _BLUE, _WHITE = (1, 0, 0, 1), (0, 1, 0, 1), (0, 0, 1, 1), (1, 1, 1, 1)
 
@@ -86,11 +88,9 @@ def sphere(radius: float, n_phi_samples: int = 17, n_theta_samples: int = 9) -> 
     phi = ((F(np.pi) * F(2.0)) * phi_ratio).astype(np.float32)
     theta = (F(np.pi) * theta_ratio).astype(np.float32)
 
-    def f32fn(fn, a):  # libm-style: correctly rounded f32 of the f32 argument
-        return fn(a.astype(np.float64)).astype(np.float32)
-
-    st, ct = f32fn(np.sin, theta), f32fn(np.cos, theta)
-    sp, cp = f32fn(np.sin, phi), f32fn(np.cos, phi)
+    # f32::sin / f32::cos of mesh.rs:176-178 = libm sinf / cosf (not correctly rounded for every argument): same calls
+    st, ct = mathx.sinf_array(theta), mathx.cosf_array(theta)
+    sp, cp = mathx.sinf_array(phi), mathx.cosf_array(phi)
     rs = (r * st).astype(np.float32)[:, None]
     x = (rs * cp[None, :]).astype(np.float32)
     y = np.broadcast_to((r * ct).astype(np.float32)[:, None], x.shape)
