@@ -565,9 +565,10 @@ __global__ void __launch_bounds__(NT) order_kernel(FrameParams P) {
     uint32_t base = 0;
     if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&P.fs->bucket_n[b], (uint32_t)__popc(peers));
     base = __shfl_sync(peers, base, leader);
-    // the entry carries the list length and the tile's bin slice too: the tile stage learns all of it with one load
+    // the entry carries the list length (bounded by the bin's capacity) and the tile's first bin entry too: the tile stage
+    // learns all of it with one load
     const uint2 tb = __ldg(reinterpret_cast<const uint2 *>(&P.tile_bin[tile]));
-    P.busy[(size_t)b * P.tiles_x * P.tiles_y + base + __popc(peers & lanemask_lt())] = make_uint4(tile, n, tb.x, tb.y);
+    P.busy[(size_t)b * P.tiles_x * P.tiles_y + base + __popc(peers & lanemask_lt())] = make_uint4(tile, min(n, tb.y), tb.x, 0u);
 }
 
 // ---- completion flags over peer memory (screen-space sharding, one process per GPU) ----

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(NT, 2) msaa_tile_kernel(FrameParams P) {
                 }
             const uint4 e = __ldcg(P.busy + (size_t)b * P.tiles_x * P.tiles_y + (work - start));
             tile = e.x;
-            n = (int)min(e.y, e.w);
+            n = (int)e.y;
             bin_off = e.z;
         }
         const int tileX0 = (int)(tile % P.tiles_x) * TW, tileY0 = (int)(tile / P.tiles_x) * TH;

@@ -305,7 +305,8 @@ struct TileSmemT {
     } u;
     uint32_t head[TILE_PX];               // per-pixel fragment list heads
     uint32_t scan[NT / 32];
-    uint32_t first_big, first_small, nfrag, ovf, cur_tile;
+    uint32_t first_big, first_small, nfrag, ovf;
+    uint4 ent;                            // the tile of this trip: {tile id, list length, first bin entry, work index}; x = ~0: none left
     uint32_t bucket_end[ORDER_BUCKETS];   // prefix of the list-length class sizes (busy-list work order)
     uint32_t clr_cursor[NT / 32];         // per-warp cursor of the empty-tile clears
     uint32_t unit_budget;                 // adaptive work-unit budget of a chunk (fragment pool occupancy predictor)
@@ -543,32 +544,33 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
     // rasterised tile, cursor kept in shared memory), the rest follows after the loop
     if (lane == 0) S.clr_cursor[warp] = blockIdx.x * (NT / 32) + warp;
     if (tid == 0) S.unit_budget = UNIT_CAP;
-    // Barriers of a tile trip: ONE at the top.  Every phase of a tile ends with a barrier and the write-back after the
-    // last one touches thread-private shared-memory words only, so thread 0 steals the next work item right there
-    // (the atomic's round trip overlaps the write-back) and the barrier at the top of the next trip publishes it.
-    if (tid == 0) S.cur_tile = atomicAdd(&P.fs->tile_cursor, 1u);
-    for (;;) {
-    __syncthreads(); // previous tile fully retired (also covers S.lut and S.bucket_end on the first trip)
-    const uint32_t n_busy = S.bucket_end[ORDER_BUCKETS - 1];
-    const uint32_t work = S.cur_tile;
-    if (work >= n_busy) break;
-    uint32_t tile, bin_off;
-    int n;
-    {
+    // Work stealing.  After the last phase barrier of a tile, thread 0 steals the next work index and loads that tile's
+    // busy entry {tile id, list length, first bin entry}; both round trips overlap the write-back of the current tile,
+    // the entry is published in shared memory at the very end of the trip and read by everybody after the barrier at the
+    // top of the next one, so a trip starts with its bin address in hand.  (Stealing further ahead -- reserving a tile
+    // while another is still being processed -- was measured: the reserved tiles of slow CTAs are held hostage at the
+    // end of the frame, C2 tile stage 83 -> 131 us.)
+    auto load_entry = [&](uint32_t w) -> uint4 {
+        const uint32_t n_busy_ = S.bucket_end[ORDER_BUCKETS - 1];
+        if (w >= n_busy_) return make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
         uint32_t b = 0, start = 0;
 #pragma unroll
         for (int k = 0; k < ORDER_BUCKETS - 1; k++)
-            if (work >= S.bucket_end[k]) {
+            if (w >= S.bucket_end[k]) {
                 b = k + 1;
                 start = S.bucket_end[k];
             }
-        // the entry carries the tile id, its list length and its bin slice (order_kernel): one load instead of three
-        // dependent ones
-        const uint4 e = __ldcg(P.busy + (size_t)b * P.tiles_x * P.tiles_y + (work - start));
-        tile = e.x;
-        n = (int)min(e.y, e.w);
-        bin_off = e.z;
-    }
+        uint4 e = __ldcg(P.busy + (size_t)b * P.tiles_x * P.tiles_y + (w - start));
+        e.w = w;
+        return e;
+    };
+    if (tid == 0) S.ent = load_entry(atomicAdd(&P.fs->tile_cursor, 1u)); // (S.bucket_end was written by this same thread)
+    for (;;) {
+    __syncthreads(); // previous tile fully retired (also covers S.lut and S.bucket_end on the first trip)
+    const uint4 ent = S.ent;
+    if (ent.x == 0xFFFFFFFFu) break;
+    const uint32_t tile = ent.x, bin_off = ent.z, work = ent.w;
+    int n = (int)ent.y;
     const uint32_t tx = tile % P.tiles_x, ty = tile / P.tiles_x;
     const int tileX0 = tx * TW, tileY0 = ty * TH;
     const int X = tileX0 + lx, Y = tileY0 + ly;
@@ -1063,8 +1065,9 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
         }
     }
     else __syncthreads(); // (a busy tile never has an empty list; keeps the hand-over below safe if it ever did)
-    // every path through the chunk loop ends with a barrier: all threads have read S.cur_tile long ago
-    if (tid == 0) S.cur_tile = atomicAdd(&P.fs->tile_cursor, 1u);
+    // every path through the chunk loop ends with a barrier: all threads have read S.ent long ago
+    uint4 ent_next = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) ent_next = load_entry(atomicAdd(&P.fs->tile_cursor, 1u)); // issued here, consumed at the end of the trip
     // ---- resolve (ColorBuffer::box_filter_color, buffers.rs:111-125) and write back ----
     const uint32_t res = box_filter(S.color[tid * 4], S.color[tid * 4 + 1], S.color[tid * 4 + 2], S.color[tid * 4 + 3]);
     if (DBG && X < (int)P.W && Y < (int)P.H) {
@@ -1105,6 +1108,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
         o[6] = 0; o[7] = 0;
     }
     if (P.spread_clears) {
+        const uint32_t n_busy = S.bucket_end[ORDER_BUCKETS - 1];
         const uint32_t stride = gridDim.x * (NT / 32), iters = max(1u, (n_busy + gridDim.x - 1) / gridDim.x);
         const uint32_t groups = ((P.tiles_x + CLEAR_GROUP - 1) / CLEAR_GROUP) * (P.ty_end - P.ty_begin);
         uint32_t g = S.clr_cursor[warp];
@@ -1112,6 +1116,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
         __syncwarp();
         if (lane == 0) S.clr_cursor[warp] = g;
     }
+    if (tid == 0) S.ent = ent_next; // publish the next trip's tile (everybody read S.ent right after the barrier at the top)
     } // persistent tile loop
 
     // ---- the rest of the tiles nothing was binned into ----

@@ -151,7 +151,7 @@ struct FrameParams {
     uint32_t rec_cap, large_cap;
     FrameState *fs;
     uint32_t *tile_count;        // [tiles_x * tiles_y]
-    uint4 *busy;                 // [ORDER_BUCKETS][tiles_x * tiles_y] non-empty tiles per class: {tile id, list length, bin offset, bin capacity}
+    uint4 *busy;                 // [ORDER_BUCKETS][tiles_x * tiles_y] non-empty tiles per class: {tile id, list length, first bin entry, -}
     uint4 *bins;                 // bin entries of all tiles (see TileBin); tile t owns [tile_bin[t].off, +cap)
     const TileBin *tile_bin;     // [tiles_x * tiles_y]
     RasterRec *recs;

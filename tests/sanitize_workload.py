@@ -53,3 +53,22 @@ for k in range(4):
     r.framebuffer_host_async(outs[k % 2].data_ptr())
 r.sync()
 assert np.array_equal(outs[1].numpy().view(np.uint32), o["fb"]); r.close(); print("ok streaming", flush=True)
+# runtime sample counts (generic N-sample tile kernel) and guard-band clipping
+for n in (1, 2, 8):
+    for sc in (scenes.default_scene(1.0, width=W, height=H), scenes.near_clip_scene(20, 10, W, H)):
+        sc.msaa = n
+        msgs = compare(oracle_render(sc), gpu_render(sc, debug=True))
+        assert not msgs, (sc.name, n, msgs)
+print("ok msaa 1/2/8", flush=True)
+for sc in (scenes.clip_test_scene(0.4, width=W, height=H), scenes.near_clip_scene(20, 10, W, H)):
+    sc.guard_band = 3.0
+    msgs = compare(oracle_render(sc), gpu_render(sc, debug=True))
+    assert not msgs, (sc.name, msgs)
+print("ok guard band", flush=True)
+# an async frame that overflows the initial tile bins: rz_sync grows and replays it
+sc = scenes.overdraw_scene(8, 8, width=64, height=64)
+sc.draws = [scenes.Draw(d.mesh, d.world, d.fs) for d in sc.draws] * 40
+r = Renderer(sc.width, sc.height); r.uniforms().bind_texture(0, sc.texture)
+out = torch.zeros((sc.height, sc.width), dtype=torch.int32).pin_memory()
+scenes.render_scene(r, sc); r.framebuffer_host_async(out.data_ptr()); r.sync()
+assert np.array_equal(out.numpy().view(np.uint32), oracle_render(sc)["fb"]); r.close(); print("ok async replay", flush=True)
