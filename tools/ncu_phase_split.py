@@ -16,7 +16,7 @@ k0 = find("__global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel")
 marks = [("prologue", k0), ("tile top / steal", find("for (;;) {", k0)), ("sort + entry load (A0 head)", find("if (n > 0) {", k0)),
          ("wild walk", find("run of items for the literal walk", k0)), ("A0 table + scan", find("chunk of small items", k0)),
          ("direct/budget", find("chunk dominated by large items: pixel-parallel, deferred", k0)),
-         ("A1 coverage+depth", find("phase A1: thread = (item", k0)), ("A1 tail/retry", find("S.nfrag keeps counting past the pool", k0)),
+         ("A1 coverage+depth", find("phase A1: thread = (item", k0)), ("A1 tail/retry", find("S.nfrag keeps counting past the pool", k0)), ("A2 depths", find("phase A2: thread = fragment", k0)),
          ("B replay", find("phase B: thread = pixel", k0)), ("C shade", find("phase C: thread = fragment", k0)),
          ("resolve+store+clear", find("every path through the chunk loop ends with a barrier", k0)), ("epilogue", find("the rest of the tiles nothing was binned into", k0))]
 helpers = [("shade()", find("__device__ __forceinline__ uint32_t shade("), k0)]
