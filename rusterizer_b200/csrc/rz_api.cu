@@ -308,6 +308,7 @@ int rz_create(int device, uint32_t width, uint32_t height, rz_ctx **out) {
     CU_NEW(cudaMalloc(&c->d_state, state_bytes(c)));
     CU_NEW(cudaMemset(c->d_state, 0, state_bytes(c)));
     CU_NEW(cudaMalloc(&c->d_out, (size_t)width * height * sizeof(uint32_t)));
+    CU_NEW(cudaMemset(c->d_out, 0, (size_t)width * height * sizeof(uint32_t))); // rows a screen-space shard does not own are never written
     CU_NEW(cudaMalloc(&c->d_cnt_backup, sizeof(unsigned long long) * 16 * CNT_STRIPES));
     CU_NEW(cudaHostAlloc(&c->h_state, sizeof(FrameState), cudaHostAllocDefault));
     for (int i = 0; i < 4; i++) CU_NEW(cudaEventCreate(&c->ev[i]));
@@ -790,7 +791,10 @@ int rz_framebuffer_host_async(rz_ctx *c, uint32_t *out_host) {
     if (c->sticky != RZ_OK) return c->sticky;
     CU(c, cudaSetDevice(c->device));
     const int p = c->out_parity;
-    if (!c->d_out_ring[p]) CU(c, cudaMalloc(&c->d_out_ring[p], (size_t)c->W * c->H * sizeof(uint32_t)));
+    if (!c->d_out_ring[p]) {
+        CU(c, cudaMalloc(&c->d_out_ring[p], (size_t)c->W * c->H * sizeof(uint32_t)));
+        CU(c, cudaMemsetAsync(c->d_out_ring[p], 0, (size_t)c->W * c->H * sizeof(uint32_t), c->stream));
+    }
     // the image rendered into this buffer two frames ago must have left for the host
     CU(c, cudaStreamWaitEvent(c->stream, c->ev_d2h_done[p], 0));
     int rc = enqueue_frame(c, c->d_out_ring[p], false);
