@@ -857,7 +857,7 @@ def main():
                                  "source": "smsp__inst_executed.sum per kernel from profiles/traffic.json (ncu --set full, same workload)"}
     except Exception:
         pass
-    cb, cb_c1 = None, None
+    cb, cb_c1, other_configs = None, None, []
     if not args.no_cpu_baseline and not tiles_mode and n_gpus == 1:  # rank 0 at N=1 only (bounded sample)
         cb = cpu_baseline(scene, budget_s=args.cpu_budget)
         # BASELINE configs[0]: the crate's default scene (main.rs:93-105, 1280x720, cube + sphere, 268 triangles) -- the config
@@ -876,6 +876,28 @@ def main():
         cb_c1["gpu_ms_per_frame"] = statistics.median(ts[2:])
         cb_c1["gpu_mtris_per_s"] = c1.n_triangles / cb_c1["gpu_ms_per_frame"] / 1e3
         cb_c1["workload"] = "BASELINE configs[0]: default `cargo run --release` scene at elapsed = 1.0 (main.rs:93-105), 1280x720, 4xMSAA"
+        # the other single-GPU BASELINE configs, device-resident meshes, per-stage CUDA events (median of 5 frames): parity
+        # of each at FULL size is tests/test_gpu_fullsize.py; they are reported here so the driver's record carries them
+        for cname, mk in (("configs[2] C3: 250K triangles straddling the near plane, 3840x2160", scenes.near_clip_scene),
+                          ("configs[3] C4(i): 1M-triangle sphere on 8192x8192, one GPU", lambda: scenes.sphere_scene(width=8192, height=8192)),
+                          ("configs[3] C4(ii): clipped full-screen quad on 8192x8192, one GPU", lambda: scenes.fullscreen_quad_scene(8192, 8192))):
+            sc = mk()
+            rc = Renderer(sc.width, sc.height, device=local)
+            rc.uniforms().bind_texture(0, sc.texture)
+            dms = [rc.upload(d.mesh) for d in sc.draws]
+            ts = []
+            for i in range(8):
+                if i == 3:
+                    rc.reset_counters()
+                scenes.render_scene(rc, sc, dms)
+                rc.framebuffer_device()
+                ts.append(rc.timings())
+            t = {k: statistics.median(x[k] for x in ts[3:]) for k in ts[0]}
+            cc = rc.counters()
+            rc.close()
+            other_configs.append({"config": cname, "triangles": sc.n_triangles, "ms": t, "mtris_per_s": sc.n_triangles / t["total_ms"] / 1e3,
+                                  "gsamples_per_s": cc["n_samples_written"] / 5 / t["total_ms"] / 1e6,
+                                  "hbm_floor_frac": sc.algorithmic_bytes() / (t["total_ms"] / 1e3) / 1e9 / peak})
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": Wm,
@@ -899,6 +921,7 @@ def main():
         "tiles": tiles_rec,
         "cpu_baseline": cb,
         "cpu_baseline_c1": cb_c1,
+        "other_configs": other_configs or None,
         "counters_per_frame": cpf,
         "timed": {"blocks_of_K_steps": blocks, "frames": K * blocks, "device_ms": total_ms_max,
                   "block_ms_min_median_max": ([min(block_ms), statistics.median(block_ms), max(block_ms)] if block_ms else None),
