@@ -441,6 +441,9 @@ def main():
     torch.cuda.set_device(local)
     host_binding = bind_host_near_gpu(local, world)  # before any pinned allocation
     if world > 1:
+        # a failed or hung collective must surface as an error: the NCCL watchdog polls ncclCommGetAsyncError and tears the
+        # communicator down instead of letting the ranks spin ("NCCL async error query")
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
 

@@ -76,6 +76,7 @@ class OracleLib:
         L.orc_write_block.argtypes = [C.c_void_p, fp, fp, fp]
         L.orc_set_scissor.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         L.orc_set_msaa.argtypes = [C.c_void_p, C.c_uint32]
+        L.orc_debug_asserts.argtypes = [u64p, C.c_int]
         L.orc_set_guard_band.argtypes = [C.c_void_p, C.c_float]
         L.orc_render.argtypes = [C.c_void_p, fp, fp, C.c_uint32, u32p, C.c_uint64, C.c_uint32, C.c_uint32]
         L.orc_rasterize.argtypes = [C.c_void_p, fp, fp, C.c_uint64, C.c_uint32]
@@ -201,6 +202,19 @@ class OracleLib:
 
     def tile_idx(self, width, row, col):
         return int(self.lib.orc_tile_idx(width, row, col))
+
+
+DEBUG_ASSERTS = ("clamp_bary_range (mod.rs:104)", "ndc_range (mod.rs:319-321)", "z_range (mod.rs:329)",
+                 "texture_uv_range (texture.rs:66-67)", "texel_xy_range (texture.rs:49-50)")
+
+
+def debug_asserts(lib: "OracleLib | None" = None, reset: bool = True) -> dict:
+    """How often each range-guarding debug_assert! of the reference would have fired in a debug build since the last
+    reset (the oracle computes the --release behaviour either way).  Per process and per library instance."""
+    lib = lib or get_lib()
+    out = (C.c_uint64 * 5)()
+    lib.lib.orc_debug_asserts(out, 1 if reset else 0)
+    return dict(zip(DEBUG_ASSERTS, (int(v) for v in out)))
 
 
 _LIBS: dict = {}

@@ -96,6 +96,18 @@ typedef struct orc_ctx {
     size_t vs_cap;
 } orc_ctx;
 
+/* "debug_assert mode" (SURVEY.md section 5): the reference guards value ranges with debug_assert!s that are compiled out of
+ * --release.  The oracle always computes the release behaviour and only COUNTS how often each of them would have fired
+ * in a debug build.  Per process (the static helpers have no context); read and reset with orc_debug_asserts(). */
+enum { DA_CLAMP_BARY, DA_NDC_RANGE, DA_Z_RANGE, DA_TEX_UV, DA_TEXEL_XY, DA_COUNT };
+static uint64_t g_dassert[DA_COUNT];
+void orc_debug_asserts(uint64_t *out5, int reset) {
+    for (int i = 0; i < DA_COUNT; i++) {
+        if (out5) out5[i] = g_dassert[i];
+        if (reset) g_dassert[i] = 0;
+    }
+}
+
 /* ---------------- math subset ---------------- */
 
 /* math/vector.rs:17-23 : sum starts at 0.0, sequential */
@@ -141,6 +153,7 @@ float orc_triangle_2x_area(const float *xy6) {
 
 /* Rust f32::clamp(0.0, 1.0): NaN stays NaN.  rasterizer/mod.rs:102-106 */
 static float clamp_bary(float x) {
+    if (!(x >= 0.0f - 0.0001f && x <= 1.0f + 0.0001f)) g_dassert[DA_CLAMP_BARY]++; /* debug_assert! mod.rs:104 */
     if (x < 0.0f) x = 0.0f;
     if (x > 1.0f) x = 1.0f;
     return x;
@@ -343,6 +356,9 @@ static void viewport_setup(uint32_t width, uint32_t height, const float *ndc12, 
         sx[i] = (float)width * (v[0] + 1.0f) / 2.0f;
         sy[i] = (float)height * (1.0f - (v[1] + 1.0f) / 2.0f);
         sz[i] = (v[2] + 1.0f) * 0.5f * (zmax - zmin) + zmin;
+        for (int a = 0; a < 3; a++)
+            if (!(v[a] <= 1.0f && v[a] >= -1.0f)) g_dassert[DA_NDC_RANGE]++; /* debug_assert! mod.rs:319-321 */
+        if (!(sz[i] >= zmin && sz[i] <= zmax)) g_dassert[DA_Z_RANGE]++;      /* debug_assert! mod.rs:329 */
         r->w[i] = v[3];
     }
     /* v0 = p1-p0, v1 = p2-p1, v2 = p0-p2 ; n_k = (-v_k.y, v_k.x) */
@@ -451,6 +467,7 @@ void orc_pixel_bbox(const float *xy6, uint64_t *out4) {
 /* texture.rs:47-63 + color.rs:22-29.  Out-of-buffer reads (a panic in the
  * reference) are clamped to the last byte and counted. */
 static void read_texel(orc_ctx *c, const tex_t *t, uint64_t x, uint64_t y, float *rgba) {
+    if (!(x < t->w) || !(y < t->h)) g_dassert[DA_TEXEL_XY]++; /* debug_assert! texture.rs:49-50 */
     uint64_t start = x * t->tw + y * t->tw * t->w;
     uint8_t b[4] = {0, 0, 0, 255};
     uint32_t n = t->tw == 4 ? 4 : 3;
@@ -467,6 +484,7 @@ static void read_texel(orc_ctx *c, const tex_t *t, uint64_t x, uint64_t y, float
 
 /* texture.rs:65-83 */
 static void tex_sample(orc_ctx *c, const tex_t *t, float u, float v, float *out) {
+    if (!(u >= 0.0f && u <= 1.0f) || !(v >= 0.0f && v <= 1.0f)) g_dassert[DA_TEX_UV]++; /* debug_assert! texture.rs:66-67 */
     float x = u * (float)(t->w - 1);
     float y = v * (float)(t->h - 1);
     uint64_t x0 = f32_as_usize(floorf(x)), x1 = f32_as_usize(ceilf(x));
@@ -866,7 +884,7 @@ void orc_eval_pixel(const float *screen9, const float *w3, const float *attrs18,
     rtri_from_screen(screen9, w3, attrs18, &r);
     eval_cov(&r, x, y);
     *mask = r.cov_mask;
-    memcpy(evals12, r.cov_eval, sizeof r.cov_eval);
+    memcpy(evals12, r.cov_eval, sizeof(float) * N_MSAA * 3); /* the KAT entry is the reference's 4-sample form */
     fragment_depths(&r, depths4);
     uint8_t m = interp_mask == 0xFF ? r.cov_mask : (uint8_t)interp_mask;
     attr_t a = interpolate(&r, x, y, m);

@@ -3,6 +3,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -prec-div=true -prec-sqrt=true
 //        -ftz=false -Xcompiler -ffp-contract=off ... (see __graft_entry__.build()).
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h> // header-only; ranges are no-ops unless a profiler is attached
 
 #include <algorithm>
 #include <cstdarg>
@@ -547,6 +548,12 @@ static FrameParams make_params(rz_ctx *c, uint32_t *out_base) {
     return P;
 }
 
+// NVTX ranges around the launches of each stage (host side: they bracket the enqueue, tools correlate the kernels).
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 // Enqueue one whole frame on the ctx stream.  timed: record stage events.
 static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     uint64_t total_tris = 0;
@@ -595,6 +602,8 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     }
     if (timed) CU(c, cudaEventRecord(c->ev[0], st));
     uint32_t tri_base = 0, draw_index = 0;
+    NvtxRange frame_range("rz frame");
+    nvtxRangePushA("rz geometry (vertex, geom, clip)");
     for (auto &d : c->draws) {
         const uint32_t nt = (uint32_t)(d.mesh->n_idx / 3);
         const uint32_t this_draw = draw_index++;
@@ -618,7 +627,9 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
         CU(c, launch_pdl(clip_kernel, dim3(ctas), dim3(NT), 0, st, P));
         c->launches++;
     }
+    nvtxRangePop();
     if (timed) CU(c, cudaEventRecord(c->ev[1], st));
+    nvtxRangePushA("rz binning (large_bin, order)");
     CU(c, launch_pdl(large_bin_kernel, dim3(c->num_sms * 2), dim3(NT), 0, st, P));
     c->launches++;
     const uint32_t n_tiles = P.tiles_x * (P.ty_end - P.ty_begin);
@@ -626,8 +637,10 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
         CU(c, launch_pdl(order_kernel, dim3((n_tiles + NT - 1) / NT), dim3(NT), 0, st, P));
         c->launches++;
     }
+    nvtxRangePop();
     if (timed) CU(c, cudaEventRecord(c->ev[2], st));
-    const dim3 tile_grid(std::min<uint32_t>(n_tiles, (uint32_t)c->num_sms * (c->debug ? 3u : 4u))); // persistent CTAs, 4 per SM
+    NvtxRange tile_range("rz tile raster + resolve");
+    const dim3 tile_grid(std::min<uint32_t>(n_tiles, (uint32_t)c->num_sms * (c->debug ? 3u : (uint32_t)RZ_TILE_CTAS))); // persistent CTAs, 4 per SM
     if (n_tiles && c->msaa != 4u) {
         // runtime sample counts other than the reference's 4: the generic pixel-parallel tile kernel (rz_msaa.cuh)
         const dim3 g(std::min<uint32_t>(n_tiles, (uint32_t)c->num_sms * 2u));

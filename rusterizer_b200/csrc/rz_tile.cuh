@@ -263,10 +263,6 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-#ifndef RZ_DEPTH_IN_A1
-#define RZ_DEPTH_IN_A1 0 // 1: covered units compute their sample depths inside phase A1 (no phase A2); measured slower:
-                         // only ~40 % of the lanes of a unit warp are covered, a fragment warp is full
-#endif
 #ifndef RZ_B_REG_MAXFRAG
 #define RZ_B_REG_MAXFRAG 640 // chunks with more fragments (> 2.5 per pixel: overdraw) replay their pixel lists by re-walking
 #endif
@@ -290,12 +286,12 @@ struct TileSmemT {
     uint32_t color[TILE_PX * 4];
     uint32_t okey[DBG ? TILE_PX * 4 : 4]; // owner keys (parity instrumentation only)
     float lut[256];                       // (b as f32) / 255.0   (Color::from_rgba, color.rs:22-29)
-    uint32_t it_key[NT];                  // items of the current chunk: order key (the rank in the list once it is sorted)
-    uint32_t it_rec[NT];                  // record index | tie-break bits << 29
-    uint32_t it_okey[DBG ? NT : 1];       // the triangle's order key as the oracle reports it (parity instrumentation only)
-    uint32_t it_box[NT];                  // lx0 | ly0 << 4 | bw << 8 | ceil(65536 / bw) << 13   (j / bw == (j * rcp) >> 16 for j < 256)
-    float4 it_q0[NT], it_q1[NT];          // the items' records, quarters 0 and 1 (screen points, z0, z1) and the first half of
-    float2 it_q2[NT];                     //   quarter 2 (z2, inv_2x_area): copied asynchronously (cp.async) while phase A0 scans
+    uint32_t it_key[CHUNK + 1];           // items of the current chunk: order key (the rank in the list once it is sorted)
+    uint32_t it_rec[CHUNK + 1];                // record index | tie-break bits << 29
+    uint32_t it_okey[DBG ? CHUNK + 1 : 1];       // the triangle's order key as the oracle reports it (parity instrumentation only)
+    uint32_t it_box[CHUNK + 1];                // lx0 | ly0 << 4 | bw << 8 | ceil(65536 / bw) << 13   (j / bw == (j * rcp) >> 16 for j < 256)
+    float4 it_q0[CHUNK + 1], it_q1[CHUNK + 1];          // the items' records, quarters 0 and 1 (screen points, z0, z1) and the first half of
+    float2 it_q2[CHUNK + 1];                   //   quarter 2 (z2, inv_2x_area): copied asynchronously (cp.async) while phase A0 scans
     uint32_t pre[NT + 1];                 // exclusive prefix of the in-tile box areas (work units)
     uint8_t unit_item[UNIT_CAP];          // work unit -> item
     union {
@@ -516,7 +512,7 @@ __device__ __forceinline__ void clear_empty_tiles(const FrameParams &P, int lane
 }
 
 template <bool DBG, bool EXT, bool DIRECT>
-__global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
+__global__ void __launch_bounds__(NT, DBG ? 3 : RZ_TILE_CTAS) tile_kernel(FrameParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef TileSmemT<DBG> SM;
     SM &S = *reinterpret_cast<SM *>(smem_raw);
@@ -784,10 +780,6 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 for (int u0 = 0; u0 < units; u0 += NT) {
                     const int u = u0 + tid;
                     uint32_t m = 0, p = 0, it = 0;
-#if RZ_DEPTH_IN_A1
-                    float e1s[4], e2s[4]; // edge values 1 and 2 of the four samples (EdgeFunctions.coverage_evaluated)
-                    float z0 = 0.0f, z1 = 0.0f;
-#endif
                     if (u < units) {
                         it = S.unit_item[u];
                         const uint32_t box = S.it_box[it];
@@ -798,9 +790,6 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                         p = (uint32_t)(lpy * TW + lpx);
                         const uint32_t rec_t = S.it_rec[it];
                         const float4 r0 = S.it_q0[it], r1 = S.it_q1[it];
-#if RZ_DEPTH_IN_A1
-                        z0 = r1.z; z1 = r1.w;
-#endif
                         // EdgeFunctions normals (mod.rs:200-205) and the single-compare form of inside() (rz_exact.cuh)
                         const float n0x = -fsub(r0.w, r0.y), n0y = fsub(r0.z, r0.x);
                         const float n1x = -fsub(r1.y, r0.w), n1y = fsub(r1.x, r0.z);
@@ -816,9 +805,6 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                             const float e1 = fadd(fmul(n1x, fsub(xs, r0.z)), fmul(n1y, fsub(ys, r0.w)));
                             const float e2 = fadd(fmul(n2x, fsub(xs, r1.x)), fmul(n2y, fsub(ys, r1.y)));
                             m |= ((e0 >= t0) & (e1 >= t1) & (e2 >= t2)) ? (1u << i) : 0u;
-#if RZ_DEPTH_IN_A1
-                            e1s[i] = e1; e2s[i] = e2;
-#endif
                         }
                     }
                     const uint32_t bal = __ballot_sync(0xffffffffu, m != 0u);
@@ -829,23 +815,6 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                         if (m) {
                             cov_try++;
                             if (slot < POOL) {
-#if RZ_DEPTH_IN_A1
-                                // RasterizerTriangle::fragment (mod.rs:225-253): the covered samples' depths from the edge
-                                // values of the coverage evaluation.  Vector::dot starts its sum at 0.0 (vector.rs:17-23),
-                                // which only turns a -0.0 edge value into +0.0: `+ 0.0f` restores exactly that.
-                                const float2 r2 = S.it_q2[it];
-                                const float z2 = r2.x, inv = r2.y;
-                                float zz[4];
-#pragma unroll
-                                for (int i = 0; i < 4; i++) {
-                                    const float b0 = clamp01(fmul(fadd(e1s[i], 0.0f), inv));
-                                    const float b1 = clamp01(fmul(fadd(e2s[i], 0.0f), inv));
-                                    const float b2 = clamp01(fsub(fsub(1.0f, b0), b1));
-                                    const float z = fadd(fadd(fmul(b0, z0), fmul(b1, z1)), fmul(b2, z2));
-                                    zz[i] = ((m >> i) & 1u) ? z : 0.0f;
-                                }
-                                S.u.fr.z[slot] = make_float4(zz[0], zz[1], zz[2], zz[3]);
-#endif
                                 S.u.fr.meta[slot] = it | (p << 8) | (m << 16);
                                 S.u.fr.next[slot] = (uint16_t)atomicExch(&S.head[p], slot);
                             } else {
@@ -894,7 +863,6 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
             }
             RZ_STAMP(1) // A1 done
             const int nfrag = (int)S.nfrag;
-#if !RZ_DEPTH_IN_A1
             // ---- phase A2: thread = fragment; the covered samples' depths (RasterizerTriangle::fragment, mod.rs:225-253),
             // every lane busy (in phase A1 only ~40 % of the units are covered)
             for (int f = tid; f < nfrag; f += NT) {
@@ -920,7 +888,6 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
                 S.u.fr.z[f] = make_float4(zz[0], zz[1], zz[2], zz[3]);
             }
             __syncthreads();
-#endif
             RZ_STAMP(2) // sample depths done
             // ---- phase B: thread = pixel; replay this pixel's fragments in submission order ----
             // (depth test exactly as Rasterizer::depth_coverage + write_pixel, mod.rs:363-397); the last writer
@@ -1148,6 +1115,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel(FrameParams P) {
     }
 }
 
-static_assert(4 * (sizeof(TileSmemT<false>) + 1024) <= 227 * 1024, "tile kernel must fit 4 CTAs per SM");
+static_assert(RZ_TILE_CTAS * (sizeof(TileSmemT<false>) + 1024) <= 227 * 1024, "tile kernel must fit RZ_TILE_CTAS CTAs per SM");
+static_assert(CHUNK <= 255 && POOL <= 65535 && UNIT_CAP <= 65535, "item ids are bytes, fragment and unit ids 16 bits");
 
 } // namespace rz

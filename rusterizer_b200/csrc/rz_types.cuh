@@ -8,9 +8,18 @@ constexpr int TW = 16;              // screen tile width  (pixels)
 constexpr int TH = 16;              // screen tile height (pixels)
 constexpr int TILE_PX = TW * TH;    // 256 = threads per tile CTA
 constexpr int NT = 256;             // threads per CTA in every kernel
-constexpr int CHUNK = 255;          // items per triangle-parallel chunk (item id fits u8, 0xFF = none)
-constexpr int UNIT_CAP = 6144;      // (item, pixel) work units per chunk (one byte each in shared memory)
-constexpr int POOL = 1024;          // per-chunk fragment records held in shared memory
+#ifndef RZ_CHUNK
+#define RZ_CHUNK 255
+#endif
+constexpr int CHUNK = RZ_CHUNK;     // items per triangle-parallel chunk (item id fits u8, 0xFF = none; <= 255)
+#ifndef RZ_UNIT_CAP
+#define RZ_UNIT_CAP 6144
+#endif
+constexpr int UNIT_CAP = RZ_UNIT_CAP; // (item, pixel) work units per chunk (one byte each in shared memory)
+#ifndef RZ_POOL
+#define RZ_POOL 1024
+#endif
+constexpr int POOL = RZ_POOL;       // per-chunk fragment records held in shared memory
 #ifndef RZ_DIRECT_MIN_AREA
 #define RZ_DIRECT_MIN_AREA 192
 #endif
@@ -54,6 +63,9 @@ enum {
 // Device-side frame bookkeeping.  `counters` and `err` persist across frames (read by rz_counters /
 // rz_sync); everything from `n_records` on, and tile_count[] which follows in the same allocation,
 // is zeroed by one memset at the start of every frame.
+#ifndef RZ_TILE_CTAS
+#define RZ_TILE_CTAS 4 // resident tile CTAs per SM (64 registers, 55 KB shared memory each)
+#endif
 constexpr int ORDER_BUCKETS = 8; // busy tiles are handed out longest-list-first in 8 classes
 constexpr int REC_STRIPES = 64; // record slots are handed out from per-stripe cursors (CTA id % stripes):
                                 // one hot cursor would serialise ~10^4 same-address atomics in L2

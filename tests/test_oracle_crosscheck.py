@@ -240,3 +240,20 @@ def test_guard_band_clipping(guard):
         # same picture: only pixels on a checkerboard edge (where the last bit of u, v picks the texel) may change visibly
         assert (np.abs(a - b).reshape(sc.height, sc.width, 4).max(-1) > 2).mean() < 0.01
         assert ((ref["fb"] != 0xFF191919) == (o["fb"] != 0xFF191919)).mean() > 0.999
+
+
+def test_oracle_debug_assert_mode():
+    """the reference's range debug_assert!s are compiled out of --release; the oracle reports how often
+    each would have fired in a debug build.  The crate's own scenes are clean; a guard band deliberately leaves the
+    [-1, 1] NDC range (mod.rs:319-321), and attributes of a (1, 1, x) pattern push u past 1.0."""
+    from oracle.oracle import debug_asserts
+
+    debug_asserts()
+    oracle_render(scenes.default_scene(1.0, width=160, height=90))
+    oracle_render(scenes.sphere_scene(33, 17, width=160, height=90))
+    clean = debug_asserts()
+    assert clean["ndc_range (mod.rs:319-321)"] == 0 and clean["z_range (mod.rs:329)"] == 0 and clean["texel_xy_range (texture.rs:49-50)"] == 0
+    sc = scenes.clip_test_scene(0.7, width=128, height=72)
+    sc.guard_band = 4.0
+    oracle_render(sc)
+    assert debug_asserts()["ndc_range (mod.rs:319-321)"] > 0
