@@ -827,7 +827,10 @@ def main():
         "bound": "hbm", "kernel": f"{dom}_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic,
         "traffic_source": {"measured_in_run": False, "what": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel from one "
-                           "ncu --set full capture of the same command (profiles/traffic.json)", "capture_commit": (tj or {}).get("_commit")},
+                           "ncu --set full capture of the same command (profiles/traffic.json); ncu flushes the caches before the "
+                           "launch, so the bin entries (16 B), raster records (48 B) and shade records (32 B) the geometry stage has "
+                           "just written are counted as DRAM reads here, while in a running frame they are L2 hits",
+                           "capture_commit": (tj or {}).get("_commit")},
         "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
         "algorithmic_bytes_per_launch": alg[dom], "kernel_ms": kt[dom],
         "kernel_ms_all": stage_avg, "kernel_share_of_frame": kt[dom] / max(stage_avg["total_ms"], 1e-9),
@@ -846,7 +849,10 @@ def main():
     fp32_peak = 148 * 128 * sm_mhz * 1e6 / 1e12
     roofline["fp32"] = {"algorithmic_gflop_per_frame": f_alg / 1e9, "achieved": f_alg / (ms_per_step / 1e3) / 1e12,
                         "peak": fp32_peak, "unit": "TFLOP/s (non-FMA f32)", "frac": f_alg / (ms_per_step / 1e3) / 1e12 / fp32_peak,
-                        "formula": "28*Nv + 40*Nt_in + 60*Nt_setup + 72*N_bbox_px + 30*N_samples + 180*N_shaded_px (texture FS)"}
+                        "formula": "28*Nv + 40*Nt_in + 60*Nt_setup + 72*N_bbox_px + 30*N_samples + 180*N_shaded_px (texture FS)",
+                        "note": "the reference's arithmetic, not the GPU's: 72 flops per bbox pixel are credited for EVERY triangle, "
+                                "also the back-facing ones (62 % of this frame's bbox pixels) that the GPU path culls exactly without "
+                                "walking them; the useful flops actually executed are about half of the numerator"}
     # third reading: the issue-slot roofline.  ncu counted the warp instructions one C2 frame executes (all kernels,
     # profiles/traffic.json); a B200 issues at most 148 SMs x 4 schedulers x clock of them per second.
     try:
