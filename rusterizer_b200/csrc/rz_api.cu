@@ -673,6 +673,15 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     return RZ_OK;
 }
 
+// Which tile-kernel instantiation the NEXT frame runs: the one with the large-item / short-list paths when the last frame
+// whose state the host has seen queued large triangles or had mostly tiles with a handful of items (a stale guess only
+// costs speed -- every instantiation is correct for every input).
+static bool wants_direct(const FrameState *fs) {
+    uint32_t busy = 0;
+    for (int b = 0; b < ORDER_BUCKETS; b++) busy += fs->bucket_n[b];
+    return fs->n_large > 0 || (busy > 0 && fs->n_few_tiles * 2u >= busy);
+}
+
 static void end_frame(rz_ctx *c) {
     c->draws.clear();
     if (c->staging_used) c->parity ^= 1;
@@ -735,7 +744,7 @@ int rz_framebuffer(rz_ctx *c, uint32_t *out_host, const uint32_t **out_device) {
         CU(c, cudaMemcpyAsync(c->h_state, dfs, sizeof(FrameState), cudaMemcpyDeviceToHost, st));
         CU(c, cudaStreamSynchronize(st));
         const uint32_t flags = c->h_state->err;
-        c->use_direct = c->h_state->n_large > 0;
+        c->use_direct = wants_direct(c->h_state);
         if (!flags) break;
         CU(c, cudaMemsetAsync(&dfs->err, 0, sizeof(uint32_t), st));
         if (flags & ERR_INDEX) {
@@ -834,7 +843,7 @@ int rz_sync(rz_ctx *c) {
     CU(c, cudaMemcpyAsync(c->h_state, dfs, sizeof(FrameState), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaStreamSynchronize(c->down_stream));
-    c->use_direct = c->h_state->n_large > 0;
+    c->use_direct = wants_direct(c->h_state);
     const uint32_t pending = c->async_pending;
     c->async_pending = 0;
     if (c->h_state->peer_timeout) {

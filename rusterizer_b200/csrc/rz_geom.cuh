@@ -559,6 +559,10 @@ __global__ void __launch_bounds__(NT) order_kernel(FrameParams P) {
     const uint32_t tile = P.ty_begin * P.tiles_x + i;
     const uint32_t n = P.tile_count[tile];
     if (n == 0u) return;
+    {   // how many tiles hold only a few items (the host picks the tile-kernel instantiation with the short-list walk by it)
+        const unsigned few = __ballot_sync(__activemask(), n <= (uint32_t)FAST_N);
+        if (few && (threadIdx.x & 31) == (unsigned)(__ffs(few) - 1)) atomicAdd(&P.fs->n_few_tiles, (uint32_t)__popc(few));
+    }
     const uint32_t b = order_class(n);
     const unsigned peers = __match_any_sync(__activemask(), b);
     const int leader = __ffs(peers) - 1;

@@ -511,6 +511,104 @@ __device__ __forceinline__ void clear_empty_tiles(const FrameParams &P, int lane
     }
 }
 
+// Tiles whose whole list has at most FAST_N items (full-screen quads, cube faces, the 8192^2 frames whose triangles span
+// several tiles each): no item table, no scan, no fragment pool and a single barrier.  Every thread reads the few bin
+// entries itself (uniform addresses: one transaction per warp), ranks them by order key, keeps its pixel's four
+// samples in registers and applies the items in submission order -- exact coverage, sample depths, strict-< depth test
+// (the literal sequence of rasterizer/mod.rs:443-473) -- with deferred shading: each surviving owner is shaded once.
+// Returns false (nothing touched) when an item needs the literal walk.  The final samples are left in the thread's own
+// words of S.depth / S.color / S.okey for the common epilogue.
+template <bool DBG, bool EXT>
+__device__ __forceinline__ bool fast_tile(const FrameParams &P, TileSmemT<DBG> &S, const uint4 *bin, int n, int X, int Y, uint32_t &c_cov,
+                                          uint32_t &c_shaded, uint32_t &c_samples, uint32_t &c_oob) {
+    const int tid = threadIdx.x, lx = tid % TW, ly = tid / TW;
+    static_assert(FAST_N <= 4, "the entries are ordered by a 4-element network");
+    uint4 e[4];
+    uint32_t anyw = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        e[i] = i < n ? __ldcg(bin + i) : make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+        if (i < n) anyw |= e[i].z;
+    }
+    if (anyw & ENTRY_WILD) return false;
+    // submission order: bubble the (at most four) entries by key; uniform across the CTA, all in registers
+#define RZ_CXE(a, b) { if (e[b].x < e[a].x) { const uint4 t_ = e[a]; e[a] = e[b]; e[b] = t_; } }
+    RZ_CXE(0, 1) RZ_CXE(2, 3) RZ_CXE(0, 2) RZ_CXE(1, 3) RZ_CXE(1, 2)
+#undef RZ_CXE
+    float4 d = make_float4(CLEAR_DEPTH, CLEAR_DEPTH, CLEAR_DEPTH, CLEAR_DEPTH);
+    uint32_t own = 0xFFFFFFFFu; // 4 x u8: item that owns sample k (0xFF: untouched)
+    uint32_t omp = 0u;          // 4 x 5 bits: that fragment's post-depth mask | (sample 0 covered) << 4
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+        if (it >= n) break;
+        const uint32_t boxw = e[it].z;
+        const uint32_t rx = (uint32_t)lx - (boxw & 15u), ry = (uint32_t)ly - ((boxw >> 4) & 15u);
+        if (rx > ((boxw >> 8) & 15u) || ry > ((boxw >> 12) & 15u)) continue; // outside the in-tile box
+        const float4 *rr = reinterpret_cast<const float4 *>(&P.recs[e[it].y & ENTRY_REC_MASK]);
+        const float4 r0 = rr[0], r1 = rr[1];
+        Setup q;
+        q.px[0] = r0.x; q.py[0] = r0.y; q.px[1] = r0.z; q.py[1] = r0.w; q.px[2] = r1.x; q.py[2] = r1.y;
+        setup_normals(q);
+        float thr[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) thr[k] = ((e[it].y >> (29 + k)) & 1u) ? 0.0f : 1.401298464e-45f;
+        const uint32_t m = coverage_mask_fast(q, thr, X, Y);
+        if (!m) continue;
+        c_cov++;
+        const float4 r2 = rr[2];
+        q.z[0] = r1.z; q.z[1] = r1.w; q.z[2] = r2.x;
+        q.inv = r2.y;
+        uint32_t mp = 0;
+        if (m & 1u) { const float z = sample_depth(q, X, Y, 0); if (z < d.x) { d.x = z; mp |= 1u; } } // strict < (mod.rs:374)
+        if (m & 2u) { const float z = sample_depth(q, X, Y, 1); if (z < d.y) { d.y = z; mp |= 2u; } }
+        if (m & 4u) { const float z = sample_depth(q, X, Y, 2); if (z < d.z) { d.z = z; mp |= 4u; } }
+        if (m & 8u) { const float z = sample_depth(q, X, Y, 3); if (z < d.w) { d.w = z; mp |= 8u; } }
+        if (!mp) continue;
+        c_shaded++;
+        c_samples += __popc(mp);
+        const uint32_t tag = mp | ((m & 1u) << 4);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if ((mp >> k) & 1u) {
+                own = (own & ~(0xFFu << (8 * k))) | ((uint32_t)it << (8 * k));
+                omp = (omp & ~(0x1Fu << (5 * k))) | (tag << (5 * k));
+            }
+    }
+    *reinterpret_cast<float4 *>(&S.depth[tid * 4]) = d;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t it = (own >> (8 * k)) & 0xFFu;
+        if (it == 0xFFu) continue;
+        bool first = true; // shade every surviving owner once (MSAA: one shader call per fragment)
+#pragma unroll
+        for (int j = 0; j < k; j++) first = first && ((own >> (8 * j)) & 0xFFu) != it;
+        if (!first) continue;
+        const uint32_t tag = (omp >> (5 * k)) & 0x1Fu;
+        const uint4 ei = it == 0u ? e[0] : (it == 1u ? e[1] : (it == 2u ? e[2] : e[3]));
+        const uint32_t rec = ei.y & ENTRY_REC_MASK;
+        const float4 *rr = reinterpret_cast<const float4 *>(&P.recs[rec]);
+        const float4 r0 = rr[0], r1 = rr[1];
+        Setup q;
+        q.px[0] = r0.x; q.py[0] = r0.y; q.px[1] = r0.z; q.py[1] = r0.w; q.px[2] = r1.x; q.py[2] = r1.y;
+        setup_normals(q);
+        float depth0 = 0.0f; // FragCoords.depths[0] (mod.rs:458-463)
+        if (tag & 16u) {
+            const float4 r2 = rr[2];
+            q.z[0] = r1.z; q.z[1] = r1.w; q.z[2] = r2.x;
+            q.inv = r2.y;
+            depth0 = sample_depth(q, X, Y, 0);
+        }
+        const uint32_t argb = shade<DBG, EXT>(P, q, rec, S.lut, X, Y, tag & 0xFu, depth0, c_oob);
+#pragma unroll
+        for (int j = k; j < 4; j++)
+            if (((own >> (8 * j)) & 0xFFu) == it) {
+                S.color[tid * 4 + j] = argb;
+                if (DBG) S.okey[tid * 4 + j] = ei.x;
+            }
+    }
+    return true;
+}
+
 template <bool DBG, bool EXT, bool DIRECT>
 __global__ void __launch_bounds__(NT, DBG ? 3 : RZ_TILE_CTAS) tile_kernel(FrameParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -583,7 +681,12 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : RZ_TILE_CTAS) tile_kernel(FrameP
         if (DBG) S.okey[tid * 4 + k] = NO_OWNER;
     }
 
-    if (n > 0) {
+    bool fast_done = false;
+    if (DIRECT && n > 0 && n <= FAST_N && !wild) {
+        fast_done = fast_tile<DBG, EXT>(P, S, P.bins + bin_off, n, X, Y, c_cov, c_shaded, c_samples, c_oob);
+        __syncthreads(); // every thread has read S.ent (thread 0 overwrites it at the end of the trip)
+    }
+    if (n > 0 && !fast_done) {
         S.head[tid] = FR_NONE;
         uint4 *bin = P.bins + bin_off;
         bool sorted = false;  // the list is in submission order
@@ -1031,7 +1134,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : RZ_TILE_CTAS) tile_kernel(FrameP
             pos += cnt;
         }
     }
-    else __syncthreads(); // (a busy tile never has an empty list; keeps the hand-over below safe if it ever did)
+    else if (!fast_done) __syncthreads(); // (a busy tile never has an empty list; keeps the hand-over below safe if it ever did)
     // every path through the chunk loop ends with a barrier: all threads have read S.ent long ago
     uint4 ent_next = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) ent_next = load_entry(atomicAdd(&P.fs->tile_cursor, 1u)); // issued here, consumed at the end of the trip

@@ -24,6 +24,10 @@ constexpr int POOL = RZ_POOL;       // per-chunk fragment records held in shared
 #define RZ_DIRECT_MIN_AREA 192
 #endif
 constexpr int DIRECT_MIN_AREA = RZ_DIRECT_MIN_AREA; // average in-tile bbox (pixels) from which a chunk is walked pixel-parallel
+#ifndef RZ_FAST_N
+#define RZ_FAST_N 2
+#endif
+constexpr int FAST_N = RZ_FAST_N;           // tiles with at most this many items are walked pixel-parallel straight from their bin
 constexpr int SORT_CAP = 2048;      // tile lists up to this length are sorted in shared memory
 constexpr int GEOM_SMALL_DIM = 16;  // bbox extent up to which a triangle is binned directly (spans at most 2x2 tiles)
 #ifndef RZ_GEOM_THIN_PX
@@ -81,7 +85,8 @@ struct FrameState {
     uint32_t large_next;  // work-stealing cursor of the large binning kernel
     uint32_t has_wild;    // a triangle with NaN / inf / absurd screen coordinates was emitted (tile stage: literal walk)
     uint32_t tile_cursor; // work-stealing cursor of the tile kernel
-    uint32_t pad1[2];
+    uint32_t n_few_tiles; // busy tiles whose list has at most FAST_N items (order_kernel): they take the barrier-free walk
+    uint32_t pad1;
     uint32_t rec_cursor[REC_STRIPES]; // emitted (post-clip, post-cull) triangles per stripe
     uint32_t bucket_n[ORDER_BUCKETS]; // non-empty tiles per list-length class (class 0 = longest lists)
 };
