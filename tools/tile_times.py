@@ -3,7 +3,7 @@ import numpy as np
 from rusterizer_b200 import scenes
 from rusterizer_b200.render import Renderer
 which = os.environ.get('RZ_SCENE', 'c2')
-sc = {'c2': scenes.sphere_scene, 'c4ii': scenes.fullscreen_quad_scene, 'c3': scenes.near_clip_scene, 'c1': scenes.default_scene, 'overdraw': scenes.overdraw_scene}[which]()
+sc = {'c2': scenes.sphere_scene, 'c4ii': scenes.fullscreen_quad_scene, 'c4i': lambda: scenes.sphere_scene(width=8192, height=8192), 'c3': scenes.near_clip_scene, 'c1': scenes.default_scene, 'overdraw': scenes.overdraw_scene}[which]()
 r = Renderer(sc.width, sc.height); r.uniforms().bind_texture(0, sc.texture)
 dm = [r.upload(d.mesh) for d in sc.draws]
 r.debug_capture(True)
