@@ -546,9 +546,13 @@ def main():
             rj, sj, bj, mj = lanes[j]
             while len(mj) < copies:
                 mj.append(rj.upload(mesh))
-            bj.view = views[0]
-            rj.render(mj[0], 0, 0)
-            rj.framebuffer_device()  # sizes the device buffers
+            # size the device buffers through the synchronous path (it grows and replays) on a spread of the views this
+            # lane will render: the async frames of the timed region must never outgrow them
+            for v in sorted({0, len(views) // 7, 2 * len(views) // 7, 3 * len(views) // 7, 4 * len(views) // 7, 5 * len(views) // 7,
+                             6 * len(views) // 7, len(views) - 1} if n_gpus > 1 else {0}):
+                bj.view = views[v]
+                rj.render(mj[0], 0, 0)
+                rj.framebuffer_device()
             for w in range(max(Wm, len(mj))):
                 bj.view = views[w % len(views)]
                 rj.render(mj[w % len(mj)], 0, 0)

@@ -78,6 +78,8 @@ struct rz_ctx {
     TileBin *d_tile_bin = nullptr;    // [tiles] {first entry, capacity}
     uint64_t bins_cap = 0;            // entries allocated in d_bins
     bool bins_planned = false;
+    std::vector<TileBin> bin_plan;    // host copy of the plan: capacities only ever grow (alternating scenes converge)
+    uint64_t bin_floor = 0;
     RasterRec *d_recs = nullptr;
     unsigned long long *d_clipq = nullptr;
     ShadeRec *d_shade = nullptr;
@@ -211,16 +213,19 @@ static int plan_bins(rz_ctx *c, const uint32_t *counts) {
     const size_t tiles = (size_t)c->tiles_x * c->tiles_y;
     std::vector<TileBin> plan(tiles);
     const uint64_t budget_per_tile = std::max<uint64_t>(32, BIN_BUDGET / sizeof(uint4) / tiles);
-    uint64_t floor_cap = std::min<uint64_t>(256, budget_per_tile);
+    uint64_t floor_cap = std::max<uint64_t>(c->bin_floor, std::min<uint64_t>(256, budget_per_tile));
     if (counts) {
         uint32_t mx = 0;
         for (size_t t = 0; t < tiles; t++) mx = std::max(mx, counts[t]);
         floor_cap = std::max<uint64_t>(floor_cap, std::min<uint64_t>((uint64_t)mx * 5 / 4 + 64, budget_per_tile));
     }
+    c->bin_floor = floor_cap;
+    const bool have_old = c->bin_plan.size() == tiles;
     uint64_t off = 0;
     for (size_t t = 0; t < tiles; t++) {
         uint64_t cap = floor_cap;
         if (counts) cap = std::max<uint64_t>(cap, (uint64_t)counts[t] * 3 / 2 + 64);
+        if (have_old) cap = std::max<uint64_t>(cap, c->bin_plan[t].cap); // never shrink: frames that alternate converge
         if (off + cap > 0xFFFFFFFFull) return fail(c, RZ_E_NOMEM, "the tile bins of this frame need more than 2^32 entries");
         plan[t].off = (uint32_t)off;
         plan[t].cap = (uint32_t)cap;
@@ -234,7 +239,8 @@ static int plan_bins(rz_ctx *c, const uint32_t *counts) {
     }
     if (!c->d_tile_bin) CU(c, cudaMalloc(&c->d_tile_bin, tiles * sizeof(TileBin)));
     CU(c, cudaMemcpyAsync(c->d_tile_bin, plan.data(), tiles * sizeof(TileBin), cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream)); // `plan` is pageable and dies with this call
+    CU(c, cudaStreamSynchronize(c->stream)); // pageable source: complete before it is touched again
+    c->bin_plan.swap(plan);
     c->bins_planned = true;
     return RZ_OK;
 }
