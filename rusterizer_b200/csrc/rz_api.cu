@@ -6,6 +6,7 @@
 #include <nvtx3/nvToolsExt.h> // header-only; ranges are no-ops unless a profiler is attached
 
 #include <algorithm>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -121,6 +122,11 @@ struct rz_ctx {
 };
 
 static thread_local std::string g_err;
+
+// Live contexts: rz_mesh_destroy has to drop a ctx's remembered async frame when it references the mesh (the replay of
+// rz_sync must never touch a destroyed mesh), and a mesh may outlive its ctx.
+static std::mutex g_ctx_mutex;
+static std::vector<rz_ctx *> g_ctxs;
 
 // Launch with programmatic stream serialization (PDL): see pdl_wait() in rz_exact.cuh.
 template <typename... KArgs, typename... Args>
@@ -342,12 +348,20 @@ int rz_create(int device, uint32_t width, uint32_t height, rz_ctx **out) {
         for (auto &e : km) CU_NEW(cudaFuncSetAttribute(e.f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem));
     }
 #undef CU_NEW
+    {
+        std::lock_guard<std::mutex> lock(g_ctx_mutex);
+        g_ctxs.push_back(c);
+    }
     *out = c;
     return RZ_OK;
 }
 
 void rz_destroy(rz_ctx *c) {
     if (!c) return;
+    {
+        std::lock_guard<std::mutex> lock(g_ctx_mutex);
+        g_ctxs.erase(std::remove(g_ctxs.begin(), g_ctxs.end(), c), g_ctxs.end());
+    }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->up_stream) cudaStreamSynchronize(c->up_stream);
@@ -466,6 +480,16 @@ int rz_mesh_create(rz_ctx *c, const float *positions, const float *attributes, u
 
 void rz_mesh_destroy(rz_mesh *m) {
     if (!m) return;
+    {   // a remembered async frame that draws this mesh can no longer be replayed
+        std::lock_guard<std::mutex> lock(g_ctx_mutex);
+        for (rz_ctx *c : g_ctxs)
+            for (const DrawCmd &d : c->last_async.draws)
+                if (d.mesh == m) {
+                    c->last_async.valid = false;
+                    c->last_async.draws.clear();
+                    break;
+                }
+    }
     cudaSetDevice(m->device);
     cudaFree(m->d_pos); cudaFree(m->d_attr); cudaFree(m->d_idx);
     delete m;

@@ -367,6 +367,18 @@ def test_async_overflow_is_replayed_by_sync():
     r.framebuffer_host_async(outs[0].data_ptr())
     r.sync()
     assert np.array_equal(outs[0].numpy().view(np.uint32), o["fb"])
+    # a mesh destroyed between the async frame and rz_sync: the frame cannot be replayed, rz_sync says so (no crash)
+    r2 = Renderer(s.width, s.height)
+    r2.uniforms().bind_texture(0, s.texture)
+    dms = [r2.upload(d.mesh) for d in s.draws]
+    scenes.render_scene(r2, s, dms)
+    r2.framebuffer_async()
+    for m in dms:
+        m.close()
+    with pytest.raises(RzError) as e:
+        r2.sync()
+    assert e.value.code == -6
+    r2.close()
     # discard: recorded draws are dropped, the next frame is just the clear colour
     scenes.render_scene(r, s)
     r.discard_frame()
