@@ -670,7 +670,8 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     nvtxRangePop();
     if (timed) CU(c, cudaEventRecord(c->ev[2], st));
     NvtxRange tile_range("rz tile raster + resolve");
-    const dim3 tile_grid(std::min<uint32_t>(n_tiles, (uint32_t)c->num_sms * (c->debug ? 3u : (uint32_t)RZ_TILE_CTAS))); // persistent CTAs, 4 per SM
+    static const float tune_tile = getenv("RZ_TUNE_TILE_CTAS_PER_SM") ? (float)atof(getenv("RZ_TUNE_TILE_CTAS_PER_SM")) : (float)RZ_TILE_CTAS;
+    const dim3 tile_grid(std::min<uint32_t>(n_tiles, c->debug ? (uint32_t)c->num_sms * 3u : (uint32_t)((float)c->num_sms * tune_tile))); // persistent CTAs, 4 per SM
     if (n_tiles && c->msaa != 4u) {
         // runtime sample counts other than the reference's 4: the generic pixel-parallel tile kernel (rz_msaa.cuh)
         const dim3 g(std::min<uint32_t>(n_tiles, (uint32_t)c->num_sms * 2u));
