@@ -24,6 +24,10 @@
 
 using namespace rz;
 
+#ifndef RZ_LARGE_BIN_CTAS
+#define RZ_LARGE_BIN_CTAS 2 // CTAs per SM of the large-triangle binning kernel
+#endif
+
 struct rz_mesh {
     rz_ctx *ctx;
     int device = 0; // kept here too: a mesh may be destroyed after its ctx
@@ -99,6 +103,7 @@ struct rz_ctx {
     uint32_t rec_cap = 0, large_cap = 0;
     bool debug = false;
     bool use_direct = true; // tile-kernel instantiation with the large-item path (see enqueue_frame)
+    uint32_t last_n_large = 0; // large-triangle binning work items of the last frame the host has seen (sizes that kernel's grid)
     // The last frame issued through an async entry point, kept so that rz_sync can grow the device buffers and replay it
     // when it turns out to have overflowed them (an async call cannot know: the cursors live on the device).
     struct AsyncFrame {
@@ -660,7 +665,9 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     nvtxRangePop();
     if (timed) CU(c, cudaEventRecord(c->ev[1], st));
     nvtxRangePushA("rz binning (large_bin, order)");
-    CU(c, launch_pdl(large_bin_kernel, dim3(c->num_sms * 2), dim3(NT), 0, st, P));
+    // two CTAs per SM keep the launch cheap for frames without large triangles; a frame like the last one with
+    // thousands of (triangle, slab) items gets the full five (48 registers)
+    CU(c, launch_pdl(large_bin_kernel, dim3(c->num_sms * (c->last_n_large > 4096u ? 5 : RZ_LARGE_BIN_CTAS)), dim3(NT), 0, st, P));
     c->launches++;
     const uint32_t n_tiles = P.tiles_x * (P.ty_end - P.ty_begin);
     if (n_tiles) {
@@ -776,6 +783,7 @@ int rz_framebuffer(rz_ctx *c, uint32_t *out_host, const uint32_t **out_device) {
         CU(c, cudaStreamSynchronize(st));
         const uint32_t flags = c->h_state->err;
         c->use_direct = wants_direct(c->h_state);
+        c->last_n_large = c->h_state->n_large;
         if (!flags) break;
         CU(c, cudaMemsetAsync(&dfs->err, 0, sizeof(uint32_t), st));
         if (flags & ERR_INDEX) {
@@ -875,6 +883,7 @@ int rz_sync(rz_ctx *c) {
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaStreamSynchronize(c->down_stream));
     c->use_direct = wants_direct(c->h_state);
+    c->last_n_large = c->h_state->n_large;
     const uint32_t pending = c->async_pending;
     c->async_pending = 0;
     if (c->h_state->peer_timeout) {

@@ -184,7 +184,7 @@ __device__ __forceinline__ void emit_setup(const FrameParams &P, const DrawParam
     sr[0] = make_uint4((D.fs & 3u) | (ca ? 4u : 0u) | (((D.fs >> 8) & 31u) << 3) | (D.draw << 8), ca ? clip_attr : i0, i1, i2);
     sr[1] = make_uint4(__float_as_uint(s.w[0]), __float_as_uint(s.w[1]), __float_as_uint(s.w[2]), 0u);
     const uint32_t rec_tie = rec | (tie_bits(s) << 29);
-    const uint32_t wild_bit = tame ? 0u : ENTRY_WILD;
+    const uint32_t wild_bit = (tame ? 0u : ENTRY_WILD) | (0xFFu << ENTRY_BLOCKS_SHIFT); // small triangles: every block may be covered
 
     if (small) {
 #pragma unroll
@@ -520,6 +520,16 @@ __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
         b.y1 = min(b.y1, P.row_end);
         const uint32_t rec_tie = li.rec | (tie_bits(s) << 29);
         const uint32_t wild_bit = setup_is_tame(s) ? 0u : ENTRY_WILD;
+        // Block masks pay for slivers (a thin triangle crossing a tile touches about half of its 8x4 blocks); a fat
+        // triangle covers nearly all blocks of the tiles it touches, so its entries simply carry 0xFF.  Heuristic only:
+        // any mask that includes every block the triangle can cover is correct.
+        bool sliver;
+        {
+            const float a2 = fabsf(cross2(fsub(s.px[1], s.px[0]), fsub(s.py[1], s.py[0]), fsub(s.px[2], s.px[0]), fsub(s.py[2], s.py[0])));
+            const float bw_f = fmaxf(fmaxf(s.px[0], s.px[1]), s.px[2]) - fminf(fminf(s.px[0], s.px[1]), s.px[2]);
+            const float bh_f = fmaxf(fmaxf(s.py[0], s.py[1]), s.py[2]) - fminf(fminf(s.py[0], s.py[1]), s.py[2]);
+            sliver = a2 < RZ_SLIVER_FRAC * bw_f * bh_f; // area2 / 2 against a fraction of the bounding box area
+        }
         const uint32_t tx0 = b.x0 / TW, tx1 = (b.x1 - 1) / TW + 1, ntx = tx1 - tx0;
         const uint32_t total = ntx * (li.ty1 - li.ty0);
         for (uint32_t t = lane; t < total; t += 32) {
@@ -539,7 +549,37 @@ __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
                 const float cy = s.ny[k] >= 0.0f ? sy_hi : sy_lo;
                 keep = keep && edge_pass(edge_eval(s, k, cx, cy), s.nx[k], s.ny[k]);
             }
-            if (keep) push_bin(P, ty * P.tiles_x + tx, li.key, rec_tie, tile_box(b.x0, b.x1, b.y0, b.y1, tx, ty) | wild_bit);
+            if (!keep) continue;
+            // a tile every sample of which is inside (all three edges pass at their LEAST favourable corner; monotone
+            // again) needs no block tests: the interior tiles of a large triangle
+            bool full = true; // fat triangles: every block of a touched tile may be covered
+#pragma unroll
+            for (int k = 0; k < 3 && sliver; k++) {
+                const float cx = s.nx[k] >= 0.0f ? sx_lo : sx_hi;
+                const float cy = s.ny[k] >= 0.0f ? sy_lo : sy_hi;
+                full = full && edge_pass(edge_eval(s, k, cx, cy), s.nx[k], s.ny[k]);
+            }
+            // the same exact reject one level down: the eight 8x4 pixel blocks of the tile (one per warp of the tile
+            // kernel's pixel-parallel walks).  A tile none of whose blocks survives is not binned at all.
+            uint32_t blocks = full ? 0xFFu : 0u;
+#pragma unroll
+            for (uint32_t blk = 0; blk < 8 && !full; blk++) {
+                const uint32_t bx0 = max(X0, tx * TW + (blk & 1u) * BLOCK_W), bx1 = min(X1, tx * TW + (blk & 1u) * BLOCK_W + BLOCK_W);
+                const uint32_t by0 = max(Y0, ty * TH + (blk >> 1) * BLOCK_H), by1 = min(Y1, ty * TH + (blk >> 1) * BLOCK_H + BLOCK_H);
+                if (bx0 >= bx1 || by0 >= by1) continue;
+                const float bx_lo = fadd((float)bx0, o_lo), bx_hi = fadd((float)(bx1 - 1), o_hi);
+                const float by_lo = fadd((float)by0, o_lo), by_hi = fadd((float)(by1 - 1), o_hi);
+                bool kb = true;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const float cx = s.nx[k] >= 0.0f ? bx_hi : bx_lo;
+                    const float cy = s.ny[k] >= 0.0f ? by_hi : by_lo;
+                    kb = kb && edge_pass(edge_eval(s, k, cx, cy), s.nx[k], s.ny[k]);
+                }
+                blocks |= (kb ? 1u : 0u) << blk;
+            }
+            if (wild_bit) blocks = 0xFFu; // non-finite coordinates: the monotonicity argument needs finite values
+            if (blocks) push_bin(P, ty * P.tiles_x + tx, li.key, rec_tie, tile_box(b.x0, b.x1, b.y0, b.y1, tx, ty) | wild_bit | (blocks << ENTRY_BLOCKS_SHIFT));
         }
     }
 }

@@ -248,11 +248,20 @@ struct __align__(16) BigSetup {
     float inv;
     uint32_t key, rec;
     uint32_t box; // lx0 | ly0 << 8 | bw << 16 | bh << 24   (tile-local)
-    uint32_t tie; // tie-break bits of the three edges
+    uint32_t tie; // tie-break bits of the three edges | block mask << 8 (bin entry, rz_types.cuh)
 };
 static_assert(sizeof(BigSetup) == 80, "BigSetup must be 20 words");
 
 constexpr uint32_t FR_NONE = 0xFFFFu;
+
+// Pixel of a thread in the pixel-parallel phases: warp w owns the 8x4 pixel block w of the tile (block row w / 2, block
+// column w % 2), lane l the pixel (l % 8, l / 8) inside it.  Eight consecutive lanes are eight consecutive pixels of a
+// row: float4 sample records stay conflict-free and the epilogue's 128-bit row stores still collect four neighbours.
+__device__ __forceinline__ void pixel_of_thread(int &lx, int &ly) {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    lx = (w & 1) * BLOCK_W + (l & 7);
+    ly = (w >> 1) * BLOCK_H + (l >> 3);
+}
 
 // Asynchronous global -> shared copies (LDGSTS): no register staging, the issuing thread does not wait.
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
@@ -351,7 +360,7 @@ __device__ __forceinline__ bool sort_tile_list(SM &S, uint4 *bin, int n) {
 // the record (cp.async); otherwise it is read from global memory.
 template <bool FROM_TABLE, typename SM>
 __device__ __forceinline__ void stage_big(const FrameParams &P, SM &S, int cnt, uint32_t key, uint32_t rec_tie, int bx0, int by0,
-                                          int bw, int bh) {
+                                          int bw, int bh, uint32_t blocks) {
     if ((int)threadIdx.x < cnt) {
         BigSetup &b = S.u.big[threadIdx.x];
         const uint32_t rec = rec_tie & ENTRY_REC_MASK;
@@ -375,7 +384,7 @@ __device__ __forceinline__ void stage_big(const FrameParams &P, SM &S, int cnt, 
         b.z[0] = r1.z; b.z[1] = r1.w; b.z[2] = r2.x;
         b.inv = r2.y; b.key = key; b.rec = rec;
         b.box = (uint32_t)bx0 | ((uint32_t)by0 << 8) | ((uint32_t)bw << 16) | ((uint32_t)bh << 24);
-        b.tie = rec_tie >> 29;
+        b.tie = (rec_tie >> 29) | (blocks << 8); // tie-break bits of the three edges | 8x4 block mask << 8
     }
 }
 __device__ __forceinline__ void big_to_setup(const BigSetup &b, Setup &q) {
@@ -393,7 +402,10 @@ __device__ __forceinline__ void big_to_setup(const BigSetup &b, Setup &q) {
 // contain it.  The chunk's items are staged in S.u.big (stage_big) and S.it_key holds their order keys.
 template <bool DBG, bool EXT>
 __device__ __forceinline__ uint4 direct_chunk(const FrameParams &P, TileSmemT<DBG> &S, int cnt, bool sorted, int X, int Y) {
-    const int tid = threadIdx.x, lx = tid % TW, ly = tid / TW;
+    const int tid = threadIdx.x;
+    int lx, ly;
+    pixel_of_thread(lx, ly);
+    const int pix = ly * TW + lx; // this thread's slot in S.depth / S.color / S.okey
     uint32_t c_cov = 0, c_shaded = 0, c_samples = 0, c_oob = 0;
     const BigSetup *B = S.u.big;
     // the walk needs submission order: an unsorted chunk (it is the whole tile list then) is ranked by
@@ -408,17 +420,18 @@ __device__ __forceinline__ uint4 direct_chunk(const FrameParams &P, TileSmemT<DB
         S.unit_item[rank] = (uint8_t)tid; // the unit table is free in this path
     }
     __syncthreads();
-    float4 d = *reinterpret_cast<const float4 *>(&S.depth[tid * 4]);
+    float4 d = *reinterpret_cast<const float4 *>(&S.depth[pix * 4]);
     uint32_t own = 0xFFFFFFFFu; // 4 x u8: chunk item that owns sample k (0xFF: untouched in this chunk)
     uint32_t omp = 0u;          // 4 x 5 bits: that fragment's post-depth mask | (sample 0 covered) << 4
     for (int r = 0; r < cnt; r++) {
         const int it = (int)S.unit_item[r];
+        if (!((B[it].tie >> (8 + (tid >> 5))) & 1u)) continue; // the binner proved this warp's 8x4 block uncovered (warp-uniform)
         const uint32_t box = B[it].box;
         const uint32_t rx = (uint32_t)lx - (box & 0xFFu), ry = (uint32_t)ly - ((box >> 8) & 0xFFu);
         if (rx >= ((box >> 16) & 0xFFu) || ry >= (box >> 24)) continue; // outside the in-tile box
         Setup q;
         big_to_setup(B[it], q);
-        const uint32_t tie = B[it].tie;
+        const uint32_t tie = B[it].tie & 7u;
         float thr[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) thr[k] = ((tie >> k) & 1u) ? 0.0f : 1.401298464e-45f;
@@ -441,7 +454,7 @@ __device__ __forceinline__ uint4 direct_chunk(const FrameParams &P, TileSmemT<DB
                 omp = (omp & ~(0x1Fu << (5 * k))) | (tag << (5 * k));
             }
     }
-    *reinterpret_cast<float4 *>(&S.depth[tid * 4]) = d;
+    *reinterpret_cast<float4 *>(&S.depth[pix * 4]) = d;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const uint32_t it = (own >> (8 * k)) & 0xFFu;
@@ -458,8 +471,8 @@ __device__ __forceinline__ uint4 direct_chunk(const FrameParams &P, TileSmemT<DB
 #pragma unroll
         for (int j = k; j < 4; j++)
             if (((own >> (8 * j)) & 0xFFu) == it) {
-                S.color[tid * 4 + j] = argb;
-                if (DBG) S.okey[tid * 4 + j] = DBG ? S.it_okey[it] : 0u;
+                S.color[pix * 4 + j] = argb;
+                if (DBG) S.okey[pix * 4 + j] = DBG ? S.it_okey[it] : 0u;
             }
     }
     __syncthreads();
@@ -521,7 +534,10 @@ __device__ __forceinline__ void clear_empty_tiles(const FrameParams &P, int lane
 template <bool DBG, bool EXT>
 __device__ __forceinline__ bool fast_tile(const FrameParams &P, TileSmemT<DBG> &S, const uint4 *bin, int n, int X, int Y, uint32_t &c_cov,
                                           uint32_t &c_shaded, uint32_t &c_samples, uint32_t &c_oob) {
-    const int tid = threadIdx.x, lx = tid % TW, ly = tid / TW;
+    const int tid = threadIdx.x;
+    int lx, ly;
+    pixel_of_thread(lx, ly);
+    const int pix = ly * TW + lx; // this thread's slot in S.depth / S.color / S.okey
     static_assert(FAST_N <= 4, "the entries are ordered by a 4-element network");
     uint4 e[4];
     uint32_t anyw = 0;
@@ -542,6 +558,7 @@ __device__ __forceinline__ bool fast_tile(const FrameParams &P, TileSmemT<DBG> &
     for (int it = 0; it < 4; it++) {
         if (it >= n) break;
         const uint32_t boxw = e[it].z;
+        if (!((boxw >> (ENTRY_BLOCKS_SHIFT + (tid >> 5))) & 1u)) continue; // this warp's 8x4 block cannot be covered
         const uint32_t rx = (uint32_t)lx - (boxw & 15u), ry = (uint32_t)ly - ((boxw >> 4) & 15u);
         if (rx > ((boxw >> 8) & 15u) || ry > ((boxw >> 12) & 15u)) continue; // outside the in-tile box
         const float4 *rr = reinterpret_cast<const float4 *>(&P.recs[e[it].y & ENTRY_REC_MASK]);
@@ -574,7 +591,7 @@ __device__ __forceinline__ bool fast_tile(const FrameParams &P, TileSmemT<DBG> &
                 omp = (omp & ~(0x1Fu << (5 * k))) | (tag << (5 * k));
             }
     }
-    *reinterpret_cast<float4 *>(&S.depth[tid * 4]) = d;
+    *reinterpret_cast<float4 *>(&S.depth[pix * 4]) = d;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const uint32_t it = (own >> (8 * k)) & 0xFFu;
@@ -602,8 +619,8 @@ __device__ __forceinline__ bool fast_tile(const FrameParams &P, TileSmemT<DBG> &
 #pragma unroll
         for (int j = k; j < 4; j++)
             if (((own >> (8 * j)) & 0xFFu) == it) {
-                S.color[tid * 4 + j] = argb;
-                if (DBG) S.okey[tid * 4 + j] = ei.x;
+                S.color[pix * 4 + j] = argb;
+                if (DBG) S.okey[pix * 4 + j] = ei.x;
             }
     }
     return true;
@@ -616,7 +633,9 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : RZ_TILE_CTAS) tile_kernel(FrameP
     SM &S = *reinterpret_cast<SM *>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int lx = tid % TW, ly = tid / TW;
+    int lx, ly;
+    pixel_of_thread(lx, ly);
+    const int pix = ly * TW + lx; // this thread's pixel in the pixel-parallel walks and in the resolve
     uint32_t c_cov = 0, c_shaded = 0, c_samples = 0, c_oob = 0;
     pdl_launch();
     pdl_wait();
@@ -676,9 +695,9 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : RZ_TILE_CTAS) tile_kernel(FrameP
     // clear (the state resolve_and_clear leaves behind, rasterizer/mod.rs:497-506)
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        S.depth[tid * 4 + k] = CLEAR_DEPTH;
-        S.color[tid * 4 + k] = CLEAR_COLOR;
-        if (DBG) S.okey[tid * 4 + k] = NO_OWNER;
+        S.depth[pix * 4 + k] = CLEAR_DEPTH; // (its own pixel's slot: the barrier-free walk writes it without a barrier in between)
+        S.color[pix * 4 + k] = CLEAR_COLOR;
+        if (DBG) S.okey[pix * 4 + k] = NO_OWNER;
     }
 
     bool fast_done = false;
@@ -702,7 +721,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : RZ_TILE_CTAS) tile_kernel(FrameP
             // ---- load this window's entries (thread = item) ----
             const int item = pos + tid;
             const bool valid = tid < CHUNK && item < n;
-            uint32_t rec_tie = 0, key = 0;
+            uint32_t rec_tie = 0, key = 0, blocks = 0;
             int bx0 = 0, by0 = 0, bw = 0, bh = 0; // in-tile box, tile-local origin
             bool big = false;
             if (valid) {
@@ -717,6 +736,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : RZ_TILE_CTAS) tile_kernel(FrameP
                 }
                 bx0 = (int)(boxw & 15u); by0 = (int)((boxw >> 4) & 15u);
                 bw = (int)((boxw >> 8) & 15u) + 1; bh = (int)((boxw >> 12) & 15u) + 1;
+                blocks = (boxw >> ENTRY_BLOCKS_SHIFT) & 0xFFu;
                 big = wild && (boxw & ENTRY_WILD) != 0u; // NaN / inf / absurd coordinates: literal per-pixel path
                 if (DBG) S.it_okey[tid] = compact ? P.recs[rec_tie & ENTRY_REC_MASK].key : key;
             }
@@ -746,15 +766,15 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : RZ_TILE_CTAS) tile_kernel(FrameP
                 // ================= run of items for the literal walk: pixel-parallel =================
                 const int run = min(first_small, nvalid);
                 const BigSetup *B = S.u.big;
-                stage_big<false>(P, S, run, key, rec_tie, bx0, by0, bw, bh);
+                stage_big<false>(P, S, run, key, rec_tie, bx0, by0, bw, bh, blocks);
                 __syncthreads();
                 float d[4];
                 uint32_t col[4], ok[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    d[k] = S.depth[tid * 4 + k];
-                    col[k] = S.color[tid * 4 + k];
-                    if (DBG) ok[k] = S.okey[tid * 4 + k];
+                    d[k] = S.depth[pix * 4 + k];
+                    col[k] = S.color[pix * 4 + k];
+                    if (DBG) ok[k] = S.okey[pix * 4 + k];
                 }
                 for (int it = 0; it < run; it++) {
                     const uint32_t box = B[it].box;
@@ -786,9 +806,9 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : RZ_TILE_CTAS) tile_kernel(FrameP
                 }
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    S.depth[tid * 4 + k] = d[k];
-                    S.color[tid * 4 + k] = col[k];
-                    if (DBG) S.okey[tid * 4 + k] = ok[k];
+                    S.depth[pix * 4 + k] = d[k];
+                    S.color[pix * 4 + k] = col[k];
+                    if (DBG) S.okey[pix * 4 + k] = ok[k];
                 }
                 __syncthreads();
                 pos += run;
@@ -845,7 +865,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : RZ_TILE_CTAS) tile_kernel(FrameP
             cp_async_wait_all();
             __syncthreads();
             if (go_direct) {
-                stage_big<true>(P, S, cnt, key, rec_tie, bx0, by0, bw, bh);
+                stage_big<true>(P, S, cnt, key, rec_tie, bx0, by0, bw, bh, blocks);
                 const uint4 dc = direct_chunk<DBG, EXT>(P, S, cnt, sorted, X, Y); // (starts with a barrier)
                 c_cov += dc.x; c_shaded += dc.y; c_samples += dc.z; c_oob += dc.w;
                 pos += cnt;
@@ -1139,19 +1159,19 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : RZ_TILE_CTAS) tile_kernel(FrameP
     uint4 ent_next = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) ent_next = load_entry(atomicAdd(&P.fs->tile_cursor, 1u)); // issued here, consumed at the end of the trip
     // ---- resolve (ColorBuffer::box_filter_color, buffers.rs:111-125) and write back ----
-    const uint32_t res = box_filter(S.color[tid * 4], S.color[tid * 4 + 1], S.color[tid * 4 + 2], S.color[tid * 4 + 3]);
+    const uint32_t res = box_filter(S.color[pix * 4], S.color[pix * 4 + 1], S.color[pix * 4 + 2], S.color[pix * 4 + 3]);
     if (DBG && X < (int)P.W && Y < (int)P.H) {
         const size_t o = ((size_t)Y * P.W + X) * 4;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            if (P.dbg_depth) P.dbg_depth[o + k] = S.depth[tid * 4 + k];
-            if (P.dbg_color) P.dbg_color[o + k] = S.color[tid * 4 + k];
-            if (P.dbg_owner) P.dbg_owner[o + k] = S.okey[tid * 4 + k];
+            if (P.dbg_depth) P.dbg_depth[o + k] = S.depth[pix * 4 + k];
+            if (P.dbg_color) P.dbg_color[o + k] = S.color[pix * 4 + k];
+            if (P.dbg_owner) P.dbg_owner[o + k] = S.okey[pix * 4 + k];
         }
     }
     if ((P.W & 3u) == 0u) {
         // 128-bit row stores without staging: lane L (L % 4 == 0) collects the pixels of lanes L..L+3, which are
-        // four consecutive pixels of one tile row (lane = pixel index mod 32, 16 pixels per row)
+        // four consecutive pixels of one row of the warp's 8x4 block (pixel_of_thread)
         const uint32_t r1 = __shfl_down_sync(0xffffffffu, res, 1), r2 = __shfl_down_sync(0xffffffffu, res, 2),
                        r3 = __shfl_down_sync(0xffffffffu, res, 3);
         if ((lane & 3) == 0 && X < (int)P.W && Y < (int)P.H)

@@ -42,7 +42,10 @@ constexpr float GEOM_THIN_AREA2 = RZ_GEOM_THIN_AREA2; // 2x screen area below wh
 #define RZ_VERTEX_PER_THREAD 1 // 1, 2 and 4 measured on one box: 41.0 / 42.0 / 42.8 us for the C2 geometry stage
 #endif
 constexpr int VERTEX_PER_THREAD = RZ_VERTEX_PER_THREAD; // vertices per thread of the vertex stage
-constexpr int LARGE_SLAB_ROWS = 8;  // tile rows per large-triangle binning work item
+#ifndef RZ_LARGE_SLAB_ROWS
+#define RZ_LARGE_SLAB_ROWS 8
+#endif
+constexpr int LARGE_SLAB_ROWS = RZ_LARGE_SLAB_ROWS; // tile rows per large-triangle binning work item
 constexpr int MAX_POLY = 10;        // clipped polygon vertex budget (=> <= 8 fan triangles, 3 key bits)
 
 constexpr uint32_t CLEAR_COLOR = 0xFF191919u;    // rasterizer/buffers.rs:5
@@ -119,10 +122,17 @@ struct __align__(16) ShadeRec {
 //   y = record index (29 bits) | tie-break bits of the three edges << 29  (EdgeFunctions::inside, mod.rs:160-168:
 //       bit k set <=> a sample exactly on edge k counts as inside, i.e. n.x > 0 || (n.x == 0 && n.y < 0))
 //   z = in-tile pixel box: lx0 | ly0 << 4 | (bw - 1) << 8 | (bh - 1) << 12, bit 16 = non-finite / absurd coordinates
-//       (literal per-pixel walk)
+//       (literal per-pixel walk), bits 17..24 = block mask: bit b set <=> the triangle may cover a sample of the 8x4
+//       pixel block b of the tile (b = block row * 2 + block column; exact corner reject by the large-triangle binner,
+//       0xFF from the small-triangle path).  The pixel-parallel walks give one block to each warp and skip the rest.
 //   w = unused
 constexpr uint32_t ENTRY_REC_MASK = 0x1FFFFFFFu;
 constexpr uint32_t ENTRY_WILD = 1u << 16;
+constexpr int ENTRY_BLOCKS_SHIFT = 17; // 8-bit block mask
+#ifndef RZ_SLIVER_FRAC
+#define RZ_SLIVER_FRAC 0.25f // a large triangle whose 2x area is below this fraction of its bounding box area gets exact block masks
+#endif
+constexpr int BLOCK_W = 8, BLOCK_H = 4;  // pixel block of one warp in the pixel-parallel phases (2 x 4 blocks per tile)
 // Per-tile bin: `off` = first entry in FrameParams::bins, `cap` = entries the tile may hold (planned on the host from the
 // counts of the last frame that overflowed: memory is O(total entries), a single hot tile no longer sizes every bin)
 struct TileBin {
