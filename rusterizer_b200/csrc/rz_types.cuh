@@ -21,7 +21,7 @@ constexpr int UNIT_CAP = RZ_UNIT_CAP; // (item, pixel) work units per chunk (one
 #endif
 constexpr int POOL = RZ_POOL;       // per-chunk fragment records held in shared memory
 #ifndef RZ_DIRECT_MIN_AREA
-#define RZ_DIRECT_MIN_AREA 192
+#define RZ_DIRECT_MIN_AREA 96
 #endif
 constexpr int DIRECT_MIN_AREA = RZ_DIRECT_MIN_AREA; // average in-tile bbox (pixels) from which a chunk is walked pixel-parallel
 #ifndef RZ_FAST_N
