@@ -12,8 +12,8 @@ def find(pat, start=0):
     for i in range(start, len(src)):
         if pat in src[i]: return i + 1
     raise KeyError(pat)
-k0 = find("__global__ void __launch_bounds__(NT, DBG ? 3 : 4) tile_kernel")
-marks = [("prologue", k0), ("tile top / steal", find("for (;;) {", k0)), ("sort + entry load (A0 head)", find("if (n > 0) {", k0)),
+k0 = find(") tile_kernel(FrameParams P) {")
+marks = [("prologue", k0), ("tile top / steal", find("for (;;) {", k0)), ("sort + entry load (A0 head)", find("if (n > 0 && !fast_done) {", k0)),
          ("wild walk", find("run of items for the literal walk", k0)), ("A0 table + scan", find("chunk of small items", k0)),
          ("direct/budget", find("chunk dominated by large items: pixel-parallel, deferred", k0)),
          ("A1 coverage+depth", find("phase A1: thread = (item", k0)), ("A1 tail/retry", find("S.nfrag keeps counting past the pool", k0)), ("A2 depths", find("phase A2: thread = fragment", k0)),
@@ -23,7 +23,7 @@ helpers = [("shade()", find("__device__ __forceinline__ uint32_t shade("), k0)]
 def phase_of(line):
     if line < k0:
         return "fn:" + ("sort" if find("block_sort(T *a")-2 <= line < find("struct __align__(16) BigSetup") or find("sort_tile_list(SM &S") <= line < find("Stage the records of") else
-                        "shade/texture" if line < find("Bitonic network") else "direct_chunk/stage" if line < find("Tiles nothing was binned into") else "clear_empty")
+                        "shade/texture" if line < find("Bitonic network") else "direct_chunk/stage" if line < find("Tiles nothing was binned into") else "clear_empty" if line < find("Tiles whose whole list has at most FAST_N items") else "fast_tile")
     cur = marks[0][0]
     for name, l in marks:
         if line >= l: cur = name

@@ -26,12 +26,12 @@ for name, mk in CONFIGS:
     r.uniforms().bind_texture(0, sc.texture)
     dms = [r.upload(d.mesh) for d in sc.draws]
     ts = []
-    for i in range(8):
-        if i == 3: r.reset_counters()
+    for i in range(25):  # 10 warm-up frames (the first config also ramps the clocks), median of the next 15
+        if i == 10: r.reset_counters()
         scenes.render_scene(r, sc, dms); r.framebuffer_device()
         ts.append(r.timings())
-    t = {k: float(np.median([x[k] for x in ts[3:]])) for k in ts[0]}
-    c = {k: v / 5 for k, v in r.counters().items()}
+    t = {k: float(np.median([x[k] for x in ts[10:]])) for k in ts[0]}
+    c = {k: v / 15 for k, v in r.counters().items()}
     print(json.dumps({"config": name, "tris": sc.n_triangles, "ms": t, "Mtris_per_s": sc.n_triangles / t["total_ms"] / 1e3,
                       "Gsamples_per_s": c["n_samples_written"] / t["total_ms"] / 1e6,
                       "clipped_in": c["n_clipped_in"], "samples_written": c["n_samples_written"], "bbox_px": c["n_bbox_px"],
