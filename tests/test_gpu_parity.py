@@ -623,3 +623,14 @@ def test_guard_band_clipping(guard):
         msgs = compare(o, gpu_render(s, debug=True))
         assert not msgs, f"{s.name} g={guard}: " + "; ".join(msgs)
         assert o["counters"]["n_clipped_in"] <= base
+
+
+def test_fuzz_campaign_slice():
+    """Sixty frames of the fuzz campaign (tests/fuzz_parity.py: random resolutions, soups, grids, huge triangles,
+    shaders, sample counts, guard bands, scissor rects); profiles/r02_fuzz.txt records a 300 s run of the same."""
+    import fuzz_parity
+
+    for seed in range(9000, 9060):
+        s = fuzz_parity.make_case(seed)
+        msgs = compare(oracle_render(s), gpu_render(s, debug=True, device_resident=bool(seed & 1)))
+        assert not msgs, f"seed {seed}: " + "; ".join(msgs)
