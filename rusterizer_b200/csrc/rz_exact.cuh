@@ -19,6 +19,19 @@ namespace rz {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256) of one aligned 32-byte sector, as two float4 halves.
+// Plain (coherent) accesses: usable on buffers an earlier kernel of the PDL chain wrote.
+__device__ __forceinline__ void ld_sector(const float4 *p, float4 &a, float4 &b) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+__device__ __forceinline__ void st_sector(float4 *p, const float4 a, const float4 b) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x),
+                 "f"(b.y), "f"(b.z), "f"(b.w)
+                 : "memory");
+}
+
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }

@@ -310,15 +310,16 @@ __global__ void __launch_bounds__(NT) vertex_kernel(FrameParams P, DrawParams D,
 #pragma unroll
         for (int r = 0; r < 4; r++)
             c[r] = dot4z(D.M[4 * r], D.M[4 * r + 1], D.M[4 * r + 2], D.M[4 * r + 3], x[k], y[k], z[k], 1.0f);
-        D.vtx[2 * (size_t)v] = project_vertex(c, (float)P.W, (float)P.H);
-        D.vtx[2 * (size_t)v + 1] = make_float4(c[0], c[1], c[2], __uint_as_float(clip_code(c, P.guard)));
+        st_sector(D.vtx + 2 * (size_t)v, project_vertex(c, (float)P.W, (float)P.H),
+                  make_float4(c[0], c[1], c[2], __uint_as_float(clip_code(c, P.guard))));
     }
 }
 
 // Stage 1b/2 -- primitive assembly, clip, setup, binning: one thread per input triangle
 // (render.rs:75-96, rasterizer/mod.rs:425-441).
 #ifndef RZ_GEOM_MIN_CTAS
-#define RZ_GEOM_MIN_CTAS 5 // 48 registers: 40 resident warps per SM (the kernel is latency bound)
+#define RZ_GEOM_MIN_CTAS 4 // 64 registers, nothing spilled: 32 resident warps per SM.  (5 CTAs = 48 registers spill 128 bytes per
+                           // thread and cost 3-4 us on the C2 frame, 16 us on the overdraw frame; 3 CTAs are no faster than 4.)
 #endif
 __global__ void __launch_bounds__(NT, RZ_GEOM_MIN_CTAS) geom_kernel(FrameParams P, DrawParams D) {
     __shared__ uint32_t s_part[NT / 32][C_COUNT];
@@ -361,9 +362,11 @@ __global__ void __launch_bounds__(NT, RZ_GEOM_MIN_CTAS) geom_kernel(FrameParams 
             // Everything a triangle may need from its three vertices is requested up front, so the
             // independent gathers overlap instead of paying one L2 round trip per decision.
             // (written by this draw's vertex kernel, the preceding launch: plain loads, not the read-only path)
-            const float4 sv0 = D.vtx[2 * (size_t)i0], cq0 = D.vtx[2 * (size_t)i0 + 1];
-            const float4 sv1 = D.vtx[2 * (size_t)i1], cq1 = D.vtx[2 * (size_t)i1 + 1];
-            const float4 sv2 = D.vtx[2 * (size_t)i2], cq2 = D.vtx[2 * (size_t)i2 + 1];
+            // one 256-bit load per vertex (sm_100 LDG.256: the record is one aligned 32-byte sector)
+            float4 sv0, cq0, sv1, cq1, sv2, cq2;
+            ld_sector(D.vtx + 2 * (size_t)i0, sv0, cq0);
+            ld_sector(D.vtx + 2 * (size_t)i1, sv1, cq1);
+            ld_sector(D.vtx + 2 * (size_t)i2, sv2, cq2);
             const float2 q0 = make_float2(cq0.x, cq0.y), q1 = make_float2(cq1.x, cq1.y), q2 = make_float2(cq2.x, cq2.y);
             const uint32_t code = __float_as_uint(cq0.w) & __float_as_uint(cq1.w) & __float_as_uint(cq2.w);
             // clipping::try_clip (rasterizer/clipping.rs:62-195): degenerate test on clip-space xy first
