@@ -630,7 +630,15 @@ static int enqueue_frame(rz_ctx *c, uint32_t *out_base, bool timed) {
     const uint32_t n16 = (uint32_t)((zeroed_state_bytes(c) - off + 15) / 16);
     uint4 *zero16 = reinterpret_cast<uint4 *>(c->d_state + off);
     bool zeroed = false; // the first vertex kernel of the frame zeroes the frame state; frames without one do it here
-    if (total_tris == 0) {
+    // ... and so do frames whose first vertex kernel is too small a grid for the job (a quad on an 8192 x 8192 target:
+    // one CTA would zero 262144 tile counters by itself)
+    uint32_t first_vertex_threads = 0;
+    for (auto &d : c->draws)
+        if (d.mesh->n_idx / 3 > 0) {
+            first_vertex_threads = std::max(1u, (d.mesh->nv + NT * VERTEX_PER_THREAD - 1) / (NT * VERTEX_PER_THREAD)) * NT;
+            break;
+        }
+    if (total_tris == 0 || n16 > 16u * first_vertex_threads) {
         CU(c, launch_pdl(frame_begin_kernel, dim3((n16 + NT - 1) / NT), dim3(NT), 0, st, zero16, n16));
         c->launches++;
         zeroed = true;

@@ -535,53 +535,76 @@ __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
         }
         const uint32_t tx0 = b.x0 / TW, tx1 = (b.x1 - 1) / TW + 1, ntx = tx1 - tx0;
         const uint32_t total = ntx * (li.ty1 - li.ty0);
-        for (uint32_t t = lane; t < total; t += 32) {
+        // bounds of the sample positions: the 4-sample rotated grid spans [1/8, 7/8] of a pixel, the other patterns
+        // are simply bounded by the pixel itself
+        const float o_lo = P.msaa == 4u ? 0.125f : 0.0f, o_hi = P.msaa == 4u ? 0.875f : 1.0f;
+        for (uint32_t t0 = 0; t0 < total; t0 += 32) { // (warp-uniform trip count: the block tests below are warp collectives)
+            const uint32_t t = t0 + lane;
             const uint32_t tx = tx0 + t % ntx, ty = li.ty0 + t / ntx;
             const uint32_t X0 = max(b.x0, tx * TW), X1 = min(b.x1, tx * TW + TW);
             const uint32_t Y0 = max(b.y0, ty * TH), Y1 = min(b.y1, ty * TH + TH);
-            if (X0 >= X1 || Y0 >= Y1 || !owns_tile_row(P, ty)) continue;
-            // bounds of the sample positions: the 4-sample rotated grid spans [1/8, 7/8] of a pixel, the other patterns
-            // are simply bounded by the pixel itself
-            const float o_lo = P.msaa == 4u ? 0.125f : 0.0f, o_hi = P.msaa == 4u ? 0.875f : 1.0f;
-            const float sx_lo = fadd((float)X0, o_lo), sx_hi = fadd((float)(X1 - 1), o_hi);
-            const float sy_lo = fadd((float)Y0, o_lo), sy_hi = fadd((float)(Y1 - 1), o_hi);
-            bool keep = true;
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const float cx = s.nx[k] >= 0.0f ? sx_hi : sx_lo;
-                const float cy = s.ny[k] >= 0.0f ? sy_hi : sy_lo;
-                keep = keep && edge_pass(edge_eval(s, k, cx, cy), s.nx[k], s.ny[k]);
-            }
-            if (!keep) continue;
-            // a tile every sample of which is inside (all three edges pass at their LEAST favourable corner; monotone
-            // again) needs no block tests: the interior tiles of a large triangle
+            bool keep = t < total && X0 < X1 && Y0 < Y1 && owns_tile_row(P, ty);
             bool full = true; // fat triangles: every block of a touched tile may be covered
-#pragma unroll
-            for (int k = 0; k < 3 && sliver; k++) {
-                const float cx = s.nx[k] >= 0.0f ? sx_lo : sx_hi;
-                const float cy = s.ny[k] >= 0.0f ? sy_lo : sy_hi;
-                full = full && edge_pass(edge_eval(s, k, cx, cy), s.nx[k], s.ny[k]);
-            }
-            // the same exact reject one level down: the eight 8x4 pixel blocks of the tile (one per warp of the tile
-            // kernel's pixel-parallel walks).  A tile none of whose blocks survives is not binned at all.
-            uint32_t blocks = full ? 0xFFu : 0u;
-#pragma unroll
-            for (uint32_t blk = 0; blk < 8 && !full; blk++) {
-                const uint32_t bx0 = max(X0, tx * TW + (blk & 1u) * BLOCK_W), bx1 = min(X1, tx * TW + (blk & 1u) * BLOCK_W + BLOCK_W);
-                const uint32_t by0 = max(Y0, ty * TH + (blk >> 1) * BLOCK_H), by1 = min(Y1, ty * TH + (blk >> 1) * BLOCK_H + BLOCK_H);
-                if (bx0 >= bx1 || by0 >= by1) continue;
-                const float bx_lo = fadd((float)bx0, o_lo), bx_hi = fadd((float)(bx1 - 1), o_hi);
-                const float by_lo = fadd((float)by0, o_lo), by_hi = fadd((float)(by1 - 1), o_hi);
-                bool kb = true;
+            if (keep) {
+                const float sx_lo = fadd((float)X0, o_lo), sx_hi = fadd((float)(X1 - 1), o_hi);
+                const float sy_lo = fadd((float)Y0, o_lo), sy_hi = fadd((float)(Y1 - 1), o_hi);
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
-                    const float cx = s.nx[k] >= 0.0f ? bx_hi : bx_lo;
-                    const float cy = s.ny[k] >= 0.0f ? by_hi : by_lo;
-                    kb = kb && edge_pass(edge_eval(s, k, cx, cy), s.nx[k], s.ny[k]);
+                    const float cx = s.nx[k] >= 0.0f ? sx_hi : sx_lo;
+                    const float cy = s.ny[k] >= 0.0f ? sy_hi : sy_lo;
+                    keep = keep && edge_pass(edge_eval(s, k, cx, cy), s.nx[k], s.ny[k]);
                 }
-                blocks |= (kb ? 1u : 0u) << blk;
+                // a tile every sample of which is inside (all three edges pass at their LEAST favourable corner; monotone
+                // again) needs no block tests: the interior tiles of a large triangle
+#pragma unroll
+                for (int k = 0; k < 3 && sliver && keep; k++) {
+                    const float cx = s.nx[k] >= 0.0f ? sx_lo : sx_hi;
+                    const float cy = s.ny[k] >= 0.0f ? sy_lo : sy_hi;
+                    full = full && edge_pass(edge_eval(s, k, cx, cy), s.nx[k], s.ny[k]);
+                }
             }
-            if (wild_bit) blocks = 0xFFu; // non-finite coordinates: the monotonicity argument needs finite values
+            // the same exact reject one level down: the eight 8x4 pixel blocks of the tile (one per warp of the tile
+            // kernel's pixel-parallel walks).  A tile none of whose blocks survives is not binned at all.  The tiles of
+            // this trip that need the test are handled four at a time, lane = (tile slot, block): a sliver's item has a
+            // dozen tiles, so a lane per tile would leave most of the warp idle during the 24 edge evaluations.
+            // (non-finite coordinates: every block, the monotonicity argument needs finite values)
+            const bool need = keep && !full && !wild_bit;
+            uint32_t blocks = keep ? 0xFFu : 0u;
+            unsigned need_mask = __ballot_sync(0xffffffffu, need);
+            while (need_mask) {
+                const int slot = lane >> 3;
+                const uint32_t blk = (uint32_t)lane & 7u;
+                unsigned m = need_mask; // the slot-th set bit of need_mask: the lane whose tile this lane helps with
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+                    if (i < slot) m &= m - 1u;
+                const bool act = m != 0u;
+                const int src = act ? __ffs(m) - 1 : 0;
+                const uint32_t stx = __shfl_sync(0xffffffffu, tx, src), sty = __shfl_sync(0xffffffffu, ty, src);
+                bool kb = false;
+                if (act) {
+                    const uint32_t SX0 = max(b.x0, stx * TW), SX1 = min(b.x1, stx * TW + TW);
+                    const uint32_t SY0 = max(b.y0, sty * TH), SY1 = min(b.y1, sty * TH + TH);
+                    const uint32_t bx0 = max(SX0, stx * TW + (blk & 1u) * BLOCK_W), bx1 = min(SX1, stx * TW + (blk & 1u) * BLOCK_W + BLOCK_W);
+                    const uint32_t by0 = max(SY0, sty * TH + (blk >> 1) * BLOCK_H), by1 = min(SY1, sty * TH + (blk >> 1) * BLOCK_H + BLOCK_H);
+                    if (bx0 < bx1 && by0 < by1) {
+                        const float bx_lo = fadd((float)bx0, o_lo), bx_hi = fadd((float)(bx1 - 1), o_hi);
+                        const float by_lo = fadd((float)by0, o_lo), by_hi = fadd((float)(by1 - 1), o_hi);
+                        kb = true;
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            const float cx = s.nx[k] >= 0.0f ? bx_hi : bx_lo;
+                            const float cy = s.ny[k] >= 0.0f ? by_hi : by_lo;
+                            kb = kb && edge_pass(edge_eval(s, k, cx, cy), s.nx[k], s.ny[k]);
+                        }
+                    }
+                }
+                const unsigned res = __ballot_sync(0xffffffffu, kb);
+                const int rank = __popc(need_mask & lanemask_lt());
+                if (((need_mask >> lane) & 1u) && rank < 4) blocks = (res >> (8 * rank)) & 0xFFu;
+#pragma unroll
+                for (int i = 0; i < 4; i++) need_mask &= need_mask - 1u; // (x & (x - 1) of 0 is 0)
+            }
             if (blocks) push_bin(P, ty * P.tiles_x + tx, li.key, rec_tie, tile_box(b.x0, b.x1, b.y0, b.y1, tx, ty) | wild_bit | (blocks << ENTRY_BLOCKS_SHIFT));
         }
     }
