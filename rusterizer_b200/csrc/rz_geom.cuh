@@ -194,16 +194,23 @@ __device__ __forceinline__ void emit_setup(const FrameParams &P, const DrawParam
                 push_bin(P, ty * P.tiles_x + tx, key, rec_tie, tile_box(b.x0, b.x1, b.y0, b.y1, tx, ty) | wild_bit);
             }
     } else {
+        // one queue item per slab of LARGE_SLAB_ROWS tile rows; the slots of all slabs are reserved with ONE atomic (a
+        // full-screen triangle on an 8192-row target has 64 slabs: a round trip per slab kept its thread busy for 50 us)
         const uint32_t tyB = (b.y1 - 1) / TH + 1;
-        for (uint32_t ty = ty0; ty < tyB; ty += LARGE_SLAB_ROWS) {
-            uint32_t li = atomicAdd(&P.fs->n_large, 1u);
-            if (li < P.large_cap) {
-                LargeItem it;
-                it.rec = rec; it.key = key; it.ty0 = ty; it.ty1 = min(ty + (uint32_t)LARGE_SLAB_ROWS, tyB);
-                P.large[li] = it;
-            } else {
-                atomicOr(&P.fs->err, ERR_LARGE_OVF);
-            }
+        const uint32_t n_slabs = (tyB - ty0 + LARGE_SLAB_ROWS - 1) / LARGE_SLAB_ROWS;
+        // (the lanes of the warp that arrive here with the same slab count share the atomic)
+        uint32_t li0 = 0;
+        {
+            const unsigned peers = __match_any_sync(__activemask(), n_slabs);
+            const int leader = __ffs(peers) - 1;
+            if ((int)(threadIdx.x & 31) == leader) li0 = atomicAdd(&P.fs->n_large, (uint32_t)__popc(peers) * n_slabs);
+            li0 = __shfl_sync(peers, li0, leader) + (uint32_t)__popc(peers & lanemask_lt()) * n_slabs;
+        }
+        if (li0 + n_slabs > P.large_cap) atomicOr(&P.fs->err, ERR_LARGE_OVF); // (the frame is replayed with a larger queue)
+        for (uint32_t k = 0; k < n_slabs && li0 + k < P.large_cap; k++) {
+            LargeItem it;
+            it.rec = rec; it.key = key; it.ty0 = ty0 + k * LARGE_SLAB_ROWS; it.ty1 = min(it.ty0 + (uint32_t)LARGE_SLAB_ROWS, tyB);
+            P.large[li0 + k] = it;
         }
     }
 }
