@@ -194,23 +194,28 @@ __device__ __forceinline__ void emit_setup(const FrameParams &P, const DrawParam
                 push_bin(P, ty * P.tiles_x + tx, key, rec_tie, tile_box(b.x0, b.x1, b.y0, b.y1, tx, ty) | wild_bit);
             }
     } else {
-        // one queue item per slab of LARGE_SLAB_ROWS tile rows; the slots of all slabs are reserved with ONE atomic (a
-        // full-screen triangle on an 8192-row target has 64 slabs: a round trip per slab kept its thread busy for 50 us)
-        const uint32_t tyB = (b.y1 - 1) / TH + 1;
+        // one queue item per slab of LARGE_SLAB_ROWS tile rows x LARGE_CHUNK_COLS tile columns; the slots of all of them are
+        // reserved with ONE atomic (a full-screen triangle on an 8192-row target has 64 slabs: a round trip per slab
+        // kept its thread busy for 50 us)
+        const uint32_t tyB = (b.y1 - 1) / TH + 1, txB = (b.x1 - 1) / TW + 1;
         const uint32_t n_slabs = (tyB - ty0 + LARGE_SLAB_ROWS - 1) / LARGE_SLAB_ROWS;
-        // (the lanes of the warp that arrive here with the same slab count share the atomic)
+        const uint32_t n_chunks = (txB - tx0 + LARGE_CHUNK_COLS - 1) / LARGE_CHUNK_COLS;
+        const uint32_t n_items = n_slabs * n_chunks;
+        // (the lanes of the warp that arrive here with the same item count share the atomic)
         uint32_t li0 = 0;
         {
-            const unsigned peers = __match_any_sync(__activemask(), n_slabs);
+            const unsigned peers = __match_any_sync(__activemask(), n_items);
             const int leader = __ffs(peers) - 1;
-            if ((int)(threadIdx.x & 31) == leader) li0 = atomicAdd(&P.fs->n_large, (uint32_t)__popc(peers) * n_slabs);
-            li0 = __shfl_sync(peers, li0, leader) + (uint32_t)__popc(peers & lanemask_lt()) * n_slabs;
+            if ((int)(threadIdx.x & 31) == leader) li0 = atomicAdd(&P.fs->n_large, (uint32_t)__popc(peers) * n_items);
+            li0 = __shfl_sync(peers, li0, leader) + (uint32_t)__popc(peers & lanemask_lt()) * n_items;
         }
-        if (li0 + n_slabs > P.large_cap) atomicOr(&P.fs->err, ERR_LARGE_OVF); // (the frame is replayed with a larger queue)
-        for (uint32_t k = 0; k < n_slabs && li0 + k < P.large_cap; k++) {
-            LargeItem it;
-            it.rec = rec; it.key = key; it.ty0 = ty0 + k * LARGE_SLAB_ROWS; it.ty1 = min(it.ty0 + (uint32_t)LARGE_SLAB_ROWS, tyB);
-            P.large[li0 + k] = it;
+        if (li0 + n_items > P.large_cap) atomicOr(&P.fs->err, ERR_LARGE_OVF); // (the frame is replayed with a larger queue)
+        uint4 *q = reinterpret_cast<uint4 *>(P.large + li0); // {rec, key, rows, cols}
+        uint32_t room = li0 < P.large_cap ? P.large_cap - li0 : 0u;
+        for (uint32_t sy = ty0; sy < tyB; sy += LARGE_SLAB_ROWS) {
+            const uint32_t rows = sy | (min(sy + (uint32_t)LARGE_SLAB_ROWS, tyB) << 16);
+            for (uint32_t sx = tx0; sx < txB && room; sx += LARGE_CHUNK_COLS, room--)
+                *q++ = make_uint4(rec, key, rows, sx | (min(sx + (uint32_t)LARGE_CHUNK_COLS, txB) << 16));
         }
     }
 }
@@ -540,14 +545,14 @@ __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
             const float bh_f = fmaxf(fmaxf(s.py[0], s.py[1]), s.py[2]) - fminf(fminf(s.py[0], s.py[1]), s.py[2]);
             sliver = a2 < RZ_SLIVER_FRAC * bw_f * bh_f; // area2 / 2 against a fraction of the bounding box area
         }
-        const uint32_t tx0 = b.x0 / TW, tx1 = (b.x1 - 1) / TW + 1, ntx = tx1 - tx0;
-        const uint32_t total = ntx * (li.ty1 - li.ty0);
+        const uint32_t tx0 = li.cols & 0xFFFFu, ntx = (li.cols >> 16) - tx0, li_ty0 = li.rows & 0xFFFFu;
+        const uint32_t total = ntx * ((li.rows >> 16) - li_ty0);
         // bounds of the sample positions: the 4-sample rotated grid spans [1/8, 7/8] of a pixel, the other patterns
         // are simply bounded by the pixel itself
         const float o_lo = P.msaa == 4u ? 0.125f : 0.0f, o_hi = P.msaa == 4u ? 0.875f : 1.0f;
         for (uint32_t t0 = 0; t0 < total; t0 += 32) { // (warp-uniform trip count: the block tests below are warp collectives)
             const uint32_t t = t0 + lane;
-            const uint32_t tx = tx0 + t % ntx, ty = li.ty0 + t / ntx;
+            const uint32_t tx = tx0 + t % ntx, ty = li_ty0 + t / ntx;
             const uint32_t X0 = max(b.x0, tx * TW), X1 = min(b.x1, tx * TW + TW);
             const uint32_t Y0 = max(b.y0, ty * TH), Y1 = min(b.y1, ty * TH + TH);
             bool keep = t < total && X0 < X1 && Y0 < Y1 && owns_tile_row(P, ty);

@@ -46,6 +46,10 @@ constexpr int VERTEX_PER_THREAD = RZ_VERTEX_PER_THREAD; // vertices per thread o
 #define RZ_LARGE_SLAB_ROWS 8
 #endif
 constexpr int LARGE_SLAB_ROWS = RZ_LARGE_SLAB_ROWS; // tile rows per large-triangle binning work item
+#ifndef RZ_LARGE_CHUNK_COLS
+#define RZ_LARGE_CHUNK_COLS 64
+#endif
+constexpr int LARGE_CHUNK_COLS = RZ_LARGE_CHUNK_COLS; // ... and tile columns: a screen-sized triangle becomes many items, one warp each
 constexpr int MAX_POLY = 10;        // clipped polygon vertex budget (=> <= 8 fan triangles, 3 key bits)
 
 constexpr uint32_t CLEAR_COLOR = 0xFF191919u;    // rasterizer/buffers.rs:5
@@ -156,7 +160,9 @@ struct DrawInfo {
 
 // Large-triangle binning work item
 struct __align__(16) LargeItem {
-    uint32_t rec, key, ty0, ty1; // tile rows [ty0, ty1)
+    uint32_t rec, key;
+    uint32_t rows; // tile rows [ty0, ty1):    ty0 | ty1 << 16   (a framebuffer has at most 4096 tiles per axis)
+    uint32_t cols; // tile columns [tx0, tx1): tx0 | tx1 << 16
 };
 
 struct TexInfo {
