@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(NT, 2) msaa_tile_kernel(FrameParams P) {
                     xs = fadd((float)X, MSAA_PAT[pb + i][0]);
                     ys = fadd((float)Y, MSAA_PAT[pb + i][1]);
                 }
-                const uint32_t argb = shade_at<true, true>(P, q, B.rec, S.lut, xs, ys, zs[0], c_oob);
+                const uint32_t argb = shade_at<true, true>(P, q, B.rec, S.lut, xs, ys, [&]() { return zs[0]; }, c_oob);
 #pragma unroll
                 for (int i = 0; i < NS; i++)
                     if ((mp >> i) & 1u) { // write_pixel (mod.rs:380-397)

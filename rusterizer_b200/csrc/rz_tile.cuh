@@ -136,13 +136,18 @@ __device__ __forceinline__ uint32_t pack_argb(const float *o) {
 // the hottest loop of the frame; frames that do not use it run the lean instantiation).
 // shade_at: the same at an explicit sample position (xs, ys) -- the caller applies the position rule of
 // Fragment::interpolate (mod.rs:70-83) for its sample pattern.
-template <bool ALPHA, bool EXT>
+// `depth0` is a callable: only the depth-visualising shader reads FragCoords.depths[0], and the pixel-parallel walks
+// would have to evaluate it (one more sample depth per fragment) just to throw it away.
+template <bool ALPHA, bool EXT, typename D0>
 __device__ __forceinline__ uint32_t shade_at(const FrameParams &P, const Setup &s, uint32_t rec, const float *lut, float xs,
-                                             float ys, float depth0, uint32_t &oob) {
+                                             float ys, D0 depth0, uint32_t &oob) {
     // (records are written by the geometry kernels of this frame: plain loads, not the read-only path)
     const uint4 sh = *reinterpret_cast<const uint4 *>(&P.shade[rec]);
     const uint32_t info = sh.x, fs = info & 3u, texidx = EXT ? (info >> 3) & 31u : 0u;
-    if (fs == 2u) return to_argb(depth0, depth0, depth0, 1.0f); // Color::grayscale(depths[0])
+    if (fs == 2u) { // Color::grayscale(depths[0])
+        const float g = depth0();
+        return to_argb(g, g, g, 1.0f);
+    }
     const float4 wq = reinterpret_cast<const float4 *>(&P.shade[rec])[1]; // depths_camera_space (same sector)
     const bool clipped = (info & 4u) != 0u;
     const float *a0, *a1, *a2;
@@ -190,9 +195,9 @@ __device__ __forceinline__ uint32_t shade_at(const FrameParams &P, const Setup &
 
 // 4-sample form: the position rule of Fragment::interpolate (mod.rs:70-83) for the rotated-grid pattern -- the pixel
 // centre when all four samples passed the depth test, else the first passing sample.
-template <bool ALPHA, bool EXT>
+template <bool ALPHA, bool EXT, typename D0>
 __device__ __forceinline__ uint32_t shade(const FrameParams &P, const Setup &s, uint32_t rec, const float *lut, int X,
-                                          int Y, uint32_t mpost, float depth0, uint32_t &oob) {
+                                          int Y, uint32_t mpost, D0 depth0, uint32_t &oob) {
     float xs, ys;
     if (mpost == 0xFu) {
         xs = fadd((float)X, 0.5f);
@@ -466,7 +471,7 @@ __device__ __forceinline__ uint4 direct_chunk(const FrameParams &P, TileSmemT<DB
         const uint32_t tag = (omp >> (5 * k)) & 0x1Fu;
         Setup q;
         big_to_setup(B[it], q);
-        const float depth0 = (tag & 16u) ? sample_depth(q, X, Y, 0) : 0.0f; // FragCoords.depths[0] (mod.rs:458-463)
+        const auto depth0 = [&]() { return (tag & 16u) ? sample_depth(q, X, Y, 0) : 0.0f; }; // FragCoords.depths[0] (mod.rs:458-463)
         const uint32_t argb = shade<DBG, EXT>(P, q, B[it].rec, S.lut, X, Y, tag & 0xFu, depth0, c_oob);
 #pragma unroll
         for (int j = k; j < 4; j++)
@@ -608,13 +613,14 @@ __device__ __forceinline__ bool fast_tile(const FrameParams &P, TileSmemT<DBG> &
         Setup q;
         q.px[0] = r0.x; q.py[0] = r0.y; q.px[1] = r0.z; q.py[1] = r0.w; q.px[2] = r1.x; q.py[2] = r1.y;
         setup_normals(q);
-        float depth0 = 0.0f; // FragCoords.depths[0] (mod.rs:458-463)
-        if (tag & 16u) {
+        const auto depth0 = [&]() { // FragCoords.depths[0] (mod.rs:458-463)
+            if (!(tag & 16u)) return 0.0f;
             const float4 r2 = rr[2];
-            q.z[0] = r1.z; q.z[1] = r1.w; q.z[2] = r2.x;
-            q.inv = r2.y;
-            depth0 = sample_depth(q, X, Y, 0);
-        }
+            Setup qd = q;
+            qd.z[0] = r1.z; qd.z[1] = r1.w; qd.z[2] = r2.x;
+            qd.inv = r2.y;
+            return sample_depth(qd, X, Y, 0);
+        };
         const uint32_t argb = shade<DBG, EXT>(P, q, rec, S.lut, X, Y, tag & 0xFu, depth0, c_oob);
 #pragma unroll
         for (int j = k; j < 4; j++)
@@ -795,7 +801,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : RZ_TILE_CTAS) tile_kernel(FrameP
                     if (!mp) continue;
                     c_shaded++;
                     c_samples += __popc(mp);
-                    const uint32_t argb = shade<true, EXT>(P, q, B[it].rec, S.lut, X, Y, mp, zs[0], c_oob);
+                    const uint32_t argb = shade<true, EXT>(P, q, B[it].rec, S.lut, X, Y, mp, [&]() { return zs[0]; }, c_oob);
 #pragma unroll
                     for (int k = 0; k < 4; k++)
                         if ((mp >> k) & 1u) {
@@ -1139,9 +1145,8 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : RZ_TILE_CTAS) tile_kernel(FrameP
                     q.px[0] = r0.x; q.py[0] = r0.y; q.px[1] = r0.z; q.py[1] = r0.w; q.px[2] = r1.x; q.py[2] = r1.y;
                     setup_normals(q);
                 }
-                const float depth0 = S.u.fr.z[f].x;
                 const uint32_t argb = shade<DBG, EXT>(P, q, rec, S.lut, tileX0 + (int)(p % TW), tileY0 + (int)(p / TW),
-                                            fin & 0xFu, depth0, c_oob);
+                                            fin & 0xFu, [&]() { return S.u.fr.z[f].x; }, c_oob);
 #pragma unroll
                 for (int k = 0; k < 4; k++)
                     if ((vis >> k) & 1u) {
