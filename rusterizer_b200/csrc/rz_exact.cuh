@@ -173,6 +173,29 @@ __device__ __forceinline__ float sample_depth(const Setup &s, int X, int Y, int 
     return fadd(fadd(fmul(b0, s.z[0]), fmul(b1, s.z[1])), fmul(b2, s.z[2]));
 }
 
+// Coverage and depth test of a pixel's four samples against one triangle, for the pixel-parallel walks (finite
+// coordinates).  d holds the four depths of the pixel (strict <, rasterizer/mod.rs:374); returns the coverage mask, mp
+// receives the post-depth-test mask.  `full`: the binner proved every sample of the item's box inside (ENTRY_FULL), the
+// coverage test is skipped.  Two separate code paths on purpose: in the general one the compiler shares the edge values
+// between coverage_mask_fast and sample_depth, and a merged form loses that.
+__device__ __forceinline__ uint32_t cover_depth4(const Setup &s, const float *thr, bool full, int X, int Y, float4 &d, uint32_t &mp) {
+    mp = 0u;
+    if (full) {
+        const float z0 = sample_depth(s, X, Y, 0), z1 = sample_depth(s, X, Y, 1), z2 = sample_depth(s, X, Y, 2), z3 = sample_depth(s, X, Y, 3);
+        if (z0 < d.x) { d.x = z0; mp |= 1u; }
+        if (z1 < d.y) { d.y = z1; mp |= 2u; }
+        if (z2 < d.z) { d.z = z2; mp |= 4u; }
+        if (z3 < d.w) { d.w = z3; mp |= 8u; }
+        return 0xFu;
+    }
+    const uint32_t m = coverage_mask_fast(s, thr, X, Y);
+    if (m & 1u) { const float z = sample_depth(s, X, Y, 0); if (z < d.x) { d.x = z; mp |= 1u; } }
+    if (m & 2u) { const float z = sample_depth(s, X, Y, 1); if (z < d.y) { d.y = z; mp |= 2u; } }
+    if (m & 4u) { const float z = sample_depth(s, X, Y, 2); if (z < d.z) { d.z = z; mp |= 4u; } }
+    if (m & 8u) { const float z = sample_depth(s, X, Y, 3); if (z < d.w) { d.w = z; mp |= 8u; } }
+    return m;
+}
+
 // PixelBoundingBox::from + Rasterizer::bounding_box (bounding_box.rs:13-42, mod.rs:347-361),
 // clamped to the viewport.  Half-open pixel ranges; empty when min >= max.
 struct BBox {

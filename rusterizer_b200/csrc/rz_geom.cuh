@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
             const uint32_t X0 = max(b.x0, tx * TW), X1 = min(b.x1, tx * TW + TW);
             const uint32_t Y0 = max(b.y0, ty * TH), Y1 = min(b.y1, ty * TH + TH);
             bool keep = t < total && X0 < X1 && Y0 < Y1 && owns_tile_row(P, ty);
-            bool full = true; // fat triangles: every block of a touched tile may be covered
+            bool full = true;
             if (keep) {
                 const float sx_lo = fadd((float)X0, o_lo), sx_hi = fadd((float)(X1 - 1), o_hi);
                 const float sy_lo = fadd((float)Y0, o_lo), sy_hi = fadd((float)(Y1 - 1), o_hi);
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
                 // a tile every sample of which is inside (all three edges pass at their LEAST favourable corner; monotone
                 // again) needs no block tests: the interior tiles of a large triangle
 #pragma unroll
-                for (int k = 0; k < 3 && sliver && keep; k++) {
+                for (int k = 0; k < 3 && keep; k++) {
                     const float cx = s.nx[k] >= 0.0f ? sx_lo : sx_hi;
                     const float cy = s.ny[k] >= 0.0f ? sy_lo : sy_hi;
                     full = full && edge_pass(edge_eval(s, k, cx, cy), s.nx[k], s.ny[k]);
@@ -580,7 +580,8 @@ __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
             // this trip that need the test are handled four at a time, lane = (tile slot, block): a sliver's item has a
             // dozen tiles, so a lane per tile would leave most of the warp idle during the 24 edge evaluations.
             // (non-finite coordinates: every block, the monotonicity argument needs finite values)
-            const bool need = keep && !full && !wild_bit;
+            // (fat triangles: every block of a touched tile may be covered, no block tests)
+            const bool need = keep && !full && sliver && !wild_bit;
             uint32_t blocks = keep ? 0xFFu : 0u;
             unsigned need_mask = __ballot_sync(0xffffffffu, need);
             while (need_mask) {
@@ -617,7 +618,8 @@ __global__ void __launch_bounds__(NT) large_bin_kernel(FrameParams P) {
 #pragma unroll
                 for (int i = 0; i < 4; i++) need_mask &= need_mask - 1u; // (x & (x - 1) of 0 is 0)
             }
-            if (blocks) push_bin(P, ty * P.tiles_x + tx, li.key, rec_tie, tile_box(b.x0, b.x1, b.y0, b.y1, tx, ty) | wild_bit | (blocks << ENTRY_BLOCKS_SHIFT));
+            if (blocks) push_bin(P, ty * P.tiles_x + tx, li.key, rec_tie, tile_box(b.x0, b.x1, b.y0, b.y1, tx, ty) | wild_bit | (blocks << ENTRY_BLOCKS_SHIFT) |
+                                      ((full && !wild_bit) ? ENTRY_FULL : 0u));
         }
     }
 }

@@ -440,6 +440,7 @@ __device__ __forceinline__ uint4 direct_chunk(const FrameParams &P, TileSmemT<DB
         float thr[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) thr[k] = ((tie >> k) & 1u) ? 0.0f : 1.401298464e-45f;
+        // (ENTRY_FULL is not used here: a second code path in this loop costs the general one 5 % -- measured on the C3 frame)
         const uint32_t m = coverage_mask_fast(q, thr, X, Y);
         if (!m) continue;
         c_cov++;
@@ -574,17 +575,13 @@ __device__ __forceinline__ bool fast_tile(const FrameParams &P, TileSmemT<DBG> &
         float thr[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) thr[k] = ((e[it].y >> (29 + k)) & 1u) ? 0.0f : 1.401298464e-45f;
-        const uint32_t m = coverage_mask_fast(q, thr, X, Y);
-        if (!m) continue;
-        c_cov++;
         const float4 r2 = rr[2];
         q.z[0] = r1.z; q.z[1] = r1.w; q.z[2] = r2.x;
         q.inv = r2.y;
-        uint32_t mp = 0;
-        if (m & 1u) { const float z = sample_depth(q, X, Y, 0); if (z < d.x) { d.x = z; mp |= 1u; } } // strict < (mod.rs:374)
-        if (m & 2u) { const float z = sample_depth(q, X, Y, 1); if (z < d.y) { d.y = z; mp |= 2u; } }
-        if (m & 4u) { const float z = sample_depth(q, X, Y, 2); if (z < d.z) { d.z = z; mp |= 4u; } }
-        if (m & 8u) { const float z = sample_depth(q, X, Y, 3); if (z < d.w) { d.w = z; mp |= 8u; } }
+        uint32_t mp;
+        const uint32_t m = cover_depth4(q, thr, (boxw & ENTRY_FULL) != 0u, X, Y, d, mp); // (uniform across the CTA)
+        if (!m) continue;
+        c_cov++;
         if (!mp) continue;
         c_shaded++;
         c_samples += __popc(mp);

@@ -133,6 +133,8 @@ struct __align__(16) ShadeRec {
 constexpr uint32_t ENTRY_REC_MASK = 0x1FFFFFFFu;
 constexpr uint32_t ENTRY_WILD = 1u << 16;
 constexpr int ENTRY_BLOCKS_SHIFT = 17; // 8-bit block mask
+constexpr uint32_t ENTRY_FULL = 1u << 25; // every sample of the in-tile box is inside the triangle (proved by the binner at the
+                                          // least favourable corner of each edge): the short-list walk (fast_tile) skips the coverage test
 #ifndef RZ_SLIVER_FRAC
 #define RZ_SLIVER_FRAC 0.25f // a large triangle whose 2x area is below this fraction of its bounding box area gets exact block masks
 #endif
