@@ -180,9 +180,11 @@ __device__ __forceinline__ void emit_setup(const FrameParams &P, const DrawParam
     rr[0] = make_float4(s.px[0], s.py[0], s.px[1], s.py[1]);
     rr[1] = make_float4(s.px[2], s.py[2], s.z[0], s.z[1]);
     rr[2] = make_float4(s.z[2], inv, __uint_as_float(key), 0.0f);
-    uint4 *sr = reinterpret_cast<uint4 *>(&P.shade[rec]);
-    sr[0] = make_uint4((D.fs & 3u) | (ca ? 4u : 0u) | (((D.fs >> 8) & 31u) << 3) | (D.draw << 8), ca ? clip_attr : i0, i1, i2);
-    sr[1] = make_uint4(__float_as_uint(s.w[0]), __float_as_uint(s.w[1]), __float_as_uint(s.w[2]), 0u);
+    // (the 32-byte shade record leaves in one 256-bit store)
+    st_sector(reinterpret_cast<float4 *>(&P.shade[rec]),
+              make_float4(__uint_as_float((D.fs & 3u) | (ca ? 4u : 0u) | (((D.fs >> 8) & 31u) << 3) | (D.draw << 8)),
+                          __uint_as_float(ca ? clip_attr : i0), __uint_as_float(i1), __uint_as_float(i2)),
+              make_float4(s.w[0], s.w[1], s.w[2], 0.0f));
     const uint32_t rec_tie = rec | (tie_bits(s) << 29);
     const uint32_t wild_bit = (tame ? 0u : ENTRY_WILD) | (0xFFu << ENTRY_BLOCKS_SHIFT); // small triangles: every block may be covered
 

@@ -142,13 +142,14 @@ template <bool ALPHA, bool EXT, typename D0>
 __device__ __forceinline__ uint32_t shade_at(const FrameParams &P, const Setup &s, uint32_t rec, const float *lut, float xs,
                                              float ys, D0 depth0, uint32_t &oob) {
     // (records are written by the geometry kernels of this frame: plain loads, not the read-only path)
-    const uint4 sh = *reinterpret_cast<const uint4 *>(&P.shade[rec]);
+    float4 shf, wq; // the whole 32-byte record in one 256-bit load; wq = depths_camera_space
+    ld_sector(reinterpret_cast<const float4 *>(&P.shade[rec]), shf, wq);
+    const uint4 sh = make_uint4(__float_as_uint(shf.x), __float_as_uint(shf.y), __float_as_uint(shf.z), __float_as_uint(shf.w));
     const uint32_t info = sh.x, fs = info & 3u, texidx = EXT ? (info >> 3) & 31u : 0u;
     if (fs == 2u) { // Color::grayscale(depths[0])
         const float g = depth0();
         return to_argb(g, g, g, 1.0f);
     }
-    const float4 wq = reinterpret_cast<const float4 *>(&P.shade[rec])[1]; // depths_camera_space (same sector)
     const bool clipped = (info & 4u) != 0u;
     const float *a0, *a1, *a2;
     if (clipped) { // interpolated attributes live in an AttrRec (written by clip_kernel in this frame)
