@@ -25,7 +25,11 @@ cases = [base, clip, sph,
                                     scenes.Draw(sph.draws[0].mesh, mathx.translate(1.0, -0.5, 1.0), scenes.fs_with_texture(scenes.FS_TEXTURE_BLEND, 1)),
                                     scenes.Draw(scenes.centered_quad(9.0), mathx.translate(0.0, 0.0, 3.0), scenes.FS_DEBUG)],
                       base.texture, [t1], scissor=(5, 3, 150, 90)),
-         scenes.overdraw_scene(nx=40, ny=20, width=W, height=H)]
+         scenes.overdraw_scene(nx=40, ny=20, width=W, height=H),
+         # wide target: the clipped quad's queue items split into column chunks and several slabs, interior tiles carry
+         # ENTRY_FULL, and the frame's tile counters are zeroed by the dedicated kernel (tiny first vertex grid)
+         scenes.fullscreen_quad_scene(1408, 272),
+         scenes.near_clip_scene(40, 12, 640, 208)]
 for sc in cases:
     for dbg in (True, False):
         msgs = compare(oracle_render(sc), gpu_render(sc, debug=dbg), check_samples=dbg)
