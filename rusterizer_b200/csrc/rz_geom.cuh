@@ -449,6 +449,12 @@ __global__ void __launch_bounds__(NT) clip_kernel(FrameParams P) {
         bool ovf = false;
         // Sutherland-Hodgman against LEFT,RIGHT,BOTTOM,TOP,NEAR,FAR (clipping.rs:118-171)
         for (int plane = 0; plane < 6; plane++) {
+            {   // a plane every vertex is inside of leaves the polygon as it is (the loop below would copy each vertex,
+                // in order, through local memory): most clipped triangles cross one plane of the six
+                bool all_in = true;
+                for (int i = 0; i < n_out; i++) all_in = all_in && clip_distance(plane, pv[cur][i], P.guard) >= 0.0f;
+                if (all_in) continue;
+            }
             const int n_in = n_out, in = cur, out = cur ^ 1;
             n_out = 0;
             for (int i = 0; i < n_in; i++) {
