@@ -822,7 +822,10 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : RZ_TILE_CTAS) tile_kernel(FrameP
             // ================= chunk of small items =================
             int cnt = sorted ? min(first_big, nvalid) : nvalid;
             // ---- phase A0: item table + exclusive scan of the in-tile box areas ----
-            const uint32_t area = (tid < cnt) ? (uint32_t)(bw * bh) : 0u;
+            // work units of phase A1 = horizontal pixel PAIRS of the in-tile box (the two pixels share the y terms of
+            // the twelve edge evaluations and the unit's decoding); a box of odd width ends its rows with a half-used pair
+            const int pw = (bw + 1) >> 1;
+            const uint32_t area = (tid < cnt) ? (uint32_t)(pw * bh) : 0u;
             if (tid < cnt) {
                 // the record travels to shared memory on its own while the scan below runs (waited for at the barrier
                 // that ends phase A0)
@@ -831,7 +834,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : RZ_TILE_CTAS) tile_kernel(FrameP
                 cp_async16(&S.it_q1[tid], rp + 16);
                 cp_async8(&S.it_q2[tid], rp + 32);
                 S.it_key[tid] = key; S.it_rec[tid] = rec_tie;
-                S.it_box[tid] = (uint32_t)bx0 | ((uint32_t)by0 << 4) | ((uint32_t)bw << 8) | (((65536u + (uint32_t)bw - 1u) / (uint32_t)bw) << 13);
+                S.it_box[tid] = (uint32_t)bx0 | ((uint32_t)by0 << 4) | ((uint32_t)bw << 8) | (((65536u + (uint32_t)pw - 1u) / (uint32_t)pw) << 13);
             }
             uint32_t incl = area;
 #pragma unroll
@@ -858,7 +861,7 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : RZ_TILE_CTAS) tile_kernel(FrameP
             // submission order (exact coverage, sample depths, strict-< depth test: the literal sequence of
             // rasterizer/mod.rs:443-473), remembers per sample which item wrote it last together with that fragment's
             // post-depth mask, and shades each surviving owner once at the end.  No fragment pool, no unit table.
-            const bool go_direct = DIRECT && cnt > 0 && total_units >= (uint32_t)DIRECT_MIN_AREA * (uint32_t)cnt;
+            const bool go_direct = DIRECT && cnt > 0 && 2u * total_units >= (uint32_t)DIRECT_MIN_AREA * (uint32_t)cnt; // (units are pixel pairs)
             {
                 const uint32_t first = wbase + incl - area; // exclusive prefix: first work unit of item <tid>
                 S.pre[tid] = first;
@@ -906,14 +909,15 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : RZ_TILE_CTAS) tile_kernel(FrameP
                 uint32_t cov_try = 0;
                 for (int u0 = 0; u0 < units; u0 += NT) {
                     const int u = u0 + tid;
-                    uint32_t m = 0, p = 0, it = 0;
+                    uint32_t m0 = 0, m1 = 0, p = 0, it = 0; // coverage of the pair's two pixels p, p + 1
                     if (u < units) {
                         it = S.unit_item[u];
                         const uint32_t box = S.it_box[it];
-                        const int ibw = (int)((box >> 8) & 0x1Fu);
+                        const int ibw = (int)((box >> 8) & 0x1Fu), ipw = (ibw + 1) >> 1;
                         const int j = u - (int)S.pre[it];
-                        const int ry = (int)(((uint32_t)j * (box >> 13)) >> 16), rx = j - ry * ibw; // j / ibw, j < 256, ibw <= 16
+                        const int ry = (int)(((uint32_t)j * (box >> 13)) >> 16), rx = 2 * (j - ry * ipw); // j / ipw, j < 256, ipw <= 8
                         const int lpx = (int)(box & 0xFu) + rx, lpy = (int)((box >> 4) & 0xFu) + ry;
+                        const bool second = rx + 1 < ibw; // (false: the row's last, half-used pair)
                         p = (uint32_t)(lpy * TW + lpx);
                         const uint32_t rec_t = S.it_rec[it];
                         const float4 r0 = S.it_q0[it], r1 = S.it_q1[it];
@@ -924,26 +928,47 @@ __global__ void __launch_bounds__(NT, DBG ? 3 : RZ_TILE_CTAS) tile_kernel(FrameP
                         const float t0 = (rec_t & (1u << 29)) ? 0.0f : 1.401298464e-45f;
                         const float t1 = (rec_t & (1u << 30)) ? 0.0f : 1.401298464e-45f;
                         const float t2 = (rec_t & (1u << 31)) ? 0.0f : 1.401298464e-45f;
-                        const float fx = (float)(tileX0 + lpx), fy = (float)(tileY0 + lpy);
+                        const float fx = (float)(tileX0 + lpx), fx1 = (float)(tileX0 + lpx + 1), fy = (float)(tileY0 + lpy);
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
-                            const float xs = fadd(fx, rgss_x(i)), ys = fadd(fy, rgss_y(i));
-                            const float e0 = fadd(fmul(n0x, fsub(xs, r0.x)), fmul(n0y, fsub(ys, r0.y)));
-                            const float e1 = fadd(fmul(n1x, fsub(xs, r0.z)), fmul(n1y, fsub(ys, r0.w)));
-                            const float e2 = fadd(fmul(n2x, fsub(xs, r1.x)), fmul(n2y, fsub(ys, r1.y)));
-                            m |= ((e0 >= t0) & (e1 >= t1) & (e2 >= t2)) ? (1u << i) : 0u;
+                            const float xs = fadd(fx, rgss_x(i)), xs1 = fadd(fx1, rgss_x(i)), ys = fadd(fy, rgss_y(i));
+                            const float y0 = fmul(n0y, fsub(ys, r0.y)), y1 = fmul(n1y, fsub(ys, r0.w)), y2 = fmul(n2y, fsub(ys, r1.y));
+                            {
+                                const float e0 = fadd(fmul(n0x, fsub(xs, r0.x)), y0);
+                                const float e1 = fadd(fmul(n1x, fsub(xs, r0.z)), y1);
+                                const float e2 = fadd(fmul(n2x, fsub(xs, r1.x)), y2);
+                                m0 |= ((e0 >= t0) & (e1 >= t1) & (e2 >= t2)) ? (1u << i) : 0u;
+                            }
+                            {
+                                const float e0 = fadd(fmul(n0x, fsub(xs1, r0.x)), y0);
+                                const float e1 = fadd(fmul(n1x, fsub(xs1, r0.z)), y1);
+                                const float e2 = fadd(fmul(n2x, fsub(xs1, r1.x)), y2);
+                                m1 |= ((e0 >= t0) & (e1 >= t1) & (e2 >= t2)) ? (1u << i) : 0u;
+                            }
                         }
+                        if (!second) m1 = 0u;
                     }
-                    const uint32_t bal = __ballot_sync(0xffffffffu, m != 0u);
-                    if (bal) { // warp-aggregated fragment allocation (ballot + popc prefix)
+                    const uint32_t bal0 = __ballot_sync(0xffffffffu, m0 != 0u), bal1 = __ballot_sync(0xffffffffu, m1 != 0u);
+                    if (bal0 | bal1) { // warp-aggregated fragment allocation (ballots + popc prefix): first pixels, then second pixels
                         uint32_t slot = 0;
-                        if (lane == 0) slot = atomicAdd(&S.nfrag, (uint32_t)__popc(bal));
-                        slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(bal & lanemask_lt());
-                        if (m) {
+                        if (lane == 0) slot = atomicAdd(&S.nfrag, (uint32_t)(__popc(bal0) + __popc(bal1)));
+                        slot = __shfl_sync(0xffffffffu, slot, 0);
+                        if (m0) {
+                            const uint32_t s0 = slot + __popc(bal0 & lanemask_lt());
                             cov_try++;
-                            if (slot < POOL) {
-                                S.u.fr.meta[slot] = it | (p << 8) | (m << 16);
-                                S.u.fr.next[slot] = (uint16_t)atomicExch(&S.head[p], slot);
+                            if (s0 < POOL) {
+                                S.u.fr.meta[s0] = it | (p << 8) | (m0 << 16);
+                                S.u.fr.next[s0] = (uint16_t)atomicExch(&S.head[p], s0);
+                            } else {
+                                S.ovf = 1u;
+                            }
+                        }
+                        if (m1) {
+                            const uint32_t s1 = slot + __popc(bal0) + __popc(bal1 & lanemask_lt());
+                            cov_try++;
+                            if (s1 < POOL) {
+                                S.u.fr.meta[s1] = it | ((p + 1u) << 8) | (m1 << 16);
+                                S.u.fr.next[s1] = (uint16_t)atomicExch(&S.head[p + 1u], s1);
                             } else {
                                 S.ovf = 1u;
                             }
