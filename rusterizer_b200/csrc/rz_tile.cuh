@@ -16,9 +16,9 @@
 // are shaded, and they write colour + depth of exactly the samples in v(F).  Nothing in a chunk
 // depends on the order in which threads run, so a tile whose list fits one chunk is never sorted.
 //   phase A0 thread = item          bin entry (order key, record index, in-tile pixel box) -> scan of the box areas
-//   phase A1 thread = (item, pixel) exact coverage; covered units compute their sample depths from the same edge
-//                                   values (as RasterizerTriangle::fragment does, mod.rs:225-253) and become fragment
-//                                   records on per-pixel lists
+//   phase A1 thread = (item, pixel pair) exact coverage of two horizontally adjacent box pixels (shared y terms);
+//                                   covered pixels become fragment records on per-pixel lists
+//   phase A2 thread = fragment      the covered samples' depths (RasterizerTriangle::fragment, mod.rs:225-253)
 //   phase B  thread = pixel         m(F), v(F): the pixel's few fragments replayed in key order (lists of up to
 //                                   four fragments are ordered and replayed in registers)
 //   phase C  thread = fragment      interpolate + fragment shader + pack; write the visible samples
